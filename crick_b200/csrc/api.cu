@@ -1,0 +1,680 @@
+// crick_b200/csrc/api.cu -- the C ABI of libcrick_cuda.so (include/crick_cuda.h):
+// library plumbing, TDigest handles, grouped digests.  Host code only; every
+// numeric result comes from the kernels in tdigest_kernels.cu / tdigest_parallel.cu.
+#include "../../include/crick_cuda.h"
+#include "api_common.h"
+#include "tdigest_ref.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace crick {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int fail(const char* what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_err = buf;
+    return -1;
+}
+int fail_msg(const char* what) {
+    g_err = what;
+    return -1;
+}
+
+static int g_sm_count = 0;
+int sm_count() {
+    if (g_sm_count) return g_sm_count;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    // keep freed stream-ordered allocations cached: staging buffers are reused every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_sm_count = n;
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// device storage for `nd` digests of one compression
+int store_alloc(DigestStore& s, double compression, long nd) {
+    if (compression < 20) compression = 20;          // tdigest_stubs.c:57-62
+    else if (compression > 1000) compression = 1000;
+    s.v.comp = compression;
+    s.v.cap = 2 * (int)std::ceil(compression);       // :65
+    s.v.bufcap = (int)(7.5 + 0.37 * compression - 2e-4 * compression * compression);  // :66
+    s.nd = nd;
+    size_t hb = ((size_t)nd * sizeof(DevHdr) + 255) & ~(size_t)255;
+    size_t cb = (size_t)nd * s.v.cap * sizeof(double2);
+    size_t bb = (((size_t)nd * s.v.bufcap * sizeof(double2)) + 255) & ~(size_t)255;
+    s.bytes = hb + 2 * cb + bb;
+    cudaError_t e = cudaMalloc(&s.base, s.bytes);
+    if (e != cudaSuccess) { s.base = nullptr; return fail("cudaMalloc(digest store)", e); }
+    unsigned char* p = reinterpret_cast<unsigned char*>(s.base);
+    s.v.hdr = reinterpret_cast<DevHdr*>(p); p += hb;
+    s.v.cen = reinterpret_cast<double2*>(p); p += cb;
+    s.v.table = reinterpret_cast<double2*>(p); p += cb;
+    s.v.buf = reinterpret_cast<double2*>(p);
+    return 0;
+}
+void store_free(DigestStore& s) {
+    if (s.base) cudaFree(s.base);
+    s.base = nullptr;
+}
+
+}  // namespace crick
+
+using namespace crick;
+
+// ---------------------------------------------------------------------------
+struct crick_tdigest {
+    DigestStore s;
+    cudaStream_t own = nullptr;      // the handle's stream
+    cudaStream_t last = nullptr;     // stream of the most recent enqueued op
+    cudaEvent_t ev = nullptr;
+    std::vector<double> px, pw;      // pending scalar adds (tdigest_add), in order
+    DevHdr mirror;                   // host copy of the header
+    bool mirror_ok = false;
+    void* scratch = nullptr;         // parallel-mode scratch (lazy)
+    size_t scratch_bytes = 0;
+};
+
+static cudaStream_t td_stream(crick_tdigest* t, void* stream) {
+    // Chain work across streams: if this op runs on a different stream than the previous
+    // one, make it wait for everything enqueued so far.
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : t->own;
+    if (t->last && t->last != st) {
+        cudaEventRecord(t->ev, t->last);
+        cudaStreamWaitEvent(st, t->ev, 0);
+    }
+    t->last = st;
+    return st;
+}
+
+static int td_drain(crick_tdigest* t, cudaStream_t st) {
+    size_t n = t->px.size();
+    if (!n) return 0;
+    double* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, 2 * n * sizeof(double), st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(pending)", e);
+    e = cudaMemcpyAsync(d, t->px.data(), n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d + n, t->pw.data(), n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = launch_ingest(t->s.v, 1, d, d + n, 0.0, 1, 1, nullptr, (long)n, 0, nullptr, 0, st);
+    // pageable source: the copies above have consumed the host vectors when they return
+    cudaFreeAsync(d, st);
+    t->px.clear();
+    t->pw.clear();
+    t->mirror_ok = false;
+    if (e != cudaSuccess) return fail("drain pending adds", e);
+    return 0;
+}
+
+static int td_sync_mirror(crick_tdigest* t) {
+    cudaStream_t st = td_stream(t, nullptr);
+    if (td_drain(t, st)) return -1;
+    if (t->mirror_ok) return 0;
+    cudaError_t e = cudaMemcpyAsync(&t->mirror, t->s.v.hdr, sizeof(DevHdr), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("read digest header", e);
+    t->mirror_ok = true;
+    return 0;
+}
+
+static int td_scratch(crick_tdigest* t) {
+    if (t->scratch) return 0;
+    size_t b = parallel_scratch_bytes(t->s.v.comp, sm_count());
+    cudaError_t e = cudaMalloc(&t->scratch, b);
+    if (e != cudaSuccess) { t->scratch = nullptr; return fail("cudaMalloc(parallel scratch)", e); }
+    t->scratch_bytes = b;
+    return 0;
+}
+
+extern "C" {
+
+// ---- library ---------------------------------------------------------------
+const char* crick_last_error(void) { return g_err.c_str(); }
+const char* crick_version(void) { return "crick_b200 0.1.0 (sm_100a)"; }
+int crick_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int crick_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail("cudaSetDevice", e);
+    g_sm_count = 0;
+    return 0;
+}
+int crick_sm_count(void) { return sm_count(); }
+int64_t crick_launch_count(void) { return (int64_t)g_launches.load(); }
+void* crick_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { fail("cudaHostAlloc", e); return nullptr; }
+    return p;
+}
+void crick_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* crick_device_alloc(int64_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)(bytes > 0 ? bytes : 1));
+    if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
+    return p;
+}
+void crick_device_free(void* p) { if (p) cudaFree(p); }
+int crick_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice,
+                                    reinterpret_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess && !stream) e = cudaStreamSynchronize(nullptr);
+    return e == cudaSuccess ? 0 : fail("memcpy h2d", e);
+}
+int crick_memcpy_d2h(void* dst, const void* src, int64_t bytes, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? 0 : fail("memcpy d2h", e);
+}
+int crick_stream_synchronize(void* stream) {
+    cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail("cudaStreamSynchronize", e);
+}
+int crick_device_synchronize(void) {
+    cudaError_t e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? 0 : fail("cudaDeviceSynchronize", e);
+}
+int crick_synth_fill(double* x, double* w, int64_t n, uint64_t seed, int64_t offset, int kind,
+                     void* stream) {
+    cudaError_t e = launch_synth(x, w, n, seed, offset, kind, reinterpret_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail("synth", e);
+}
+
+// ---- TDigest ---------------------------------------------------------------
+crick_tdigest_t* crick_tdigest_new(double compression) {
+    if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
+    crick_tdigest* t = new (std::nothrow) crick_tdigest();
+    if (!t) return nullptr;
+    if (store_alloc(t->s, compression, 1)) { delete t; return nullptr; }
+    cudaError_t e = cudaStreamCreateWithFlags(&t->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = launch_init_hdr(t->s.v.hdr, 1, t->own);
+    if (e != cudaSuccess) { fail("tdigest_new", e); crick_tdigest_free(t); return nullptr; }
+    t->last = t->own;
+    return t;
+}
+
+void crick_tdigest_free(crick_tdigest_t* t) {
+    if (!t) return;
+    if (t->last) cudaStreamSynchronize(t->last);
+    if (t->own) { cudaStreamSynchronize(t->own); cudaStreamDestroy(t->own); }
+    if (t->ev) cudaEventDestroy(t->ev);
+    if (t->scratch) cudaFree(t->scratch);
+    store_free(t->s);
+    delete t;
+}
+
+int crick_tdigest_add(crick_tdigest_t* t, double x, double w) {
+    t->px.push_back(x);
+    t->pw.push_back(w);
+    if (t->px.size() >= (1u << 16)) return td_drain(t, td_stream(t, nullptr));
+    return 0;
+}
+
+// host-resident input, parallel mode: same sample positions as the device sampler, then
+// double-buffered chunks (copy of chunk k+1 overlaps the accumulate of chunk k)
+static int td_update_host_parallel(crick_tdigest* t, const double* x, const double* w, double wsc,
+                                   int64_t n, cudaStream_t st) {
+    if (td_scratch(t)) return -1;
+    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    if (e != cudaSuccess) return fail("flush", e);
+    const long S = parallel_sample_len(n);
+    std::vector<double> sx((size_t)S), sw((size_t)S);
+    for (long i = 0; i < S; ++i) {
+        long pos = parallel_sample_pos(i, n, S);
+        sx[i] = x[pos];
+        sw[i] = w ? w[pos] : wsc;
+    }
+    e = cudaMemcpyAsync(parallel_sample_x(t->scratch), sx.data(), S * sizeof(double),
+                        cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(parallel_sample_w(t->scratch), sw.data(), S * sizeof(double),
+                            cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = parallel_begin_from_sample(t->s.v, S, t->scratch, st);
+    if (e != cudaSuccess) return fail("parallel edges", e);
+
+    const int64_t chunk = 1 << 24;  // 16 Mi values: 128 MiB per array per buffer
+    const int nbuf = 2;
+    double* dbuf[2] = {nullptr, nullptr};
+    cudaStream_t cst = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    const int64_t cw = ((n < chunk ? n : chunk) + 1) & ~(int64_t)1;  // even: w half stays 16-byte aligned
+    const size_t per = (size_t)cw * sizeof(double) * (w ? 2 : 1);
+    int rc = 0;
+    e = cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking);
+    for (int b = 0; b < nbuf && e == cudaSuccess; ++b) {
+        e = cudaMalloc(&dbuf[b], per);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) {
+        // the copy stream must see the edges/flush work only through buffer reuse events;
+        // it only touches dbuf, so no extra dependency is needed at the start
+        int k = 0;
+        for (int64_t off = 0; off < n && e == cudaSuccess; off += chunk, ++k) {
+            const int b = k % nbuf;
+            const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+            if (k >= nbuf) e = cudaStreamWaitEvent(cst, done[b], 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(dbuf[b], x + off, m * sizeof(double), cudaMemcpyHostToDevice, cst);
+            if (e == cudaSuccess && w)
+                e = cudaMemcpyAsync(dbuf[b] + cw, w + off, m * sizeof(double), cudaMemcpyHostToDevice, cst);
+            if (e == cudaSuccess) e = cudaEventRecord(copied[b], cst);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
+            if (e == cudaSuccess)
+                e = parallel_accumulate(t->s.v, dbuf[b], w ? dbuf[b] + cw : nullptr, wsc, m,
+                                        t->scratch, sm_count(), st, k == 0);
+            if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
+        }
+        if (e == cudaSuccess) e = parallel_finalize(t->s.v, 0, t->scratch, sm_count(), st);
+    }
+    if (e != cudaSuccess) rc = fail("host-chunked parallel update", e);
+    // buffers are freed only after the work that reads them has finished
+    cudaStreamSynchronize(st);
+    if (cst) { cudaStreamSynchronize(cst); cudaStreamDestroy(cst); }
+    for (int b = 0; b < nbuf; ++b) {
+        if (dbuf[b]) cudaFree(dbuf[b]);
+        if (copied[b]) cudaEventDestroy(copied[b]);
+        if (done[b]) cudaEventDestroy(done[b]);
+    }
+    return rc;
+}
+
+int crick_tdigest_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
+                         int64_t n, int x_on_device, int w_on_device, int mode, void* stream) {
+    if (n <= 0) return 0;  // tdigest_stubs.c:648-650
+    cudaStream_t st = td_stream(t, stream);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    bool parallel = mode == CRICK_MODE_PARALLEL ||
+                    (mode == CRICK_MODE_AUTO && n >= 4 * (int64_t)CRICK_PARALLEL_MIN);
+    if (mode == CRICK_MODE_PARALLEL && n < CRICK_PARALLEL_MIN)
+        return fail_msg("parallel mode needs n >= CRICK_PARALLEL_MIN");
+    const bool w_arr = w != nullptr;
+    if (w_arr && (x_on_device != w_on_device))
+        return fail_msg("x and w must both be host or both be device arrays");
+    if (!x_on_device) {
+        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st);
+        // reference mode from host memory: stage the whole (small) input
+        double* d = nullptr;
+        size_t bytes = (size_t)n * sizeof(double) * (w_arr ? 2 : 1);
+        cudaError_t e = cudaMallocAsync(&d, bytes, st);
+        if (e != cudaSuccess) return fail("cudaMallocAsync(stage)", e);
+        e = cudaMemcpyAsync(d, x, n * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && w_arr)
+            e = cudaMemcpyAsync(d + n, w, n * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = launch_ingest(t->s.v, 1, d, w_arr ? d + n : nullptr, w_scalar, 1, 1, nullptr, n, 0,
+                              nullptr, 0, st);
+        cudaFreeAsync(d, st);
+        if (e != cudaSuccess) return fail("reference-mode update", e);
+        // the source may be pageable or reused by the caller right away
+        e = cudaStreamSynchronize(st);
+        return e == cudaSuccess ? 0 : fail("update sync", e);
+    }
+    cudaError_t e;
+    if (parallel) {
+        if (td_scratch(t)) return -1;
+        e = launch_flush(t->s.v, 0, 1, 1, st);
+        if (e == cudaSuccess)
+            e = launch_parallel_update(t->s.v, 0, x, w, w_scalar, n, t->scratch, sm_count(), st);
+    } else {
+        e = launch_ingest(t->s.v, 1, x, w, w_scalar, 1, 1, nullptr, n, 0, nullptr, 0, st);
+    }
+    return e == cudaSuccess ? 0 : fail("update", e);
+}
+
+int crick_tdigest_flush(crick_tdigest_t* t) {
+    cudaStream_t st = td_stream(t, nullptr);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    return e == cudaSuccess ? 0 : fail("flush", e);
+}
+
+int crick_tdigest_merge(crick_tdigest_t* t, crick_tdigest_t* const* others, int n_others) {
+    cudaStream_t st = td_stream(t, nullptr);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    for (int i = 0; i < n_others; ++i) {
+        crick_tdigest* o = others[i];
+        cudaStream_t ost = td_stream(o, nullptr);
+        if (td_drain(o, ost)) return -1;
+        o->mirror_ok = false;
+        cudaError_t e = launch_flush(o->s.v, 0, 1, 1, ost);  // tdigest_merge flushes `other` (:595)
+        if (e == cudaSuccess && o != t) {
+            e = cudaEventRecord(o->ev, ost);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, o->ev, 0);
+        }
+        if (e == cudaSuccess) e = launch_merge_pairs(t->s.v, o->s.v, 0, 0, 0, 0, 1, st);
+        if (e == cudaSuccess && o != t) {
+            // `o` must not be mutated/freed before the merge has read it
+            e = cudaEventRecord(t->ev, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, t->ev, 0);
+        }
+        if (e != cudaSuccess) return fail("merge", e);
+    }
+    return 0;
+}
+
+int crick_tdigest_scale(crick_tdigest_t* t, double factor) {
+    cudaStream_t st = td_stream(t, nullptr);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    if (e == cudaSuccess) e = launch_scale(t->s.v, 0, factor, st);
+    return e == cudaSuccess ? 0 : fail("scale", e);
+}
+
+static int td_query(crick_tdigest* t, bool cdf, const double* in, double* out, int64_t n,
+                    int on_device, void* stream) {
+    cudaStream_t st = td_stream(t, stream);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;  // query_prep flushes (tdigest_stubs.c:307)
+    cudaError_t e = launch_query_prep(t->s.v, 0, 1, st);
+    if (e != cudaSuccess) return fail("query prep", e);
+    if (n <= 0) return 0;
+    if (on_device) {
+        e = launch_query(t->s.v, 0, cdf, in, out, n, sm_count(), st);
+        return e == cudaSuccess ? 0 : fail("query", e);
+    }
+    double* d = nullptr;
+    e = cudaMallocAsync(&d, 2 * (size_t)n * sizeof(double), st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(query)", e);
+    e = cudaMemcpyAsync(d, in, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_query(t->s.v, 0, cdf, d, d + n, n, sm_count(), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + n, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? 0 : fail("query", e);
+}
+
+int crick_tdigest_quantile(crick_tdigest_t* t, const double* q, double* out, int64_t n,
+                           int on_device, void* stream) {
+    return td_query(t, false, q, out, n, on_device, stream);
+}
+int crick_tdigest_cdf(crick_tdigest_t* t, const double* x, double* out, int64_t n, int on_device,
+                      void* stream) {
+    return td_query(t, true, x, out, n, on_device, stream);
+}
+
+double crick_tdigest_compression(crick_tdigest_t* t) { return t->s.v.comp; }
+int crick_tdigest_size(crick_tdigest_t* t) { return t->s.v.cap; }
+int crick_tdigest_buffer_size(crick_tdigest_t* t) { return t->s.v.bufcap; }
+double crick_tdigest_min(crick_tdigest_t* t) { return td_sync_mirror(t) ? NAN : t->mirror.vmin; }
+double crick_tdigest_max(crick_tdigest_t* t) { return td_sync_mirror(t) ? NAN : t->mirror.vmax; }
+int crick_tdigest_ncentroids(crick_tdigest_t* t) { return td_sync_mirror(t) ? -1 : t->mirror.n; }
+int crick_tdigest_buffer_ncentroids(crick_tdigest_t* t) { return td_sync_mirror(t) ? -1 : t->mirror.bn; }
+double crick_tdigest_total_weight(crick_tdigest_t* t) { return td_sync_mirror(t) ? NAN : t->mirror.total; }
+double crick_tdigest_buffer_total_weight(crick_tdigest_t* t) {
+    return td_sync_mirror(t) ? NAN : t->mirror.btotal;
+}
+
+int crick_tdigest_get_centroids(crick_tdigest_t* t, double* out, int on_device) {
+    if (td_sync_mirror(t)) return -1;
+    int n = t->mirror.n;
+    if (n <= 0) return 0;
+    cudaStream_t st = td_stream(t, nullptr);
+    cudaError_t e = cudaMemcpyAsync(out, t->s.v.cen, (size_t)n * sizeof(double2),
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? n : fail("get_centroids", e);
+}
+
+const double* crick_tdigest_centroids_device(crick_tdigest_t* t) {
+    return reinterpret_cast<const double*>(t->s.v.cen);
+}
+
+int crick_tdigest_set_state(crick_tdigest_t* t, const double* centroids, int n, double total_weight,
+                            double vmin, double vmax) {
+    if (n < 0 || n > t->s.v.cap) return fail_msg("set_state: more centroids than 2*ceil(compression)");
+    if (td_sync_mirror(t)) return -1;
+    cudaStream_t st = td_stream(t, nullptr);
+    DevHdr h = t->mirror;
+    h.total = total_weight; h.vmin = vmin; h.vmax = vmax;
+    if (n > 0) h.n = n;  // tdigest.pyx:260-263
+    cudaError_t e = cudaSuccess;
+    if (n > 0)
+        e = cudaMemcpyAsync(t->s.v.cen, centroids, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->s.v.hdr, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("set_state", e);
+    t->mirror = h;
+    return 0;
+}
+
+int crick_tdigest_debug_edges(crick_tdigest_t* t, double* out, int max_out) {
+    if (!t->scratch) return 0;
+    return parallel_debug_edges(t->scratch, out, max_out, td_stream(t, nullptr));
+}
+
+int crick_tdigest_record_doubles(crick_tdigest_t* t) { return 4 + 2 * t->s.v.cap; }
+
+int crick_tdigest_export_record(crick_tdigest_t* t, double* record_dev, void* stream) {
+    cudaStream_t st = td_stream(t, stream);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    if (e == cudaSuccess) e = launch_pack_record(t->s.v, 0, record_dev, st);
+    return e == cudaSuccess ? 0 : fail("export_record", e);
+}
+
+int crick_tdigest_merge_records(crick_tdigest_t* t, const double* records_dev, int n_records, int skip,
+                                void* stream) {
+    cudaStream_t st = td_stream(t, stream);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    cudaError_t e = launch_merge_records(t->s.v, 0, records_dev, n_records, skip, st);
+    return e == cudaSuccess ? 0 : fail("merge_records", e);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// grouped digests
+struct crick_tdigest_group {
+    DigestStore s;
+    cudaStream_t own = nullptr;
+    cudaStream_t last = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+
+static cudaStream_t grp_stream(crick_tdigest_group* g, void* stream) {
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : g->own;
+    if (g->last && g->last != st) {
+        cudaEventRecord(g->ev, g->last);
+        cudaStreamWaitEvent(st, g->ev, 0);
+    }
+    g->last = st;
+    return st;
+}
+
+extern "C" {
+
+crick_tdigest_group_t* crick_tdigest_group_new(double compression, int64_t n_groups) {
+    if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
+    if (n_groups <= 0) { fail_msg("n_groups must be > 0"); return nullptr; }
+    crick_tdigest_group* g = new (std::nothrow) crick_tdigest_group();
+    if (!g) return nullptr;
+    if (store_alloc(g->s, compression, n_groups)) { delete g; return nullptr; }
+    cudaError_t e = cudaStreamCreateWithFlags(&g->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = launch_init_hdr(g->s.v.hdr, n_groups, g->own);
+    if (e != cudaSuccess) { fail("tdigest_group_new", e); crick_tdigest_group_free(g); return nullptr; }
+    g->last = g->own;
+    return g;
+}
+
+void crick_tdigest_group_free(crick_tdigest_group_t* g) {
+    if (!g) return;
+    if (g->last) cudaStreamSynchronize(g->last);
+    if (g->own) { cudaStreamSynchronize(g->own); cudaStreamDestroy(g->own); }
+    if (g->ev) cudaEventDestroy(g->ev);
+    store_free(g->s);
+    delete g;
+}
+
+int64_t crick_tdigest_group_count(crick_tdigest_group_t* g) { return g->s.nd; }
+
+int crick_tdigest_group_update(crick_tdigest_group_t* g, const double* values, const double* weights,
+                               double w_scalar, const int64_t* offsets, int64_t row_len,
+                               int64_t row_stride, int on_device, void* stream) {
+    cudaStream_t st = grp_stream(g, stream);
+    const long ng = g->s.nd;
+    static_assert(sizeof(long) == sizeof(int64_t), "LP64 expected");
+    if (on_device) {
+        cudaError_t e = launch_ingest(g->s.v, ng, values, weights, w_scalar, 1, 1,
+                                      reinterpret_cast<const long*>(offsets), row_len, row_stride,
+                                      nullptr, 0, st);
+        return e == cudaSuccess ? 0 : fail("group_update", e);
+    }
+    // host input: stage values (+weights, +offsets) once
+    int64_t total;
+    if (offsets) total = offsets[ng];
+    else total = (ng - 1) * row_stride + row_len;
+    if (total <= 0) return 0;
+    double* d = nullptr;
+    long* doff = nullptr;
+    size_t bytes = (size_t)total * sizeof(double) * (weights ? 2 : 1);
+    cudaError_t e = cudaMallocAsync(&d, bytes, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(group stage)", e);
+    e = cudaMemcpyAsync(d, values, total * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && weights)
+        e = cudaMemcpyAsync(d + total, weights, total * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && offsets) {
+        e = cudaMallocAsync(&doff, (size_t)(ng + 1) * sizeof(long), st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(doff, offsets, (size_t)(ng + 1) * sizeof(long), cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess)
+        e = launch_ingest(g->s.v, ng, d, weights ? d + total : nullptr, w_scalar, 1, 1, doff, row_len,
+                          row_stride, nullptr, 0, st);
+    cudaFreeAsync(d, st);
+    if (doff) cudaFreeAsync(doff, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? 0 : fail("group_update", e);
+}
+
+int crick_tdigest_group_flush(crick_tdigest_group_t* g) {
+    cudaStream_t st = grp_stream(g, nullptr);
+    cudaError_t e = launch_flush(g->s.v, 0, 1, g->s.nd, st);
+    return e == cudaSuccess ? 0 : fail("group_flush", e);
+}
+
+int crick_tdigest_group_merge_tree(crick_tdigest_group_t* g, crick_tdigest_t* out) {
+    if (out->s.v.cap != g->s.v.cap || out->s.v.bufcap != g->s.v.bufcap)
+        return fail_msg("merge_tree: output digest has a different compression");
+    cudaStream_t st = grp_stream(g, nullptr);
+    const long n = g->s.nd;
+    cudaError_t e = cudaSuccess;
+    for (long s = 1; s < n && e == cudaSuccess; s <<= 1) {
+        long count = (n - s + 2 * s - 1) / (2 * s);  // pairs (i, i+s), i = 0, 2s, 4s, ... with i+s < n
+        e = launch_flush(g->s.v, s, 2 * s, count, st);
+        if (e == cudaSuccess) e = launch_merge_pairs(g->s.v, g->s.v, 0, 2 * s, s, 2 * s, count, st);
+    }
+    if (e != cudaSuccess) return fail("merge_tree", e);
+    cudaStream_t ost = td_stream(out, nullptr);
+    if (td_drain(out, ost)) return -1;
+    out->mirror_ok = false;
+    e = cudaEventRecord(g->ev, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, g->ev, 0);
+    if (e == cudaSuccess) e = launch_copy_digest(out->s.v, 0, g->s.v, 0, ost);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ost);
+    return e == cudaSuccess ? 0 : fail("merge_tree copy", e);
+}
+
+static int grp_query(crick_tdigest_group* g, bool cdf, const double* in, int nq, double* out,
+                     int on_device, void* stream) {
+    cudaStream_t st = grp_stream(g, stream);
+    const long ng = g->s.nd;
+    cudaError_t e = launch_query_prep(g->s.v, 0, ng, st);
+    if (e != cudaSuccess) return fail("group query prep", e);
+    if (nq <= 0) return 0;
+    if (on_device) {
+        e = launch_query_grouped(g->s.v, ng, cdf, in, out, nq, st);
+        return e == cudaSuccess ? 0 : fail("group query", e);
+    }
+    double* d = nullptr;
+    size_t outn = (size_t)ng * nq;
+    e = cudaMallocAsync(&d, (nq + outn) * sizeof(double), st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(group query)", e);
+    e = cudaMemcpyAsync(d, in, nq * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_query_grouped(g->s.v, ng, cdf, d, d + nq, nq, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + nq, outn * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? 0 : fail("group query", e);
+}
+
+int crick_tdigest_group_quantile(crick_tdigest_group_t* g, const double* q, int nq, double* out,
+                                 int on_device, void* stream) {
+    return grp_query(g, false, q, nq, out, on_device, stream);
+}
+int crick_tdigest_group_cdf(crick_tdigest_group_t* g, const double* x, int nq, double* out,
+                            int on_device, void* stream) {
+    return grp_query(g, true, x, nq, out, on_device, stream);
+}
+
+int crick_tdigest_group_meta(crick_tdigest_group_t* g, double* out_meta) {
+    cudaStream_t st = grp_stream(g, nullptr);
+    const long ng = g->s.nd;
+    double* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, (size_t)ng * 4 * sizeof(double), st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(meta)", e);
+    e = launch_group_meta(g->s.v, ng, d, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_meta, d, (size_t)ng * 4 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? 0 : fail("group_meta", e);
+}
+
+int crick_tdigest_group_get_centroids(crick_tdigest_group_t* g, int64_t i, double* out) {
+    if (i < 0 || i >= g->s.nd) return fail_msg("group index out of range");
+    cudaStream_t st = grp_stream(g, nullptr);
+    cudaError_t e = launch_flush(g->s.v, i, 1, 1, st);
+    DevHdr h;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, g->s.v.hdr + i, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("group_get_centroids", e);
+    if (h.n > 0) {
+        e = cudaMemcpyAsync(out, g->s.v.cen + i * (long)g->s.v.cap, (size_t)h.n * sizeof(double2),
+                            cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail("group_get_centroids", e);
+    }
+    return h.n;
+}
+
+int crick_tdigest_group_extract(crick_tdigest_group_t* g, int64_t i, crick_tdigest_t* out) {
+    if (i < 0 || i >= g->s.nd) return fail_msg("group index out of range");
+    if (out->s.v.cap != g->s.v.cap || out->s.v.bufcap != g->s.v.bufcap)
+        return fail_msg("extract: output digest has a different compression");
+    cudaStream_t st = grp_stream(g, nullptr);
+    cudaStream_t ost = td_stream(out, nullptr);
+    if (td_drain(out, ost)) return -1;
+    out->mirror_ok = false;
+    cudaError_t e = cudaEventRecord(g->ev, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, g->ev, 0);
+    if (e == cudaSuccess) e = launch_copy_digest(out->s.v, 0, g->s.v, i, ost);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ost);
+    return e == cudaSuccess ? 0 : fail("group_extract", e);
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// crick_b200/csrc/api_common.h -- host-side plumbing shared by the C-ABI translation units
+#pragma once
+#include <atomic>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace crick {
+
+int fail(const char* what, cudaError_t e);  // records crick_last_error(), returns -1
+int fail_msg(const char* what);
+int sm_count();                              // 0 when there is no usable device
+
+struct DigestStore {
+    BatchView v{};
+    long nd = 0;
+    void* base = nullptr;
+    size_t bytes = 0;
+};
+int store_alloc(DigestStore& s, double compression, long nd);
+void store_free(DigestStore& s);
+
+}  // namespace crick

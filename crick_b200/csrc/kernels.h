@@ -1,0 +1,58 @@
+// crick_b200/csrc/kernels.h -- host-callable launchers (internal to libcrick_cuda.so)
+#pragma once
+#include "common.cuh"
+
+namespace crick {
+
+// ---- reference-compatible path (tdigest_kernels.cu)
+cudaError_t launch_ingest(const BatchView& v, long ngroups, const double* X, const double* W,
+                          double wsc, long sx, long sw, const long* offsets, long fixed_len,
+                          long row_stride, const long* dmap, int flags, cudaStream_t st);
+cudaError_t launch_flush(const BatchView& v, long first, long step, long count, cudaStream_t st);
+cudaError_t launch_merge_pairs(const BatchView& dv, const BatchView& sv, long dfirst, long dstep,
+                               long sfirst, long sstep, long count, cudaStream_t st);
+cudaError_t launch_scale(const BatchView& v, long d, double factor, cudaStream_t st);
+cudaError_t launch_query_prep(const BatchView& v, long first, long count, cudaStream_t st);
+cudaError_t launch_query(const BatchView& v, long d, bool cdf, const double* in, double* out,
+                         long nq, int sm_count, cudaStream_t st);
+cudaError_t launch_query_grouped(const BatchView& v, long ngroups, bool cdf, const double* in,
+                                 double* out, int nq, cudaStream_t st);
+
+cudaError_t launch_init_hdr(DevHdr* hdr, long n, cudaStream_t st);
+cudaError_t launch_pack_record(const BatchView& v, long d, double* rec, cudaStream_t st);
+cudaError_t launch_merge_records(const BatchView& v, long d, const double* recs, int nrec, int skip,
+                                 cudaStream_t st);
+cudaError_t launch_copy_digest(const BatchView& dv, long dd, const BatchView& sv, long sd,
+                               cudaStream_t st);
+cudaError_t launch_group_meta(const BatchView& v, long ng, double* out, cudaStream_t st);
+
+// ---- parallel k-bucket path (tdigest_parallel.cu)
+size_t parallel_scratch_bytes(double compression, int sm_count);
+// X/W device pointers (W may be null -> scalar wsc). Accumulates the whole array
+// into digest `d` of `v` (which must have an empty buffer): sample -> edges ->
+// accumulate -> finalize, all on `st`, no host synchronisation.
+cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
+                                   double wsc, long n, void* scratch, int sm_count,
+                                   cudaStream_t st);
+// The same pipeline in pieces, for host-resident input streamed in chunks: edges
+// from a caller-provided sample (copied to parallel_sample_x/w), any number of
+// accumulate calls (first = 1 on the first), then one finalize.
+cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratch, cudaStream_t st);
+cudaError_t parallel_accumulate(const BatchView& v, const double* X, const double* W, double wsc,
+                                long n, void* scratch, int sm_count, cudaStream_t st, int first);
+cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_count,
+                              cudaStream_t st);
+// debug/test accessor: copy the bucket edges of the last parallel update to the host
+int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st);
+double* parallel_sample_x(void* scratch);
+double* parallel_sample_w(void* scratch);
+long parallel_sample_capacity(void* scratch);
+// host mirrors of the device sampler, so that host-resident input picks the same sample
+long parallel_sample_len(long n);
+long parallel_sample_pos(long i, long n, long S);
+
+// ---- synthetic data (synth.cu)
+cudaError_t launch_synth(double* x, double* w, long n, unsigned long long seed, long offset,
+                         int kind, cudaStream_t st);
+
+}  // namespace crick

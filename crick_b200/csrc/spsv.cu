@@ -1,0 +1,566 @@
+// crick_b200/csrc/spsv.cu -- SpaceSaving (Stream-Summary) for int64 / float64-bit-pattern items
+// on the GPU.  Replaces crick/space_saving_stubs.c.in (int64 instantiation).
+//
+// The reference keeps a circular doubly-linked list sorted by (count desc, error asc) over a
+// slot array, plus a khash map item -> slot.  The list order depends on the exact sequence of
+// "walk backwards until a node >= me" steps (:121-138), so the reference-compatible path here
+// replays the stream IN ORDER with one warp:
+//   * the list is an explicit `order[]` array (position -> slot); the backwards walk is done
+//     32 predecessors at a time (ballot), the re-insertion is a warp-wide shift;
+//   * the map is an open-addressing table probed 32 slots at a time.
+// State lives in HBM between calls and is staged in shared memory during a call when it
+// fits (capacity <~ 2400), otherwise the kernel works on the HBM copy directly.
+//
+// Quirks kept: eviction ignores the weight (:229-231); float64 items are
+// compared by bit pattern.  Quirk NOT kept: the dangling hash key the reference leaves behind
+// on the merge's early `break` (:334/:345, segfault) -- nothing is inserted here.
+#include "../../include/crick_cuda.h"
+#include "api_common.h"
+
+namespace crick {
+
+struct SpsvHdr {
+    long capacity;
+    long size;
+    int hcap;   // power of two >= 4*capacity
+    int tomb;   // deleted markers currently in the table
+};
+
+struct SpsvView {
+    SpsvHdr* hdr;
+    long long* item;   // [capacity] slot arrays, creation order
+    long long* count;
+    long long* error;
+    int* order;        // [capacity] list position -> slot (0 = head)
+    int* pos;          // [capacity] slot -> list position
+    long long* hkey;   // [hcap]
+    int* hval;         // [hcap]  slot, -1 empty, -2 deleted
+};
+
+static size_t spsv_bytes(long cap, int hcap) {
+    return 64 + (size_t)cap * (24 + 8) + (size_t)hcap * 12 + 64;
+}
+
+__host__ __device__ inline SpsvView spsv_carve(unsigned char* base, long cap, int hcap) {
+    SpsvView v;
+    v.hdr = reinterpret_cast<SpsvHdr*>(base);
+    unsigned char* p = base + 64;
+    v.item = reinterpret_cast<long long*>(p); p += cap * 8;
+    v.count = reinterpret_cast<long long*>(p); p += cap * 8;
+    v.error = reinterpret_cast<long long*>(p); p += cap * 8;
+    v.hkey = reinterpret_cast<long long*>(p); p += (size_t)hcap * 8;
+    v.order = reinterpret_cast<int*>(p); p += cap * 4;
+    v.pos = reinterpret_cast<int*>(p); p += cap * 4;
+    v.hval = reinterpret_cast<int*>(p);
+    return v;
+}
+
+__device__ __forceinline__ unsigned hash64(long long k) {
+    unsigned long long x = (unsigned long long)k;
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (unsigned)x;
+}
+
+// working copy: header in registers (warp-uniform), arrays via pointers (shared or global)
+struct SpsvW {
+    long long *item, *count, *error, *hkey;
+    int *order, *pos, *hval;
+    long capacity, size;
+    int hcap, tomb;
+};
+
+// warp-parallel probe; returns table index of `k` or -1
+__device__ __forceinline__ int map_find(const SpsvW& w, long long k, int lane) {
+    unsigned base = hash64(k) & (unsigned)(w.hcap - 1);
+    for (int step = 0; step < w.hcap; step += 32) {
+        int idx = (int)((base + step + lane) & (unsigned)(w.hcap - 1));
+        int v = w.hval[idx];
+        bool hit = v >= 0 && w.hkey[idx] == k;
+        bool empty = v == -1;
+        unsigned mh = __ballot_sync(CRICK_FULL, hit), me = __ballot_sync(CRICK_FULL, empty);
+        // first event along the probe sequence decides
+        int fh = mh ? __ffs(mh) - 1 : 64, fe = me ? __ffs(me) - 1 : 64;
+        if (fh < fe) return (int)((base + step + fh) & (unsigned)(w.hcap - 1));
+        if (fe < 64) return -1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void map_put(SpsvW& w, long long k, int slot, int lane) {
+    unsigned base = hash64(k) & (unsigned)(w.hcap - 1);
+    for (int step = 0; step < w.hcap; step += 32) {
+        int idx = (int)((base + step + lane) & (unsigned)(w.hcap - 1));
+        int v = w.hval[idx];
+        unsigned mf = __ballot_sync(CRICK_FULL, v < 0);
+        if (mf) {
+            int f = __ffs(mf) - 1;
+            int tgt = (int)((base + step + f) & (unsigned)(w.hcap - 1));
+            int old = w.hval[tgt];
+            __syncwarp();
+            if (lane == 0) { w.hkey[tgt] = k; w.hval[tgt] = slot; }
+            if (old == -2) w.tomb--;
+            __syncwarp();
+            return;
+        }
+    }
+}
+
+__device__ __forceinline__ void map_rebuild(SpsvW& w, int lane) {
+    for (int i = lane; i < w.hcap; i += 32) w.hval[i] = -1;
+    __syncwarp();
+    w.tomb = 0;
+    for (long s = 0; s < w.size; ++s) map_put(w, w.item[s], (int)s, lane);
+}
+
+__device__ __forceinline__ void map_del(SpsvW& w, long long k, int lane) {
+    int idx = map_find(w, k, lane);
+    if (idx >= 0) {
+        if (lane == 0) w.hval[idx] = -2;
+        w.tomb++;
+        __syncwarp();
+    }
+}
+
+// counter_ge (:112-118) with offset
+__device__ __forceinline__ bool ctr_ge(long long ac, long long ae, long long bc, long long be,
+                                       long long off) {
+    long long c = bc + off, e = be + off;
+    return ac > c || (ac == c && ae <= e);
+}
+
+// Move the slot at list position p towards the head until its predecessor is >= it
+// (counter_insert :121-138 / rebalance :167-183): exact linear-walk semantics, 32 at a time.
+__device__ __forceinline__ void sift(SpsvW& w, int p, int lane) {
+    const int s = w.order[p];
+    const long long sc = w.count[s], se = w.error[s];
+    int t = p;  // final position
+    while (t > 0) {
+        int j = t - 1 - lane;
+        bool ge = true;  // positions before the head stop the walk
+        if (j >= 0) { int o = w.order[j]; ge = ctr_ge(w.count[o], w.error[o], sc, se, 0); }
+        unsigned m = __ballot_sync(CRICK_FULL, ge);
+        int adv = m ? __ffs(m) - 1 : 32;  // predecessors that are NOT >= me
+        t -= adv;
+        if (adv < 32) break;
+    }
+    if (t == p) return;
+    // shift order[t .. p) one step towards the tail, highest chunk first
+    for (int hi = p; hi > t; hi -= 32) {
+        int j = hi - 1 - lane;  // source position
+        int o = (j >= t) ? w.order[j] : -1;
+        __syncwarp();
+        if (j >= t) { w.order[j + 1] = o; w.pos[o] = j + 1; }
+        __syncwarp();
+    }
+    if (lane == 0) { w.order[t] = s; w.pos[s] = t; }
+    __syncwarp();
+}
+
+// counter_new (:141-164)
+__device__ __forceinline__ int ctr_new(SpsvW& w, long long item, long long count, long long error,
+                                       int lane) {
+    int s = (int)w.size;
+    if (lane == 0) {
+        w.item[s] = item; w.count[s] = count; w.error[s] = error;
+        w.order[s] = s; w.pos[s] = s;
+    }
+    w.size++;
+    __syncwarp();
+    sift(w, s, lane);
+    map_put(w, item, s, lane);
+    return s;
+}
+
+// swap (:186-210): relabel slot s, rebalance
+__device__ __forceinline__ void ctr_replace(SpsvW& w, int s, long long item, long long count,
+                                            long long error, int lane) {
+    map_del(w, w.item[s], lane);
+    if (lane == 0) { w.item[s] = item; w.count[s] = count; w.error[s] = error; }
+    __syncwarp();
+    sift(w, w.pos[s], lane);
+    map_put(w, item, s, lane);
+    if (w.tomb > w.hcap / 4) map_rebuild(w, lane);
+}
+
+// spsv_add (:213-250)
+__device__ __forceinline__ void spsv_add1(SpsvW& w, long long item, long long cnt, int lane) {
+    int idx = map_find(w, item, lane);
+    if (idx < 0) {
+        if (w.size == w.capacity) {
+            int s = w.order[w.size - 1];
+            long long c = w.count[s];
+            ctr_replace(w, s, item, c + 1, c, lane);  // ignores cnt (quirk P2)
+        } else {
+            ctr_new(w, item, cnt, 0, lane);
+        }
+    } else {
+        int s = w.hval[idx];
+        if (lane == 0) w.count[s] += cnt;
+        __syncwarp();
+        sift(w, w.pos[s], lane);
+    }
+}
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__device__ __forceinline__ SpsvW open_state(unsigned char* gbase, long cap, int hcap, int use_smem,
+                                            int lane) {
+    SpsvView g = spsv_carve(gbase, cap, hcap);
+    SpsvHdr h = *g.hdr;
+    SpsvView v = g;
+    if (use_smem) {
+        v = spsv_carve(smem_raw, cap, hcap);
+        for (long i = lane; i < h.size; i += 32) {
+            v.item[i] = g.item[i]; v.count[i] = g.count[i]; v.error[i] = g.error[i];
+            v.order[i] = g.order[i]; v.pos[i] = g.pos[i];
+        }
+        for (int i = lane; i < hcap; i += 32) { v.hkey[i] = g.hkey[i]; v.hval[i] = g.hval[i]; }
+        __syncwarp();
+    }
+    SpsvW w;
+    w.item = v.item; w.count = v.count; w.error = v.error; w.hkey = v.hkey;
+    w.order = v.order; w.pos = v.pos; w.hval = v.hval;
+    w.capacity = h.capacity; w.size = h.size; w.hcap = h.hcap; w.tomb = h.tomb;
+    return w;
+}
+
+__device__ __forceinline__ void close_state(const SpsvW& w, unsigned char* gbase, long cap, int hcap,
+                                            int use_smem, int lane) {
+    SpsvView g = spsv_carve(gbase, cap, hcap);
+    __syncwarp();
+    if (use_smem) {
+        for (long i = lane; i < w.size; i += 32) {
+            g.item[i] = w.item[i]; g.count[i] = w.count[i]; g.error[i] = w.error[i];
+            g.order[i] = w.order[i]; g.pos[i] = w.pos[i];
+        }
+        for (int i = lane; i < hcap; i += 32) { g.hkey[i] = w.hkey[i]; g.hval[i] = w.hval[i]; }
+    }
+    if (lane == 0) {
+        SpsvHdr h;
+        h.capacity = w.capacity; h.size = w.size; h.hcap = w.hcap; h.tomb = w.tomb;
+        *g.hdr = h;
+    }
+}
+
+// spsv_int64_update_ndarray loop (:422-435), in order
+__global__ void __launch_bounds__(32) k_spsv_update(unsigned char* state, long cap, int hcap,
+                                                    int use_smem, const long long* __restrict__ item,
+                                                    const long long* __restrict__ cnt,
+                                                    long long cnt_scalar, long n) {
+    const int lane = threadIdx.x;
+    SpsvW w = open_state(state, cap, hcap, use_smem, lane);
+    for (long base = 0; base < n; base += 32) {
+        long i = base + lane;
+        long long it = i < n ? item[i] : 0;
+        long long c = cnt ? (i < n ? cnt[i] : 0) : cnt_scalar;
+        int m = (int)((n - base) < 32 ? (n - base) : 32);
+        for (int k = 0; k < m; ++k) {
+            long long itk = __shfl_sync(CRICK_FULL, it, k);
+            long long ck = __shfl_sync(CRICK_FULL, c, k);
+            spsv_add1(w, itk, ck, lane);
+        }
+    }
+    close_state(w, state, cap, hcap, use_smem, lane);
+}
+
+// set_state (:253-286); returns status in *status: 1 ok, -2 duplicate
+__global__ void __launch_bounds__(32) k_spsv_set_state(unsigned char* state, long cap, int hcap,
+                                                       int use_smem, const long long* __restrict__ c3,
+                                                       long n, int* status) {
+    const int lane = threadIdx.x;
+    SpsvW w = open_state(state, cap, hcap, use_smem, lane);
+    int rc = 1;
+    for (long i = 0; i < n; ++i) {
+        long long it = c3[3 * i], cn = c3[3 * i + 1], er = c3[3 * i + 2];
+        if (map_find(w, it, lane) >= 0) { rc = -2; break; }
+        ctr_new(w, it, cn, er, lane);
+    }
+    close_state(w, state, cap, hcap, use_smem, lane);
+    if (lane == 0) *status = rc;
+}
+
+// spsv_merge (:289-364), T2 read-only from HBM
+__global__ void __launch_bounds__(32) k_spsv_merge(unsigned char* s1, long cap1, int hcap1,
+                                                   int use_smem, unsigned char* s2, long cap2,
+                                                   int hcap2) {
+    const int lane = threadIdx.x;
+    SpsvView g2 = spsv_carve(s2, cap2, hcap2);
+    SpsvHdr h2 = *g2.hdr;
+    if (h2.size == 0) return;
+    SpsvW w2;
+    w2.item = g2.item; w2.count = g2.count; w2.error = g2.error; w2.hkey = g2.hkey;
+    w2.order = g2.order; w2.pos = g2.pos; w2.hval = g2.hval;
+    w2.capacity = h2.capacity; w2.size = h2.size; w2.hcap = h2.hcap; w2.tomb = h2.tomb;
+    SpsvW w = open_state(s1, cap1, hcap1, use_smem, lane);
+    long long m1 = w.size < w.capacity ? 0 : w.count[w.order[w.size - 1]];
+    long long m2 = w2.size < w2.capacity ? 0 : w2.count[w2.order[w2.size - 1]];
+    for (long s = 0; s < w.size; ++s) {  // slot order (:308)
+        int idx = map_find(w2, w.item[s], lane);
+        if (lane == 0) {
+            if (idx >= 0) {
+                int s2i = w2.hval[idx];
+                w.count[s] += w2.count[s2i];
+                w.error[s] += w2.error[s2i];
+            } else {
+                w.count[s] += m2;
+                w.error[s] += m2;
+            }
+        }
+        __syncwarp();
+        sift(w, w.pos[s], lane);
+    }
+    for (long p = 0; p < w2.size; ++p) {  // T2's list order (:330)
+        int s2i = w2.order[p];
+        long long it = w2.item[s2i], cn = w2.count[s2i], er = w2.error[s2i];
+        if (map_find(w, it, lane) >= 0) continue;
+        if (w.size == w.capacity) {
+            int tail = w.order[w.size - 1];
+            if (ctr_ge(w.count[tail], w.error[tail], cn, er, m1)) break;
+            ctr_replace(w, tail, it, cn + m1, er + m1, lane);
+        } else {
+            ctr_new(w, it, cn + m1, er + m1, lane);
+        }
+    }
+    close_state(w, s1, cap1, hcap1, use_smem, lane);
+}
+
+// int64_counters walk (space_saving.pyx:368-386)
+__global__ void k_spsv_counters(unsigned char* state, long cap, int hcap, long long* out, long k) {
+    SpsvView g = spsv_carve(state, cap, hcap);
+    long n = g.hdr->size < k ? g.hdr->size : k;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int s = g.order[i];
+        out[3 * i] = g.item[s]; out[3 * i + 1] = g.count[s]; out[3 * i + 2] = g.error[s];
+    }
+}
+
+__global__ void k_spsv_init(unsigned char* state, long cap, int hcap) {
+    SpsvView g = spsv_carve(state, cap, hcap);
+    for (int i = threadIdx.x; i < hcap; i += blockDim.x) g.hval[i] = -1;
+    if (threadIdx.x == 0) {
+        SpsvHdr h; h.capacity = cap; h.size = 0; h.hcap = hcap; h.tomb = 0;
+        *g.hdr = h;
+    }
+}
+
+}  // namespace crick
+
+using namespace crick;
+
+struct crick_spsv {
+    unsigned char* d = nullptr;
+    long cap = 0;
+    int hcap = 0;
+    int use_smem = 0;
+    size_t smem = 0;
+    cudaStream_t own = nullptr, last = nullptr;
+    cudaEvent_t ev = nullptr;
+    std::vector<long long> pi, pc;  // pending scalar adds
+    long size_mirror = 0;
+    bool mirror_ok = false;
+};
+
+static cudaStream_t sp_stream(crick_spsv* s, void* stream) {
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : s->own;
+    if (s->last && s->last != st) {
+        cudaEventRecord(s->ev, s->last);
+        cudaStreamWaitEvent(st, s->ev, 0);
+    }
+    s->last = st;
+    return st;
+}
+
+static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const long long* cnt,
+                                    long long cs, long n, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    if (s->smem > 48 * 1024)
+        e = cudaFuncSetAttribute(k_spsv_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    k_spsv_update<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, item, cnt, cs, n);
+    return cudaGetLastError();
+}
+
+static int sp_drain(crick_spsv* s, cudaStream_t st) {
+    size_t n = s->pi.size();
+    if (!n) return 0;
+    long long* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, n * 16, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(spsv pending)", e);
+    e = cudaMemcpyAsync(d, s->pi.data(), n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, s->pc.data(), n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = sp_launch_update(s, d, d + n, 1, (long)n, st);
+    cudaFreeAsync(d, st);
+    s->pi.clear(); s->pc.clear();
+    s->mirror_ok = false;
+    return e == cudaSuccess ? 0 : fail("spsv drain", e);
+}
+
+extern "C" {
+
+crick_spsv_t* crick_spsv_new(int64_t capacity) {
+    if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
+    if (capacity <= 0 || capacity > (1 << 26)) { fail_msg("capacity out of range"); return nullptr; }
+    crick_spsv* s = new (std::nothrow) crick_spsv();
+    if (!s) return nullptr;
+    s->cap = capacity;
+    int h = 64;
+    while (h < 4 * capacity) h <<= 1;
+    s->hcap = h;
+    size_t bytes = spsv_bytes(s->cap, s->hcap);
+    s->use_smem = bytes <= 200 * 1024;
+    s->smem = s->use_smem ? bytes : 0;
+    cudaError_t e = cudaMalloc(&s->d, bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        count_launch();
+        k_spsv_init<<<1, 256, 0, s->own>>>(s->d, s->cap, s->hcap);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { fail("spsv_new", e); crick_spsv_free(s); return nullptr; }
+    s->last = s->own;
+    s->size_mirror = 0;
+    s->mirror_ok = true;
+    return s;
+}
+
+void crick_spsv_free(crick_spsv_t* s) {
+    if (!s) return;
+    if (s->last) cudaStreamSynchronize(s->last);
+    if (s->own) { cudaStreamSynchronize(s->own); cudaStreamDestroy(s->own); }
+    if (s->ev) cudaEventDestroy(s->ev);
+    if (s->d) cudaFree(s->d);
+    delete s;
+}
+
+int crick_spsv_add(crick_spsv_t* s, int64_t item, int64_t count) {
+    s->pi.push_back(item);
+    s->pc.push_back(count);
+    s->mirror_ok = false;
+    if (s->pi.size() >= (1u << 16)) return sp_drain(s, sp_stream(s, nullptr));
+    return 0;
+}
+
+int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count, int64_t count_scalar,
+                      int64_t n, int item_on_device, int count_on_device, int mode, void* stream) {
+    (void)mode;
+    if (n <= 0) return 0;
+    cudaStream_t st = sp_stream(s, stream);
+    if (sp_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    const long long* di = reinterpret_cast<const long long*>(item);
+    const long long* dc = reinterpret_cast<const long long*>(count);
+    unsigned char* stage = nullptr;
+    cudaError_t e = cudaSuccess;
+    size_t need = (item_on_device ? 0 : (size_t)n * 8) + ((count && !count_on_device) ? (size_t)n * 8 : 0);
+    if (need) {
+        e = cudaMallocAsync(&stage, need, st);
+        if (e != cudaSuccess) return fail("cudaMallocAsync(spsv stage)", e);
+        unsigned char* p = stage;
+        if (!item_on_device) {
+            e = cudaMemcpyAsync(p, item, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            di = reinterpret_cast<const long long*>(p); p += (size_t)n * 8;
+        }
+        if (e == cudaSuccess && count && !count_on_device) {
+            e = cudaMemcpyAsync(p, count, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            dc = reinterpret_cast<const long long*>(p);
+        }
+    }
+    if (e == cudaSuccess) e = sp_launch_update(s, di, dc, count_scalar, n, st);
+    if (stage) {
+        cudaFreeAsync(stage, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    return e == cudaSuccess ? 0 : fail("spsv_update", e);
+}
+
+int crick_spsv_merge(crick_spsv_t* s, crick_spsv_t* const* others, int n_others) {
+    cudaStream_t st = sp_stream(s, nullptr);
+    if (sp_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    for (int i = 0; i < n_others; ++i) {
+        crick_spsv* o = others[i];
+        if (o == s) return fail_msg("spsv_merge: cannot merge a summary into itself");
+        cudaStream_t ost = sp_stream(o, nullptr);
+        if (sp_drain(o, ost)) return -1;
+        cudaError_t e = cudaEventRecord(o->ev, ost);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, o->ev, 0);
+        if (e == cudaSuccess && s->smem > 48 * 1024)
+            e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+        if (e == cudaSuccess) {
+            count_launch();
+            k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, o->d, o->cap, o->hcap);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            e = cudaEventRecord(s->ev, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, s->ev, 0);
+        }
+        if (e != cudaSuccess) return fail("spsv_merge", e);
+    }
+    return 0;
+}
+
+int crick_spsv_set_state(crick_spsv_t* s, const int64_t* counters3, int64_t n) {
+    if (n > s->cap) return fail_msg("deserialization failed, size > capacity");
+    if (n <= 0) return 1;
+    cudaStream_t st = sp_stream(s, nullptr);
+    if (sp_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    long long* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, (size_t)n * 24 + 8, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(spsv set_state)", e);
+    int* dstatus = reinterpret_cast<int*>(d + 3 * n);
+    int status = 0;
+    e = cudaMemcpyAsync(d, counters3, (size_t)n * 24, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && s->smem > 48 * 1024)
+        e = cudaFuncSetAttribute(k_spsv_set_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+    if (e == cudaSuccess) {
+        count_launch();
+        k_spsv_set_state<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, d, n, dstatus);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("spsv_set_state", e);
+    if (status == -2) return fail_msg("deserialization failed, duplicate items found");
+    return 1;
+}
+
+int64_t crick_spsv_size(crick_spsv_t* s) {
+    cudaStream_t st = sp_stream(s, nullptr);
+    if (sp_drain(s, st)) return -1;
+    if (s->mirror_ok) return s->size_mirror;
+    SpsvHdr h;
+    cudaError_t e = cudaMemcpyAsync(&h, s->d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("spsv_size", e);
+    s->size_mirror = h.size;
+    s->mirror_ok = true;
+    return h.size;
+}
+
+int64_t crick_spsv_capacity(crick_spsv_t* s) { return s->cap; }
+
+int64_t crick_spsv_counters(crick_spsv_t* s, int64_t* out3, int64_t k) {
+    int64_t size = crick_spsv_size(s);
+    if (size < 0) return -1;
+    int64_t n = size < k ? size : k;
+    if (n <= 0) return 0;
+    cudaStream_t st = sp_stream(s, nullptr);
+    long long* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, (size_t)n * 24, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(spsv counters)", e);
+    count_launch();
+    k_spsv_counters<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->d, s->cap, s->hcap, d, n);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out3, d, (size_t)n * 24, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? n : fail("spsv_counters", e);
+}
+
+}  // extern "C"

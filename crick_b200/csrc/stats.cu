@@ -1,0 +1,544 @@
+// crick_b200/csrc/stats.cu -- SummaryStats on the GPU (replaces crick/stats_stubs.c).
+//
+// State (stats_t, stats_stubs.c:12-22) lives on the device; the host keeps a mirror
+// for the getters and the scalar finalisers (mean/var/std/skew/kurt, :98-136).
+//
+// Two update paths:
+//  * sequential  (n < kStatsParallelMin, and every scalar add): one thread replays
+//    stats_update_ndarray's loop (:199-210) with stats_do_update (:47-75) per element --
+//    bit-identical to the reference whenever its int64 products do not overflow.
+//  * parallel    (large arrays): per-thread shifted power sums -> central moments ->
+//    Pebay pairwise merges up warp / CTA / grid, then one merge into the state.
+//    Same formulas, different association: compared at tolerance (tests/test_stats.py).
+//
+// Integer products (row S1 of SURVEY.md 8a): the reference computes n1*n2, n1^2, n2^2 and
+// n1n2*(n1^2 - n1n2 + n2^2) in int64 and silently wraps.  Here the int64 value is used when
+// it is exact (so results match the reference bit for bit), and fp64 products otherwise
+// (where the reference is wrong).  This is a deliberate, documented divergence.
+#include "../../include/crick_cuda.h"
+#include "api_common.h"
+
+#include <cmath>
+
+namespace crick {
+
+struct StatsState {
+    long long count;
+    double sum, vmin, vmax, m2, m3, m4;
+    double first_value;
+    int homogeneous;
+    int pad;
+};
+
+constexpr long kStatsParallelMin = 1 << 16;
+
+__host__ __device__ inline void stats_fresh(StatsState& s) {
+    s.count = 0; s.sum = 0; s.vmin = DBL_MAX; s.vmax = -DBL_MIN;  // :29-37 (max quirk S0)
+    s.m2 = 0; s.m3 = 0; s.m4 = 0; s.homogeneous = 1; s.first_value = 0.0; s.pad = 0;
+}
+
+// does a*b fit in int64 (both non-negative)?
+__host__ __device__ inline bool mul_fits(long long a, long long b) {
+    if (a == 0 || b == 0) return true;
+    return a <= 9223372036854775807ll / b;
+}
+
+// stats_do_update, stats_stubs.c:47-75
+__host__ __device__ inline void stats_combine(StatsState& T, long long n2, double sum2, double min2,
+                                              double max2, double m4_2, double m3_2, double m2_2) {
+#ifdef __CUDA_ARCH__
+#define D_ADD(a, b) __dadd_rn(a, b)
+#define D_MUL(a, b) __dmul_rn(a, b)
+#define D_DIV(a, b) __ddiv_rn(a, b)
+#else
+#define D_ADD(a, b) ((a) + (b))
+#define D_MUL(a, b) ((a) * (b))
+#define D_DIV(a, b) ((a) / (b))
+#endif
+    const double u2 = D_DIV(sum2, (double)n2);
+    const double delta = T.count ? D_ADD(u2, -D_DIV(T.sum, (double)T.count)) : u2;
+    const long long n1 = T.count;
+    const long long n = n1 + n2;
+    const double dn = D_DIV(delta, (double)n);
+    const double dn2 = D_MUL(dn, dn);
+    const double dn3 = D_MUL(dn2, dn);
+    if (min2 < T.vmin) T.vmin = min2;
+    if (max2 > T.vmax) T.vmax = max2;
+    // integer products: exact int64 when they fit, fp64 otherwise
+    double n1n2, n1_2, n2_2, t4, t3;
+    bool fits = mul_fits(n1, n2) && mul_fits(n1, n1) && mul_fits(n2, n2);
+    if (fits) {
+        long long i12 = n1 * n2, i11 = n1 * n1, i22 = n2 * n2;
+        // n1^2 - n1n2 + n2^2 >= 0 and <= n1^2 + n2^2
+        bool ok = i11 <= 9223372036854775807ll - i22;
+        long long inner = ok ? (i11 - i12 + i22) : 0;
+        ok = ok && mul_fits(i12, inner);
+        n1n2 = (double)i12; n1_2 = (double)i11; n2_2 = (double)i22;
+        t4 = ok ? (double)(i12 * inner) : D_MUL((double)i12, D_ADD(D_ADD((double)i11, -(double)i12), (double)i22));
+        long long diff = n1 - n2;
+        long long ad = diff < 0 ? -diff : diff;
+        t3 = mul_fits(i12, ad) ? (double)(i12 * diff) : D_MUL((double)i12, (double)diff);
+    } else {
+        double f1 = (double)n1, f2 = (double)n2;
+        n1n2 = D_MUL(f1, f2); n1_2 = D_MUL(f1, f1); n2_2 = D_MUL(f2, f2);
+        t4 = D_MUL(n1n2, D_ADD(D_ADD(n1_2, -n1n2), n2_2));
+        t3 = D_MUL(n1n2, D_ADD(f1, -f2));
+    }
+    const double f1 = (double)n1, f2 = (double)n2;
+    // T->m4 += (m4_2 + t4*delta*dn3 + 6*(n1_2*m2_2 + n2_2*T->m2)*dn2 + 4*(n1*m3_2 - n2*T->m3)*dn)
+    {
+        double a = D_MUL(D_MUL(t4, delta), dn3);
+        double b = D_MUL(D_MUL(6.0, D_ADD(D_MUL(n1_2, m2_2), D_MUL(n2_2, T.m2))), dn2);
+        double c = D_MUL(D_MUL(4.0, D_ADD(D_MUL(f1, m3_2), -D_MUL(f2, T.m3))), dn);
+        T.m4 = D_ADD(T.m4, D_ADD(D_ADD(D_ADD(m4_2, a), b), c));
+    }
+    // T->m3 += (m3_2 + t3*delta*dn2 + 3*(n1*m2_2 - n2*T->m2)*dn)
+    {
+        double a = D_MUL(D_MUL(t3, delta), dn2);
+        double b = D_MUL(D_MUL(3.0, D_ADD(D_MUL(f1, m2_2), -D_MUL(f2, T.m2))), dn);
+        T.m3 = D_ADD(T.m3, D_ADD(D_ADD(m3_2, a), b));
+    }
+    // T->m2 += m2_2 + n1n2*delta*dn
+    T.m2 = D_ADD(T.m2, D_ADD(m2_2, D_MUL(D_MUL(n1n2, delta), dn)));
+    T.count += n2;
+    T.sum = D_ADD(T.sum, sum2);
+#undef D_ADD
+#undef D_MUL
+#undef D_DIV
+}
+
+// stats_merge, stats_stubs.c:78-90
+__host__ __device__ inline void stats_merge_state(StatsState& T1, const StatsState& T2) {
+    if (T2.count == 0) return;
+    if (T1.homogeneous && !T2.homogeneous) T1.homogeneous = 0;
+    else if (T1.homogeneous && T2.homogeneous) T1.homogeneous = (T1.first_value == T2.first_value);
+    stats_combine(T1, T2.count, T2.sum, T2.vmin, T2.vmax, T2.m4, T2.m3, T2.m2);
+}
+
+template <typename XT>
+__device__ __forceinline__ double load_x(const XT* x, long i) { return (double)x[i]; }
+
+// sequential replay of stats_update_ndarray's loop (:199-210)
+template <typename XT>
+__global__ void k_stats_seq(StatsState* st, const XT* __restrict__ x,
+                            const long long* __restrict__ cnt, long long cnt_scalar, long n,
+                            int track /* 0: replay of scalar stats_add calls, no :200-205 bookkeeping */) {
+    if (threadIdx.x || blockIdx.x) return;
+    StatsState T = *st;
+    for (long i = 0; i < n; ++i) {
+        double v = load_x(x, i);
+        if (track) {
+            if (T.count == 0) T.first_value = v;
+            else if (T.homogeneous && T.first_value != v) T.homogeneous = 0;
+        }
+        if (v != v) continue;  // stats_add :93
+        long long c = cnt ? cnt[i] : cnt_scalar;
+        stats_combine(T, c, v, v, v, 0.0, 0.0, 0.0);
+    }
+    *st = T;
+}
+
+// ---------------------------------------------------------------------------
+// parallel path
+struct StatsPart {          // mergeable summary of a contiguous index range
+    long long count;
+    double sum, vmin, vmax, m2, m3, m4;
+    long first_idx;          // index of first non-NaN element (LONG_MAX if none)
+    long last_nan_idx;       // index of last NaN element (-1 if none)
+    double first_value;      // value at first_idx
+    double last_value;       // value of the last element seen (for the all-NaN case)
+    long last_idx;
+};
+
+__device__ __forceinline__ void part_fresh(StatsPart& p) {
+    p.count = 0; p.sum = 0; p.vmin = INFINITY; p.vmax = -INFINITY; p.m2 = p.m3 = p.m4 = 0;
+    p.first_idx = 0x7fffffffffffffffl; p.last_nan_idx = -1; p.first_value = 0.0;
+    p.last_value = 0.0; p.last_idx = -1;
+}
+
+__device__ __forceinline__ void part_merge(StatsPart& a, const StatsPart& b) {
+    if (b.first_idx < a.first_idx) { a.first_idx = b.first_idx; a.first_value = b.first_value; }
+    if (b.last_nan_idx > a.last_nan_idx) a.last_nan_idx = b.last_nan_idx;
+    if (b.last_idx > a.last_idx) { a.last_idx = b.last_idx; a.last_value = b.last_value; }
+    if (b.count == 0) return;
+    if (a.count == 0) {
+        a.count = b.count; a.sum = b.sum; a.vmin = b.vmin; a.vmax = b.vmax;
+        a.m2 = b.m2; a.m3 = b.m3; a.m4 = b.m4;
+        return;
+    }
+    // Pebay pairwise merge, fp64 products
+    double n1 = (double)a.count, n2 = (double)b.count, n = n1 + n2;
+    double delta = b.sum / n2 - a.sum / n1;
+    double dn = delta / n, dn2 = dn * dn, dn3 = dn2 * dn;
+    double n1n2 = n1 * n2;
+    double m4 = a.m4 + b.m4 + n1n2 * (n1 * n1 - n1n2 + n2 * n2) * delta * dn3 +
+                6.0 * (n1 * n1 * b.m2 + n2 * n2 * a.m2) * dn2 + 4.0 * (n1 * b.m3 - n2 * a.m3) * dn;
+    double m3 = a.m3 + b.m3 + n1n2 * (n1 - n2) * delta * dn2 + 3.0 * (n1 * b.m2 - n2 * a.m2) * dn;
+    double m2 = a.m2 + b.m2 + n1n2 * delta * dn;
+    a.m4 = m4; a.m3 = m3; a.m2 = m2;
+    a.count += b.count; a.sum += b.sum;
+    a.vmin = fmin(a.vmin, b.vmin); a.vmax = fmax(a.vmax, b.vmax);
+}
+
+__device__ __forceinline__ StatsPart part_shfl_xor(const StatsPart& p, int m) {
+    StatsPart o;
+    o.count = __shfl_xor_sync(CRICK_FULL, p.count, m);
+    o.sum = shfl_xor_d(p.sum, m); o.vmin = shfl_xor_d(p.vmin, m); o.vmax = shfl_xor_d(p.vmax, m);
+    o.m2 = shfl_xor_d(p.m2, m); o.m3 = shfl_xor_d(p.m3, m); o.m4 = shfl_xor_d(p.m4, m);
+    o.first_idx = __shfl_xor_sync(CRICK_FULL, p.first_idx, m);
+    o.last_nan_idx = __shfl_xor_sync(CRICK_FULL, p.last_nan_idx, m);
+    o.first_value = shfl_xor_d(p.first_value, m);
+    o.last_value = shfl_xor_d(p.last_value, m);
+    o.last_idx = __shfl_xor_sync(CRICK_FULL, p.last_idx, m);
+    return o;
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(256) k_stats_partial(const XT* __restrict__ x,
+                                                       const long long* __restrict__ cnt,
+                                                       long long cnt_scalar, long n,
+                                                       StatsPart* __restrict__ parts) {
+    __shared__ StatsPart s_part[8];
+    const long stride = (long)gridDim.x * blockDim.x;
+    // per-thread shifted power sums around K = first non-NaN value this thread sees
+    double K = 0.0;
+    bool haveK = false;
+    double cN = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, sx = 0.0;
+    long long cnt_i = 0;
+    StatsPart p;
+    part_fresh(p);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = load_x(x, i);
+        p.last_idx = i; p.last_value = v;
+        if (v != v) { p.last_nan_idx = i; continue; }
+        long long c = cnt ? cnt[i] : cnt_scalar;
+        if (i < p.first_idx) { p.first_idx = i; p.first_value = v; }
+        double cd = (double)c;
+        double u = v / cd;  // stats_do_update: u2 = sum2 / n2 (:51)
+        if (!haveK) { K = u; haveK = true; }
+        double d = u - K, d2 = d * d;
+        cN += cd; cnt_i += c; sx += v;
+        s1 += cd * d; s2 += cd * d2; s3 += cd * d2 * d; s4 += cd * d2 * d2;
+        p.vmin = fmin(p.vmin, v); p.vmax = fmax(p.vmax, v);
+    }
+    if (haveK) {
+        double md = s1 / cN;
+        p.count = cnt_i; p.sum = sx;
+        p.m2 = s2 - cN * md * md;
+        p.m3 = s3 - 3.0 * md * s2 + 2.0 * cN * md * md * md;
+        p.m4 = s4 - 4.0 * md * s3 + 6.0 * md * md * s2 - 3.0 * cN * md * md * md * md;
+        if (p.m2 < 0.0) p.m2 = 0.0;
+        if (p.m4 < 0.0) p.m4 = 0.0;
+    }
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        StatsPart o = part_shfl_xor(p, m);
+        // fixed association (lower lane on the left) => deterministic
+        if ((threadIdx.x & m) == 0) part_merge(p, o);
+        else { StatsPart t = o; part_merge(t, p); p = t; }
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) s_part[warp] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatsPart t = s_part[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) part_merge(t, s_part[w]);
+        parts[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_stats_final(StatsState* st, const StatsPart* __restrict__ parts, int nparts) {
+    if (threadIdx.x || blockIdx.x) return;
+    StatsPart t = parts[0];
+    for (int i = 1; i < nparts; ++i) part_merge(t, parts[i]);
+    StatsState T = *st;
+    // homogeneous / first_value bookkeeping of the update loop (:200-205)
+    const bool any_nonnan = t.first_idx != 0x7fffffffffffffffl;
+    if (T.count == 0) {
+        if (any_nonnan) {
+            T.first_value = t.first_value;
+            bool all_eq = (t.vmin == t.vmax) && (t.vmin == t.first_value);
+            bool nan_after = t.last_nan_idx > t.first_idx;
+            if (T.homogeneous && (!all_eq || nan_after)) T.homogeneous = 0;
+        } else if (t.last_idx >= 0) {
+            T.first_value = t.last_value;  // rewritten by every element while count == 0
+        }
+    } else if (t.last_idx >= 0) {
+        bool all_eq = any_nonnan && t.last_nan_idx < 0 && t.vmin == t.vmax && t.vmin == T.first_value;
+        if (T.homogeneous && !all_eq) T.homogeneous = 0;
+    }
+    if (t.count > 0) stats_combine(T, t.count, t.sum, t.vmin, t.vmax, t.m4, t.m3, t.m2);
+    *st = T;
+}
+
+__global__ void k_stats_merge(StatsState* dst, const StatsState* src) {
+    if (threadIdx.x || blockIdx.x) return;
+    StatsState T = *dst;
+    stats_merge_state(T, *src);
+    *dst = T;
+}
+
+}  // namespace crick
+
+using namespace crick;
+
+struct crick_stats {
+    StatsState* d = nullptr;
+    StatsPart* parts = nullptr;
+    int nparts = 0;
+    cudaStream_t own = nullptr, last = nullptr;
+    cudaEvent_t ev = nullptr;
+    std::vector<double> px;
+    std::vector<long long> pc;
+    StatsState mirror;
+    bool mirror_ok = false;
+};
+
+static cudaStream_t ss_stream(crick_stats* s, void* stream) {
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : s->own;
+    if (s->last && s->last != st) {
+        cudaEventRecord(s->ev, s->last);
+        cudaStreamWaitEvent(st, s->ev, 0);
+    }
+    s->last = st;
+    return st;
+}
+
+static int ss_drain(crick_stats* s, cudaStream_t st) {
+    size_t n = s->px.size();
+    if (!n) return 0;
+    unsigned char* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, n * 16, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(stats pending)", e);
+    double* dx = reinterpret_cast<double*>(d);
+    long long* dc = reinterpret_cast<long long*>(d + n * 8);
+    e = cudaMemcpyAsync(dx, s->px.data(), n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dc, s->pc.data(), n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        count_launch();
+        k_stats_seq<double><<<1, 32, 0, st>>>(s->d, dx, dc, 1, (long)n, 0);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(d, st);
+    s->px.clear(); s->pc.clear();
+    s->mirror_ok = false;
+    return e == cudaSuccess ? 0 : fail("stats drain", e);
+}
+
+static int ss_sync(crick_stats* s) {
+    cudaStream_t st = ss_stream(s, nullptr);
+    if (ss_drain(s, st)) return -1;
+    if (s->mirror_ok) return 0;
+    cudaError_t e = cudaMemcpyAsync(&s->mirror, s->d, sizeof(StatsState), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("stats read state", e);
+    s->mirror_ok = true;
+    return 0;
+}
+
+template <typename XT>
+static cudaError_t stats_launch(crick_stats* s, const XT* x, const long long* c, long long cs, long n,
+                                cudaStream_t st) {
+    if (n < kStatsParallelMin) {
+        count_launch();
+        k_stats_seq<XT><<<1, 32, 0, st>>>(s->d, x, c, cs, n, 1);
+        return cudaGetLastError();
+    }
+    long blocks = (n + 256 * 16 - 1) / (256 * 16);
+    if (blocks > s->nparts) blocks = s->nparts;
+    count_launch();
+    k_stats_partial<XT><<<(unsigned)blocks, 256, 0, st>>>(x, c, cs, n, s->parts);
+    count_launch();
+    k_stats_final<<<1, 32, 0, st>>>(s->d, s->parts, (int)blocks);
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+crick_stats_t* crick_stats_new(void) {
+    if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
+    crick_stats* s = new (std::nothrow) crick_stats();
+    if (!s) return nullptr;
+    s->nparts = sm_count() * 8;
+    cudaError_t e = cudaMalloc(&s->d, sizeof(StatsState));
+    if (e == cudaSuccess) e = cudaMalloc(&s->parts, sizeof(StatsPart) * s->nparts);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
+    stats_fresh(s->mirror);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d, &s->mirror, sizeof(StatsState), cudaMemcpyHostToDevice, s->own);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->own);
+    if (e != cudaSuccess) { fail("stats_new", e); crick_stats_free(s); return nullptr; }
+    s->mirror_ok = true;
+    s->last = s->own;
+    return s;
+}
+
+void crick_stats_free(crick_stats_t* s) {
+    if (!s) return;
+    if (s->last) cudaStreamSynchronize(s->last);
+    if (s->own) { cudaStreamSynchronize(s->own); cudaStreamDestroy(s->own); }
+    if (s->ev) cudaEventDestroy(s->ev);
+    if (s->d) cudaFree(s->d);
+    if (s->parts) cudaFree(s->parts);
+    delete s;
+}
+
+int crick_stats_add(crick_stats_t* s, double x, int64_t count) {
+    // stats_add (:92-95) is what SummaryStats.add calls: no homogeneous bookkeeping there
+    // (that lives in the ndarray driver), so NaN is simply dropped and the rest is queued.
+    if (x != x) return 0;
+    s->px.push_back(x);
+    s->pc.push_back(count);
+    s->mirror_ok = false;
+    if (s->px.size() >= (1u << 16)) return ss_drain(s, ss_stream(s, nullptr));
+    return 0;
+}
+
+int crick_stats_update(crick_stats_t* s, const void* x, int x_is_int64, const int64_t* count,
+                       int64_t count_scalar, int64_t n, int x_on_device, int count_on_device,
+                       void* stream) {
+    if (n <= 0) return 0;
+    cudaStream_t st = ss_stream(s, stream);
+    if (ss_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    const void* dx = x;
+    const long long* dc = reinterpret_cast<const long long*>(count);
+    unsigned char* stage = nullptr;
+    cudaError_t e = cudaSuccess;
+    size_t need = (x_on_device ? 0 : (size_t)n * 8) + ((count && !count_on_device) ? (size_t)n * 8 : 0);
+    if (need) {
+        e = cudaMallocAsync(&stage, need, st);
+        if (e != cudaSuccess) return fail("cudaMallocAsync(stats stage)", e);
+        unsigned char* p = stage;
+        if (!x_on_device) {
+            e = cudaMemcpyAsync(p, x, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            dx = p; p += (size_t)n * 8;
+        }
+        if (e == cudaSuccess && count && !count_on_device) {
+            e = cudaMemcpyAsync(p, count, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            dc = reinterpret_cast<const long long*>(p);
+        }
+    }
+    if (e == cudaSuccess) {
+        if (x_is_int64) e = stats_launch<long long>(s, reinterpret_cast<const long long*>(dx), dc, count_scalar, n, st);
+        else e = stats_launch<double>(s, reinterpret_cast<const double*>(dx), dc, count_scalar, n, st);
+    }
+    if (stage) {
+        cudaFreeAsync(stage, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    return e == cudaSuccess ? 0 : fail("stats_update", e);
+}
+
+int crick_stats_merge(crick_stats_t* s, crick_stats_t* const* others, int n_others) {
+    cudaStream_t st = ss_stream(s, nullptr);
+    if (ss_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    for (int i = 0; i < n_others; ++i) {
+        crick_stats* o = others[i];
+        cudaStream_t ost = ss_stream(o, nullptr);
+        if (ss_drain(o, ost)) return -1;
+        cudaError_t e = cudaSuccess;
+        if (o != s) {
+            e = cudaEventRecord(o->ev, ost);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, o->ev, 0);
+        }
+        if (e == cudaSuccess) {
+            count_launch();
+            k_stats_merge<<<1, 32, 0, st>>>(s->d, o->d);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && o != s) {
+            e = cudaEventRecord(s->ev, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, s->ev, 0);
+        }
+        if (e != cudaSuccess) return fail("stats_merge", e);
+    }
+    return 0;
+}
+
+int crick_stats_getstate(crick_stats_t* s, int64_t* count, double* f7, int* homogeneous) {
+    if (ss_sync(s)) return -1;
+    const StatsState& m = s->mirror;
+    *count = m.count;
+    f7[0] = m.sum; f7[1] = m.vmin; f7[2] = m.vmax; f7[3] = m.m2; f7[4] = m.m3; f7[5] = m.m4;
+    f7[6] = m.first_value;
+    *homogeneous = m.homogeneous;
+    return 0;
+}
+
+int crick_stats_setstate(crick_stats_t* s, int64_t count, const double* f7, int homogeneous) {
+    cudaStream_t st = ss_stream(s, nullptr);
+    if (ss_drain(s, st)) return -1;
+    StatsState m;
+    m.count = count; m.sum = f7[0]; m.vmin = f7[1]; m.vmax = f7[2]; m.m2 = f7[3]; m.m3 = f7[4];
+    m.m4 = f7[5]; m.first_value = f7[6]; m.homogeneous = homogeneous ? 1 : 0; m.pad = 0;
+    s->mirror = m;
+    cudaError_t e = cudaMemcpyAsync(s->d, &s->mirror, sizeof(StatsState), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("stats_setstate", e);
+    s->mirror_ok = true;
+    return 0;
+}
+
+// finalisers: scalar host code on the mirrored state (stats_stubs.c:98-136)
+double crick_stats_mean(crick_stats_t* s) {
+    if (ss_sync(s)) return NAN;
+    const StatsState& m = s->mirror;
+    return m.count ? m.sum / m.count : NAN;
+}
+double crick_stats_var(crick_stats_t* s, int64_t ddof) {
+    if (ss_sync(s)) return NAN;
+    const StatsState& m = s->mirror;
+    return m.count ? m.m2 / (m.count - ddof) : NAN;
+}
+double crick_stats_std(crick_stats_t* s, int64_t ddof) { return std::sqrt(crick_stats_var(s, ddof)); }
+double crick_stats_skew(crick_stats_t* s, int bias) {
+    if (ss_sync(s)) return NAN;
+    const StatsState& m = s->mirror;
+    if (m.homogeneous) return NAN;
+    double n = (double)m.count, m2 = m.m2 / m.count, m3 = m.m3 / m.count;
+    double skew = m2 ? m3 / (std::sqrt(m2) * m2) : 0;
+    if (!bias && n > 2 && m2 > 0) return std::sqrt((n - 1) * n) / (n - 2) * skew;
+    return skew;
+}
+double crick_stats_kurt(crick_stats_t* s, int fisher, int bias) {
+    if (ss_sync(s)) return NAN;
+    const StatsState& m = s->mirror;
+    if (m.homogeneous) return NAN;
+    double n = (double)m.count, m2 = m.m2 / m.count, m4 = m.m4 / m.count;
+    double kurt = m2 ? m4 / (m2 * m2) : 0;
+    if (!bias && n > 3 && m2 > 0) kurt = ((n * n - 1) * kurt - 9 * n + 15) / ((n - 2) * (n - 3));
+    return fisher ? kurt - 3 : kurt;
+}
+
+int crick_stats_export_record(crick_stats_t* s, double* r) {
+    if (ss_sync(s)) return -1;
+    const StatsState& m = s->mirror;
+    r[0] = (double)m.count; r[1] = m.sum; r[2] = m.vmin; r[3] = m.vmax; r[4] = m.m2; r[5] = m.m3;
+    r[6] = m.m4; r[7] = (double)m.homogeneous; r[8] = m.first_value;
+    return 0;
+}
+
+int crick_stats_merge_record(crick_stats_t* s, const double* r) {
+    cudaStream_t st = ss_stream(s, nullptr);
+    if (ss_drain(s, st)) return -1;
+    StatsState o;
+    o.count = (long long)r[0]; o.sum = r[1]; o.vmin = r[2]; o.vmax = r[3]; o.m2 = r[4]; o.m3 = r[5];
+    o.m4 = r[6]; o.homogeneous = r[7] != 0.0; o.first_value = r[8]; o.pad = 0;
+    StatsState* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, sizeof(StatsState), st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(stats record)", e);
+    e = cudaMemcpyAsync(d, &o, sizeof(o), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        count_launch();
+        k_stats_merge<<<1, 32, 0, st>>>(s->d, d);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    s->mirror_ok = false;
+    return e == cudaSuccess ? 0 : fail("stats_merge_record", e);
+}
+
+}  // extern "C"

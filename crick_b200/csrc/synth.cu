@@ -1,0 +1,57 @@
+// crick_b200/csrc/synth.cu -- synthetic, counter-based input generators for
+// bench.py and the GPU tests (NOT part of the hot path).  Element i of the
+// stream depends only on (seed, i), so any sharding of a stream across GPUs
+// reproduces the same values.
+#include "kernels.h"
+
+namespace crick {
+
+__device__ __forceinline__ unsigned long long sm64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(unsigned long long r) {  // (0, 1)
+    return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// kind 0: x = exp(N(0,1)) (lognormal), w = U(0.5, 1.5)
+// kind 1: x = U(0, 1),                 w = U(0.5, 1.5)
+// kind 2: x = N(0, 1),                 w = U(0.5, 1.5)
+// kind 3: x = Zipf(1.1)-like heavy-tailed positive integers stored as f64 (inverse-CDF of the
+//         continuous Pareto with the same tail, floored), w = 1
+__global__ void k_synth(double* __restrict__ x, double* __restrict__ w, long n,
+                        unsigned long long seed, long offset, int kind) {
+    long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long g = (unsigned long long)(i + offset);
+        unsigned long long r0 = sm64(seed ^ sm64(3 * g));
+        unsigned long long r1 = sm64(seed ^ sm64(3 * g + 1));
+        unsigned long long r2 = sm64(seed ^ sm64(3 * g + 2));
+        double u0 = u01(r0), u1 = u01(r1), u2 = u01(r2);
+        double v;
+        if (kind == 1) v = u0;
+        else if (kind == 3) {
+            double p = pow(u0, -10.0);           // Pareto(alpha = 0.1): tail ~ k^-1.1
+            v = p > 9.0e18 ? 9.0e18 : floor(p);
+        } else {
+            double nrm = sqrt(-2.0 * log(u0)) * cospi(2.0 * u1);
+            v = (kind == 0) ? exp(nrm) : nrm;
+        }
+        x[i] = v;
+        if (w) w[i] = (kind == 3) ? 1.0 : 0.5 + u2;
+    }
+}
+
+cudaError_t launch_synth(double* x, double* w, long n, unsigned long long seed, long offset,
+                         int kind, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    count_launch();
+    k_synth<<<(unsigned)blocks, 256, 0, st>>>(x, w, n, seed, offset, kind);
+    return cudaGetLastError();
+}
+
+}  // namespace crick

@@ -1,0 +1,786 @@
+// crick_b200/csrc/tdigest_parallel.cu
+//
+// Parallel "k-bucket" update for one huge stream (SURVEY.md 2.3 K1/K3/K5, 7 option (c)).
+//
+// The reference folds values into centroids 42 at a time through a strictly
+// sequential chain (tdigest_stubs.c:219-298); 1e9 values would be 23.8 M
+// dependent flushes.  A centroid, however, is only (sum w, sum w*x) over a
+// contiguous quantile range, and both sums are order independent.  So:
+//
+//   1. k_sample        strided+hashed sample of S (x, w) pairs            (reads S*16 B)
+//   2. k_bitonic_*     sort the sample by x (S = 16 Ki or 64 Ki)
+//   3. k_make_edges    weighted sample quantiles at the k-scale grid
+//                      q_j = sin^2(pi*j/(2*ov*c)), j = 1..ov*c-1  (ov sub-buckets
+//                      per unit of k, so NO asin per element), heavy duplicates get a
+//                      bucket of their own [v, nextafter(v)); plus a 4096-cell lookup
+//                      table over the order-preserving bit pattern of x
+//   4. k_bin_accumulate  THE HOT KERNEL: every value is read exactly once from HBM
+//                      (128-bit streaming loads), filtered like tdigest_add (:285),
+//                      mapped to its bucket (one table probe + 0-2 edge compares) and
+//                      accumulated into warp-private (sum w, sum w*x) arrays in shared
+//                      memory -- no atomics: lanes of a warp that hit the same bucket
+//                      are serialised with __match_any_sync.
+//   5. k_finalize      bucket sums -> <= ov*c weighted points in sorted order, which are
+//                      merged into the digest with the reference's own greedy k-scale
+//                      merge (warp_merge_sorted == tdigest_flush phases 2-5).
+//
+// Result: the digest the reference would produce had it been handed the
+// pre-aggregated bucket points in one flush.  Bit parity with the sequential
+// reference is impossible by construction (different clustering); parity here
+// is (a) bucket sums vs a CPU restatement of the same partition at 1e-12 and
+// (b) rank error <= the reference's on the same data (tests/test_parallel.py).
+#include "kernels.h"
+#include "tdigest_ref.cuh"
+
+namespace crick {
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+constexpr int kNC = 4096;        // lookup-table cells
+constexpr int kEMax = 1024;      // max edges (buckets - 1)
+constexpr int kBPad = kEMax + 8; // row stride of the per-CTA partial sums
+constexpr long kSMax = 65536;    // max sample size
+constexpr int kSortChunk = 4096; // elements sorted per CTA in shared memory
+
+struct ParHeader {
+    int E;       // number of edges; buckets = E + 1, bucket b = [edge[b-1], edge[b])
+    int shift;   // cell = ((key - ubase) >> shift) + 1
+    unsigned long long ubase;
+    long S;      // sample length (power of two)
+    int ncta;    // CTAs that wrote partials
+    int pad;
+    double sample_total;
+};
+
+struct ParLayout {
+    ParHeader* hdr;
+    double* edges;       // [kEMax]
+    unsigned* tab;       // [kNC]   lo | hi << 16
+    double* sx;          // [kSMax]
+    double* sw;          // [kSMax]
+    double* cw;          // [kSMax]
+    double2* partial;    // [ncta_max * kBPad]
+    double2* minmax;     // [ncta_max]
+    unsigned char* fin;  // finalize workspace (global fallback)
+    size_t fin_bytes;
+};
+
+static int ov_for(double comp) {
+    int c = (int)ceil(comp);
+    int ov = kEMax / c;
+    if (ov > 4) ov = 4;
+    if (ov < 1) ov = 1;
+    return ov;
+}
+static int bmax_for(double comp) { return ov_for(comp) * (int)ceil(comp); }
+static int mmax_for(double comp) { return 2 * bmax_for(comp) + 2 * (int)ceil(comp) + 8; }
+
+static size_t fin_ws_bytes(int cap, int mmax) {
+    // cen[cap] + sb[mmax] + items[cap+mmax] + kend + start
+    size_t t = (size_t)cap + mmax;
+    size_t b = (size_t)cap * 16 + (size_t)mmax * 16 + t * 16 + t * 8 + (t + 1) * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t parallel_scratch_bytes(double comp, int sm_count) {
+    int cap = 2 * (int)ceil(comp);
+    size_t b = 256;
+    b += sizeof(double) * kEMax + sizeof(unsigned) * kNC;
+    b += 3 * sizeof(double) * kSMax;
+    b += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
+    b += sizeof(double2) * (size_t)(2 * sm_count);
+    b += fin_ws_bytes(cap, mmax_for(comp)) + 64;
+    return b;
+}
+
+static ParLayout carve(void* scratch, double comp, int sm_count) {
+    ParLayout L;
+    unsigned char* p = reinterpret_cast<unsigned char*>(scratch);
+    L.hdr = reinterpret_cast<ParHeader*>(p); p += 256;
+    L.edges = reinterpret_cast<double*>(p); p += sizeof(double) * kEMax;
+    L.tab = reinterpret_cast<unsigned*>(p); p += sizeof(unsigned) * kNC;
+    L.sx = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.sw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.cw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.partial = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
+    L.minmax = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count);
+    L.fin = p;
+    L.fin_bytes = fin_ws_bytes(2 * (int)ceil(comp), mmax_for(comp));
+    return L;
+}
+
+double* parallel_sample_x(void* scratch) {
+    return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256 +
+                                     sizeof(double) * kEMax + sizeof(unsigned) * kNC);
+}
+double* parallel_sample_w(void* scratch) { return parallel_sample_x(scratch) + kSMax; }
+long parallel_sample_capacity(void*) { return kSMax; }
+
+// next representable double above / below a finite x (zeros are canonical +0.0)
+__device__ __forceinline__ double next_up(double x) {
+    if (x == 0.0) return __longlong_as_double(1ll);
+    long long b = __double_as_longlong(x);
+    return __longlong_as_double(x > 0.0 ? b + 1 : b - 1);
+}
+__device__ __forceinline__ double next_down(double x) {
+    if (x == 0.0) return __longlong_as_double((long long)0x8000000000000001ull);
+    long long b = __double_as_longlong(x);
+    return __longlong_as_double(x > 0.0 ? b - 1 : b + 1);
+}
+
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// 1. sample: element i comes from segment i of n/S, at a hashed offset (so a
+// periodic input cannot alias with the stride).  Rejected values (tdigest_add's
+// filter, :285) become (+inf, 0) and sort to the end.
+__global__ void k_sample(const double* __restrict__ X, const double* __restrict__ W, double wsc,
+                         long n, long S, double* __restrict__ sx, double* __restrict__ sw,
+                         ParHeader* hdr) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) hdr->S = S;
+    if (i >= S) return;
+    long seg = n / S;
+    double x = INFINITY, w = 0.0;
+    if (seg > 0) {
+        long pos = i * seg + (long)(mix64((unsigned long long)i) % (unsigned long long)seg);
+        double xv = X[pos];
+        double wv = W ? W[pos] : wsc;
+        if (is_finite_d(xv) && !(wv <= DBL_EPSILON)) { x = xv + 0.0; w = wv; }
+    } else if (i < n) {
+        double xv = X[i];
+        double wv = W ? W[i] : wsc;
+        if (is_finite_d(xv) && !(wv <= DBL_EPSILON)) { x = xv + 0.0; w = wv; }
+    }
+    sx[i] = x;
+    sw[i] = w;
+}
+
+// 2. bitonic sort of (key, value) pairs, ascending by key.
+__device__ __forceinline__ void ce(double& ka, double& va, double& kb, double& vb, bool asc) {
+    bool sw = asc ? (kb < ka) : (ka < kb);
+    if (sw) { double t = ka; ka = kb; kb = t; t = va; va = vb; vb = t; }
+}
+
+// all stages with stride < kSortChunk for the given k range, inside shared memory
+// mode 0: full local sort (k = 2 .. kSortChunk); mode 1: merge tail of level K (j = kSortChunk/2 .. 1)
+__global__ void __launch_bounds__(512) k_bitonic_local(double* __restrict__ keys,
+                                                       double* __restrict__ vals, long K, int mode) {
+    double* sk = reinterpret_cast<double*>(smem_raw);
+    double* sv = sk + kSortChunk;
+    const long base = (long)blockIdx.x * kSortChunk;
+    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) {
+        sk[i] = keys[base + i];
+        sv[i] = vals[base + i];
+    }
+    __syncthreads();
+    long k0 = mode == 0 ? 2 : K;
+    long k1 = mode == 0 ? kSortChunk : K;
+    for (long k = k0; k <= k1; k <<= 1) {
+        for (int j = (int)((k >> 1) < kSortChunk ? (k >> 1) : (kSortChunk >> 1)); j > 0; j >>= 1) {
+            for (int p = threadIdx.x; p < kSortChunk / 2; p += blockDim.x) {
+                int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                int q = i | j;
+                bool asc = (((base + i) & k) == 0);
+                double ka = sk[i], va = sv[i], kb = sk[q], vb = sv[q];
+                ce(ka, va, kb, vb, asc);
+                sk[i] = ka; sv[i] = va; sk[q] = kb; sv[q] = vb;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) {
+        keys[base + i] = sk[i];
+        vals[base + i] = sv[i];
+    }
+}
+
+__global__ void k_bitonic_global(double* __restrict__ keys, double* __restrict__ vals, long L,
+                                 long j, long k) {
+    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L / 2) return;
+    long i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+    long q = i | j;
+    bool asc = ((i & k) == 0);
+    double ka = keys[i], va = vals[i], kb = keys[q], vb = vals[q];
+    bool sw = asc ? (kb < ka) : (ka < kb);
+    if (sw) { keys[i] = kb; vals[i] = vb; keys[q] = ka; vals[q] = va; }
+}
+
+static cudaError_t sort_sample(double* keys, double* vals, long L, cudaStream_t st) {
+    size_t smem = (size_t)kSortChunk * 16;
+    cudaError_t e = cudaFuncSetAttribute(k_bitonic_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned nchunk = (unsigned)(L / kSortChunk);
+    count_launch();
+    k_bitonic_local<<<nchunk, 512, smem, st>>>(keys, vals, 0, 0);
+    for (long k = 2L * kSortChunk; k <= L; k <<= 1) {
+        for (long j = k >> 1; j >= kSortChunk; j >>= 1) {
+            count_launch();
+            k_bitonic_global<<<(unsigned)((L / 2 + 255) / 256), 256, 0, st>>>(keys, vals, L, j, k);
+        }
+        count_launch();
+        k_bitonic_local<<<nchunk, 512, smem, st>>>(keys, vals, k, 1);
+    }
+    return cudaGetLastError();
+}
+
+// 3. edges + lookup table.  Single CTA, 1024 threads.
+__device__ __forceinline__ int cell_of(unsigned long long key, unsigned long long ubase, int shift) {
+    if (key < ubase) return 0;
+    unsigned long long c = ((key - ubase) >> shift) + 1ull;
+    return c > (unsigned long long)(kNC - 1) ? (kNC - 1) : (int)c;
+}
+
+__global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const double* __restrict__ sx,
+                                                     const double* __restrict__ sw,
+                                                     double* __restrict__ cw, double* __restrict__ edges,
+                                                     unsigned* __restrict__ tab, double comp, int ov) {
+    __shared__ double s_part[1024];
+    __shared__ double s_raw[kEMax];
+    __shared__ int s_cnt[kEMax];
+    __shared__ int s_scan[1024];
+    __shared__ int s_E;
+    const int tid = threadIdx.x;
+    const long S = hdr->S;
+    const long per = S / 1024 > 0 ? S / 1024 : 1;
+    // a. inclusive scan of sample weights (fixed order => deterministic)
+    {
+        long lo = (long)tid * per, hi = lo + per;
+        if (hi > S) hi = S;
+        double s = 0.0;
+        for (long i = lo; i < hi; ++i) s += sw[i];
+        s_part[tid] = (lo < S) ? s : 0.0;
+        __syncthreads();
+        if (tid == 0) {
+            double run = 0.0;
+            for (int t = 0; t < 1024; ++t) { double v = s_part[t]; s_part[t] = run; run += v; }
+        }
+        __syncthreads();
+        double run = s_part[tid];
+        for (long i = lo; i < hi; ++i) { run += sw[i]; cw[i] = run; }
+    }
+    __syncthreads();
+    const double Wt = cw[S - 1];
+    const int c = (int)ceil(comp);
+    const int E0 = ov * c - 1;
+    // b. raw edges at the k-scale grid
+    for (int j = tid; j < E0; j += blockDim.x) {
+        double kq = (double)(j + 1) / (double)ov;                 // k in (0, c)
+        double sn = sin(CRICK_PI_2 * kq / comp);
+        double q = sn * sn;                                        // k^-1(kq)
+        if (q > 1.0) q = 1.0;
+        double target = q * Wt;
+        long lo = 0, hi = S - 1;                                   // first i with cw[i] >= target
+        while (lo < hi) {
+            long mid = (lo + hi) >> 1;
+            if (cw[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        double e = sx[lo];
+        s_raw[j] = e;
+    }
+    __syncthreads();
+    // c. dedupe; a value chosen more than once is "heavy" and gets [v, nextafter(v))
+    for (int j = tid; j < E0; j += blockDim.x) {
+        double v = s_raw[j];
+        int cnt = 0;
+        bool first = (j == 0) || (s_raw[j - 1] != v);
+        if (first && is_finite_d(v) && Wt > 0.0) {
+            cnt = 1;
+            if (j + 1 < E0 && s_raw[j + 1] == v) {
+                int jn = j + 1;
+                while (jn < E0 && s_raw[jn] == v) ++jn;
+                double nx = next_up(v);
+                if (is_finite_d(nx) && !(jn < E0 && s_raw[jn] == nx)) cnt = 2;
+            }
+        }
+        s_cnt[j] = cnt;
+    }
+    __syncthreads();
+    // exclusive scan of s_cnt (E0 <= 1023): thread t owns element t
+    {
+        int v = (tid < E0) ? s_cnt[tid] : 0;
+        s_scan[tid] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            int o = (tid >= d) ? s_scan[tid - d] : 0;
+            __syncthreads();
+            s_scan[tid] += o;
+            __syncthreads();
+        }
+        int excl = s_scan[tid] - v;
+        if (tid < E0 && v > 0) {
+            double e = s_raw[tid];
+            edges[excl] = e;
+            if (v == 2) edges[excl + 1] = next_up(e);
+        }
+        if (tid == 1023) s_E = s_scan[1023];
+    }
+    __syncthreads();
+    const int E = s_E;
+    // d. lookup table over the ordered bit pattern
+    unsigned long long ubase = 0;
+    int shift = 0;
+    if (E > 0) {
+        ubase = ordered_key(edges[0]);
+        unsigned long long span = ordered_key(edges[E - 1]) - ubase;
+        while (shift < 63 && ((span >> shift) + 1ull) > (unsigned long long)(kNC - 2)) ++shift;
+    }
+    for (int cell = tid; cell < kNC; cell += blockDim.x) {
+        // lo = #edges with cell_of(e) < cell ; hi = #edges with cell_of(e) <= cell
+        int a = 0, b = E;
+        while (a < b) {
+            int mid = (a + b) >> 1;
+            if (cell_of(ordered_key(edges[mid]), ubase, shift) < cell) a = mid + 1; else b = mid;
+        }
+        int lo = a;
+        b = E;
+        while (a < b) {
+            int mid = (a + b) >> 1;
+            if (cell_of(ordered_key(edges[mid]), ubase, shift) <= cell) a = mid + 1; else b = mid;
+        }
+        tab[cell] = (unsigned)lo | ((unsigned)a << 16);
+    }
+    if (tid == 0) {
+        hdr->E = E;
+        hdr->shift = shift;
+        hdr->ubase = ubase;
+        hdr->sample_total = Wt;
+        hdr->ncta = 0;
+    }
+}
+
+// 4. THE HOT KERNEL -----------------------------------------------------------
+struct AccCtx {
+    const double* edges;   // shared
+    const unsigned* tab;   // shared
+    double2* acc;          // shared, this warp's private bucket sums
+    unsigned long long ubase;
+    int shift;
+    int E;
+};
+
+__device__ __forceinline__ int bucket_of(const AccCtx& c, double xx) {
+    unsigned long long key = ordered_key(xx);
+    int cell = cell_of(key, c.ubase, c.shift);
+    unsigned t = c.tab[cell];
+    int lo = (int)(t & 0xffffu), hi = (int)(t >> 16);
+    while (lo < hi) {  // #edges <= xx, restricted to the cell's candidates
+        int mid = (lo + hi) >> 1;
+        if (c.edges[mid] <= xx) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Add (x, w) of every lane into the warp-private bucket sums.  Lanes that land in
+// the same bucket are serialised by rank inside their __match_any_sync group.
+__device__ __forceinline__ void warp_accumulate(const AccCtx& c, double x, double w, bool ok,
+                                                int lane, double& vmin, double& vmax) {
+    __syncwarp();       // order this step's shared-memory updates after the previous step's
+    int b = -1 - lane;  // unique per lane => never matches
+    double xx = x + 0.0;  // -0.0 -> +0.0 so both zeros share a bucket
+    if (ok) {
+        b = bucket_of(c, xx);
+        vmin = fmin(vmin, x);
+        vmax = fmax(vmax, x);
+    }
+    unsigned peers = __match_any_sync(CRICK_FULL, b);
+    int rank = __popc(peers & ((1u << lane) - 1u));
+    int maxrank = __popc(peers) - 1;
+    for (int r = 0;; ++r) {
+        if (ok && rank == r) {
+            double2 a = c.acc[b];
+            a.x = __dadd_rn(a.x, w);
+            a.y = __fma_rn(w, xx, a.y);
+            c.acc[b] = a;
+        }
+        if (!__any_sync(CRICK_FULL, ok && maxrank > r)) break;
+        __syncwarp();
+    }
+}
+
+template <bool HAS_W, bool VEC>
+__global__ void __launch_bounds__(1024, 1) k_bin_accumulate(const double* __restrict__ X,
+                                                            const double* __restrict__ W, double wsc,
+                                                            long n, ParHeader* hdr,
+                                                            const double* __restrict__ g_edges,
+                                                            const unsigned* __restrict__ g_tab,
+                                                            double2* __restrict__ partial,
+                                                            double2* __restrict__ minmax, int bmax,
+                                                            int accumulate_into) {
+    // shared: tab[kNC] | edges[bmax] | acc[nwarps][bmax]
+    unsigned* s_tab = reinterpret_cast<unsigned*>(smem_raw);
+    double* s_edges = reinterpret_cast<double*>(smem_raw + sizeof(unsigned) * kNC);
+    double2* s_acc = reinterpret_cast<double2*>(s_edges + bmax);
+    __shared__ double s_min[32], s_max[32];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int E = hdr->E;
+    const int B = E + 1;
+    for (int i = threadIdx.x; i < kNC; i += blockDim.x) s_tab[i] = g_tab[i];
+    for (int i = threadIdx.x; i < E; i += blockDim.x) s_edges[i] = g_edges[i];
+    for (int i = threadIdx.x; i < nwarps * bmax; i += blockDim.x) s_acc[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    AccCtx c;
+    c.edges = s_edges; c.tab = s_tab; c.acc = s_acc + (size_t)warp * bmax;
+    c.ubase = hdr->ubase; c.shift = hdr->shift; c.E = E;
+    double vmin = INFINITY, vmax = -INFINITY;
+
+    constexpr int U = 4;                       // loads in flight per lane per array
+    constexpr int PER = VEC ? 2 : 1;           // doubles per load
+    constexpr long TILE = 32L * PER * U;       // values per warp iteration
+    const long ntiles = n / TILE;
+    const long gw = (long)blockIdx.x * nwarps + warp;
+    const long tw = (long)gridDim.x * nwarps;
+    for (long t = gw; t < ntiles; t += tw) {
+        const long base = t * TILE;
+        double xs[U * PER], ws[U * PER];
+        if (VEC) {
+            const double2* x2 = reinterpret_cast<const double2*>(X + base);
+            const double2* w2 = reinterpret_cast<const double2*>(W + base);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double2 a = ldg_stream2(x2 + u * 32 + lane);
+                xs[2 * u] = a.x; xs[2 * u + 1] = a.y;
+            }
+            if (HAS_W) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double2 a = ldg_stream2(w2 + u * 32 + lane);
+                    ws[2 * u] = a.x; ws[2 * u + 1] = a.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) xs[u] = ldg_stream1(X + base + u * 32 + lane);
+            if (HAS_W) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) ws[u] = ldg_stream1(W + base + u * 32 + lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U * PER; ++u) {
+            double w = HAS_W ? ws[u] : wsc;
+            bool ok = is_finite_d(xs[u]) && !(w <= DBL_EPSILON);
+            warp_accumulate(c, xs[u], w, ok, lane, vmin, vmax);
+        }
+    }
+    // ragged tail (< TILE values): warp 0 of CTA 0
+    if (gw == 0) {
+        for (long i = ntiles * TILE + lane; i < ((n + 31) / 32) * 32; i += 32) {
+            bool in = i < n;
+            double x = in ? X[i] : 0.0;
+            double w = HAS_W ? (in ? W[i] : 0.0) : wsc;
+            bool ok = in && is_finite_d(x) && !(w <= DBL_EPSILON);
+            warp_accumulate(c, x, w, ok, lane, vmin, vmax);
+        }
+    }
+    // CTA reduction in fixed warp order -> deterministic partials
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        vmin = fmin(vmin, shfl_xor_d(vmin, d));
+        vmax = fmax(vmax, shfl_xor_d(vmax, d));
+    }
+    if (lane == 0) { s_min[warp] = vmin; s_max[warp] = vmax; }
+    __syncthreads();
+    double2* row = partial + (size_t)blockIdx.x * kBPad;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        double sw_ = 0.0, sx_ = 0.0;
+        for (int wv = 0; wv < nwarps; ++wv) {
+            double2 a = s_acc[(size_t)wv * bmax + b];
+            sw_ += a.x; sx_ += a.y;
+        }
+        if (accumulate_into) { double2 o = row[b]; sw_ += o.x; sx_ += o.y; }
+        row[b] = make_double2(sw_, sx_);
+    }
+    if (threadIdx.x == 0) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (int wv = 0; wv < nwarps; ++wv) { mn = fmin(mn, s_min[wv]); mx = fmax(mx, s_max[wv]); }
+        if (accumulate_into) { double2 o = minmax[blockIdx.x]; mn = fmin(mn, o.x); mx = fmax(mx, o.y); }
+        minmax[blockIdx.x] = make_double2(mn, mx);
+        if (blockIdx.x == 0) hdr->ncta = gridDim.x;
+    }
+}
+
+// 5. finalize: bucket sums -> sorted weighted points -> greedy k-scale merge.
+__global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeader* hdr,
+                                                   const double* __restrict__ edges,
+                                                   const double2* __restrict__ partial,
+                                                   const double2* __restrict__ minmax,
+                                                   unsigned char* gws, int mmax, int use_smem) {
+    __shared__ int s_scan[1024 + 1];
+    __shared__ double s_mm[2];
+    __shared__ int s_m;
+    __shared__ double s_W;
+    const int tid = threadIdx.x;
+    const int E = hdr->E;
+    const int B = E + 1;
+    const int ncta = hdr->ncta;
+    const int cap = v.cap;
+    unsigned char* wsbase = use_smem ? smem_raw : gws;
+    // custom carve: cen[cap] | sb[mmax] | items[cap+mmax] | kend | start  (no unsorted buf)
+    WarpWS ws;
+    {
+        size_t t = (size_t)cap + mmax;
+        ws.cen = reinterpret_cast<double2*>(wsbase);
+        ws.sb = ws.cen + cap;
+        ws.buf = ws.sb;
+        ws.items = ws.sb + mmax;
+        ws.kend = reinterpret_cast<double*>(ws.items + t);
+        ws.start = reinterpret_cast<int*>(ws.kend + t);
+    }
+    // a. reduce partials over CTAs (fixed order) and the batch total weight
+    double bw = 0.0, bs = 0.0;
+    const int b = tid;  // B <= 1024 (ov*c <= kEMax): one thread per bucket
+    auto reduce_bucket = [&](int bb, double& w_, double& s_) {
+        w_ = 0.0; s_ = 0.0;
+        for (int cta = 0; cta < ncta; ++cta) {
+            double2 a = partial[(size_t)cta * kBPad + bb];
+            w_ += a.x; s_ += a.y;
+        }
+    };
+    if (b < B) reduce_bucket(b, bw, bs);
+    if (tid == 0) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (int cta = 0; cta < ncta; ++cta) {
+            mn = fmin(mn, minmax[cta].x); mx = fmax(mx, minmax[cta].y);
+        }
+        s_mm[0] = mn; s_mm[1] = mx;
+    }
+    // batch weight: sum of bucket weights in bucket order (deterministic)
+    s_scan[tid] = 0;
+    __syncthreads();
+    __shared__ double s_bw[1024];
+    if (b < B) s_bw[b] = bw;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < B; ++i) t += s_bw[i];
+        s_W = t;
+    }
+    __syncthreads();
+    const double Wb = s_W;          // weight of this batch
+    const double mn = s_mm[0], mx = s_mm[1];
+    // b. pieces per bucket.  A single-valued bucket [v, nextafter(v)) heavier than
+    // half a k-unit is split into equal pieces with the same mean, so that the
+    // digest keeps several centroids on a heavy duplicate like the reference does.
+    auto pieces_of = [&](int bb, double w_, double before) -> int {
+        if (!(w_ > 0.0)) return 0;
+        bool single = bb >= 1 && bb <= E - 1 && edges[bb] == next_up(edges[bb - 1]);
+        if (!single) return 1;
+        double q0 = before / Wb, q1 = (before + w_) / Wb;
+        double span = kscale(v.comp, q1) - kscale(v.comp, q0);
+        int p = (int)ceil(span * 2.0);
+        return p < 1 ? 1 : p;
+    };
+    // cumulative weight before each bucket (exclusive, bucket order)
+    __shared__ double s_before[1024];
+    if (tid == 0) {
+        double run = 0.0;
+        for (int i = 0; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
+    }
+    __syncthreads();
+    int np = (b < B) ? pieces_of(b, bw, s_before[b]) : 0;
+    // exclusive scan over 1024 buckets
+    s_scan[tid] = np;
+    __syncthreads();
+    for (int dd = 1; dd < 1024; dd <<= 1) {
+        int o = (tid >= dd) ? s_scan[tid - dd] : 0;
+        __syncthreads();
+        s_scan[tid] += o;
+        __syncthreads();
+    }
+    int pos = s_scan[tid] - np;
+    int total1024 = s_scan[1023];
+    auto emit = [&](int bb, double w_, double s_, int p, int at) {
+        if (p <= 0) return;
+        double lo = (bb == 0) ? mn : edges[bb - 1];
+        double hi = (bb == E) ? mx : next_down(edges[bb]);
+        double mean = s_ / w_;
+        if (p > 1 || (bb >= 1 && bb < E && edges[bb] == next_up(edges[bb - 1])))
+            mean = edges[bb - 1];                    // every member equals the left edge
+        mean = fmin(fmax(mean, lo), hi);
+        if (at + p > mmax) p = mmax - at > 0 ? mmax - at : 0;
+        double each = w_ / (double)p;
+        for (int k = 0; k < p; ++k) {
+            double wk = (k == p - 1) ? (w_ - each * (double)(p - 1)) : each;
+            ws.sb[at + k] = make_double2(mean, wk);
+        }
+    };
+    if (b < B) emit(b, bw, bs, np, pos);
+    if (tid == 0) {
+        int m = total1024;
+        s_m = m > mmax ? mmax : m;
+    }
+    __syncthreads();
+    // c. merge into the digest: warp 0 only (the greedy chain is sequential)
+    if (tid < 32) {
+        const int lane = tid;
+        const int m = s_m;
+        Hdr h;
+        const DevHdr dh = v.hdr[d];
+        h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
+        const double2* cg = v.cen + d * (long)cap;
+        for (int i = lane; i < h.n; i += 32) ws.cen[i] = cg[i];
+        __syncwarp();
+        if (m > 0) {
+            // batch weight in item order, sequential (pieces re-sum to the bucket weight
+            // only up to rounding, so sum what is actually merged)
+            double bt = 0.0;
+            if (lane == 0) for (int i = 0; i < m; ++i) bt = __dadd_rn(bt, ws.sb[i].y);
+            bt = shfl_d(bt, 0);
+            if (h.vmin > mn) h.vmin = mn;
+            if (h.vmax < mx) h.vmax = mx;
+            h.total = __dadd_rn(h.total, bt);
+            warp_merge_sorted(ws, v.comp, h, m, cap, lane);
+            double2* cgo = v.cen + d * (long)cap;
+            for (int i = lane; i < h.n; i += 32) cgo[i] = ws.cen[i];
+            if (lane == 0) {
+                DevHdr o = dh;
+                o.vmin = h.vmin; o.vmax = h.vmax; o.total = h.total; o.btotal = 0.0;
+                o.n = h.n; o.bn = 0;
+                v.hdr[d] = o;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+long parallel_sample_pos(long i, long n, long S) {
+    long seg = n / S;
+    if (seg <= 0) return i;
+    return i * seg + (long)(mix64((unsigned long long)i) % (unsigned long long)seg);
+}
+long parallel_sample_len(long n);
+static long sample_len(long n) { return parallel_sample_len(n); }
+long parallel_sample_len(long n) {
+    long S = (n >= (1L << 22)) ? kSMax : 16384;
+    while (S > kSortChunk && S * 4 > n) S >>= 1;
+    return S;
+}
+
+static cudaError_t edges_from_sorted_sample(const BatchView& v, ParLayout& L, long S,
+                                            cudaStream_t st) {
+    cudaError_t e = sort_sample(L.sx, L.sw, S, st);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    k_make_edges<<<1, 1024, 0, st>>>(L.hdr, L.sx, L.sw, L.cw, L.edges, L.tab, v.comp,
+                                     ov_for(v.comp));
+    return cudaGetLastError();
+}
+
+// host supplies ns (<= kSMax) sample pairs already copied into parallel_sample_x/w
+__global__ void k_pad_sample(double* sx, double* sw, long ns, long S, ParHeader* hdr) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) hdr->S = S;
+    if (i >= S) return;
+    if (i >= ns) { sx[i] = INFINITY; sw[i] = 0.0; return; }
+    double x = sx[i], w = sw[i];
+    if (!(is_finite_d(x) && !(w <= DBL_EPSILON))) { sx[i] = INFINITY; sw[i] = 0.0; }
+    else sx[i] = x + 0.0;
+}
+
+cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratch,
+                                       cudaStream_t st) {
+    ParLayout L = carve(scratch, v.comp, 1);
+    long S = kSortChunk;
+    while (S < ns && S < kSMax) S <<= 1;
+    count_launch();
+    k_pad_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(L.sx, L.sw, ns, S, L.hdr);
+    return edges_from_sorted_sample(v, L, S, st);
+}
+
+static int acc_warps(int bmax) {
+    size_t fixed = sizeof(unsigned) * kNC + sizeof(double) * (size_t)bmax + 1024;
+    size_t budget = 200 * 1024;
+    int nw = (int)((budget - fixed) / ((size_t)bmax * 16));
+    if (nw > 32) nw = 32;
+    nw &= ~3;
+    if (nw < 4) nw = 4;
+    return nw;
+}
+
+static cudaError_t accumulate_impl(const BatchView& v, const double* X, const double* W, double wsc,
+                                   long n, void* scratch, int sm_count, cudaStream_t st,
+                                   int accumulate_into) {
+    ParLayout L = carve(scratch, v.comp, sm_count);
+    const int bmax = (bmax_for(v.comp) + 2) & ~1;  // even: keeps the double2 rows 16-byte aligned
+    const int nw = acc_warps(bmax);
+    size_t smem = sizeof(unsigned) * kNC + sizeof(double) * (size_t)bmax + (size_t)nw * bmax * 16;
+    smem = (smem + 15) & ~(size_t)15;
+    const bool vec = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+    const unsigned grid = (unsigned)sm_count;
+    const unsigned block = (unsigned)nw * 32;
+    cudaError_t e;
+#define CRICK_LAUNCH_ACC(HW, VC)                                                                  \
+    e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)smem);                                                          \
+    if (e != cudaSuccess) return e;                                                               \
+    count_launch();                                                                               \
+    k_bin_accumulate<HW, VC><<<grid, block, smem, st>>>(X, W, wsc, n, L.hdr, L.edges, L.tab,      \
+                                                        L.partial, L.minmax, bmax, accumulate_into)
+    if (W) { if (vec) { CRICK_LAUNCH_ACC(true, true); } else { CRICK_LAUNCH_ACC(true, false); } }
+    else { if (vec) { CRICK_LAUNCH_ACC(false, true); } else { CRICK_LAUNCH_ACC(false, false); } }
+#undef CRICK_LAUNCH_ACC
+    return cudaGetLastError();
+}
+
+cudaError_t parallel_accumulate(const BatchView& v, const double* X, const double* W, double wsc,
+                                long n, void* scratch, int sm_count, cudaStream_t st, int first) {
+    return accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, first ? 0 : 1);
+}
+
+cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_count,
+                              cudaStream_t st) {
+    ParLayout L = carve(scratch, v.comp, sm_count);
+    const int mmax = mmax_for(v.comp);
+    size_t wsb = fin_ws_bytes(v.cap, mmax);
+    int use_smem = wsb <= 180 * 1024;
+    size_t smem = use_smem ? wsb : 0;
+    cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(use_smem ? wsb : 0));
+    if (e != cudaSuccess) return e;
+    count_launch();
+    k_finalize<<<1, 1024, smem, st>>>(v, d, L.hdr, L.edges, L.partial, L.minmax, L.fin, mmax,
+                                      use_smem);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
+                                   double wsc, long n, void* scratch, int sm_count,
+                                   cudaStream_t st) {
+    ParLayout L = carve(scratch, v.comp, sm_count);
+    long S = sample_len(n);
+    count_launch();
+    k_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(X, W, wsc, n, S, L.sx, L.sw, L.hdr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = edges_from_sorted_sample(v, L, S, st);
+    if (e != cudaSuccess) return e;
+    e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0);
+    if (e != cudaSuccess) return e;
+    return parallel_finalize(v, d, scratch, sm_count, st);
+}
+
+int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st) {
+    ParLayout L = carve(scratch, 100.0, 1);
+    ParHeader h;
+    if (cudaMemcpyAsync(&h, L.hdr, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    int E = h.E < max_out ? h.E : max_out;
+    if (E > 0) {
+        if (cudaMemcpyAsync(out, L.edges, sizeof(double) * E, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            return -1;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    }
+    return h.E;
+}
+
+}  // namespace crick

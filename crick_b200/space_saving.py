@@ -1,0 +1,229 @@
+"""SpaceSaving -- drop-in for ``crick.SpaceSaving`` (reference: crick/space_saving.pyx) for the
+int64 and float64 item types, on the GPU.  The object dtype needs ``PyObject_Hash`` /
+``RichCompare`` per item (space_saving_stubs.c.in:20-29) and cannot run on a GPU: it is out of
+this build's scope and raises NotImplementedError."""
+import numpy as np
+
+from ._arrays import device_view, korder_pair
+from ._lib import check, check_handle, handle_array, lib
+
+COUNTER_INT64_DTYPE = np.dtype([("item", np.int64), ("count", np.int64), ("error", np.int64)])
+COUNTER_FLOAT64_DTYPE = np.dtype([("item", np.float64), ("count", np.int64), ("error", np.int64)])
+
+
+class TopKResult(tuple):
+    """TopKResult(item, count, error)
+
+    A result from ``SpaceSaving.topk``: the item, its estimated frequency, and an upper
+    bound on the error of that estimate.
+    """
+
+    __slots__ = ()
+
+    def __new__(cls, item, count, error):
+        return tuple.__new__(cls, (item, count, error))
+
+    def __repr__(self):
+        return "TopKResult(item=%r, count=%r, error=%r)" % self
+
+    def __getnewargs__(self):
+        return tuple(self)
+
+    def __dict__(self):
+        return dict(zip(("item", "count", "error"), self))
+
+    def __getstate__(self):
+        pass
+
+    @property
+    def item(self):
+        return self[0]
+
+    @property
+    def count(self):
+        return self[1]
+
+    @property
+    def error(self):
+        return self[2]
+
+
+def _as_int(v, name):
+    if isinstance(v, (str, bytes)) or v is None or (isinstance(v, float) and v != int(v)):
+        raise TypeError("%s must be an integer" % name)
+    try:
+        return int(v)
+    except (TypeError, ValueError):
+        raise TypeError("%s must be an integer" % name)
+
+
+class SpaceSaving:
+    """SpaceSaving(capacity=20, dtype='f8')
+
+    Approximate TopK: keeps ``capacity`` counters for the most frequent elements of a
+    stream (Metwally et al. Space-Saving / Stream-Summary; merge by Cafaro et al.).
+    Integer dtypes are tracked as int64, float dtypes as float64 (by bit pattern).
+    """
+
+    __slots__ = ("_h", "dtype", "__weakref__")
+
+    def __init__(self, capacity=20, dtype="f8"):
+        self._h = None
+        capacity = _as_int(capacity, "capacity")
+        if capacity <= 0:  # space_saving.pyx:180-181
+            raise ValueError("capacity must be > 0")
+        dtype = np.dtype(dtype)
+        if dtype.kind == "O":
+            raise NotImplementedError(
+                "SpaceSaving(dtype=object) needs Python hashing/equality per item and is "
+                "outside the GPU build's scope; use dtype='i8' or 'f8'")
+        elif dtype.kind in "iu":
+            dtype = np.dtype(np.int64)
+        elif dtype.kind == "f":
+            dtype = np.dtype(np.float64)
+        else:
+            raise ValueError("dtype %s not supported" % dtype)
+        self.dtype = dtype
+        self._h = check_handle(lib.crick_spsv_new(capacity), "SpaceSaving()")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.crick_spsv_free(h)
+
+    def __repr__(self):  # space_saving.pyx:207-209
+        return "SpaceSaving<capacity={0}, dtype={1}, size={2}>".format(self.capacity, self.dtype,
+                                                                       self.size())
+
+    @property
+    def capacity(self):
+        return int(lib.crick_spsv_capacity(self._h))
+
+    def size(self):
+        """The number of active counters."""
+        return int(check(lib.crick_spsv_size(self._h), "size"))
+
+    def counters(self):
+        """A copy of all the counters in the summary, most frequent first."""
+        return self.topk(self.size())
+
+    def __reduce__(self):  # space_saving.pyx:229-230
+        return (SpaceSaving, (self.capacity, self.dtype), self.__getstate__())
+
+    def __getstate__(self):
+        return (self.counters(),)
+
+    def __setstate__(self, state):  # space_saving.pyx:235-245
+        counters = np.ascontiguousarray(state[0])
+        if self.dtype.kind == "f":
+            counters = counters.view(COUNTER_INT64_DTYPE)
+        counters = np.ascontiguousarray(counters, dtype=COUNTER_INT64_DTYPE)
+        rc = lib.crick_spsv_set_state(self._h, counters.ctypes.data, len(counters))
+        if rc < 0:
+            from ._lib import last_error
+            raise ValueError(last_error())
+
+    def _item_bits(self, item):
+        if self.dtype.kind == "f":
+            return int(np.asarray(item, dtype=np.float64).reshape(()).view(np.int64))
+        if isinstance(item, (str, bytes)) or item is None:
+            raise TypeError("an integer is required")
+        if isinstance(item, float):
+            if item != int(item):
+                raise TypeError("an integer is required")
+        return int(item)
+
+    def add(self, item, count=1):
+        """add(self, item, count=1)
+
+        Add an element to the summary.
+        """  # space_saving.pyx:247-268
+        count = _as_int(count, "count")
+        if count <= 0:
+            raise ValueError("count must be > 0")
+        try:
+            bits = self._item_bits(item)
+        except (ValueError, OverflowError):
+            raise TypeError("item cannot be converted to %s" % self.dtype)
+        check(lib.crick_spsv_add(self._h, bits, count), "add")
+
+    def update(self, item, count=1, stream=None):
+        """update(self, item, count=1)
+
+        Add many elements to the summary.  `item` may be NumPy-compatible or an
+        int64 / float64 CUDA array matching the summary's dtype.
+        """  # space_saving.pyx:270-302
+        idv = device_view(item)
+        if idv is not None:
+            if idv.dtype != self.dtype:
+                raise TypeError("CUDA item array must have dtype %s" % self.dtype)
+            if idv.size == 0:
+                return
+            cd = device_view(count)
+            if cd is not None:
+                if cd.dtype != np.int64 or cd.size != idv.size:
+                    raise TypeError("count must be an int64 CUDA array shaped like item")
+                check(lib.crick_spsv_update(self._h, idv.ptr, cd.ptr, 0, idv.size, 1, 1, 0, stream),
+                      "update")
+            else:
+                c = _as_int(count, "count")
+                if c <= 0:
+                    raise ValueError("count must be > 0")
+                check(lib.crick_spsv_update(self._h, idv.ptr, None, c, idv.size, 1, 0, 0, stream),
+                      "update")
+            return
+        item = np.asarray(item)
+        check_count = not (np.isscalar(count) and count == 1)
+        count = np.asarray(count)
+        item = item.astype(self.dtype, casting="safe", copy=False)
+        count = count.astype(np.int64, casting="safe", copy=False)
+        if check_count and (count <= 0).any():
+            raise ValueError("count must be > 0")
+        if item.size == 0 or count.size == 0:
+            return
+        if self.dtype.kind == "f":
+            item = item.view("i8")
+        xf, cf = korder_pair(item, count, w_dtype="i8", x_dtype="i8")
+        if isinstance(cf, np.ndarray):
+            check(lib.crick_spsv_update(self._h, xf.ctypes.data, cf.ctypes.data, 0, xf.size, 0, 0, 0,
+                                        stream), "update")
+        else:
+            check(lib.crick_spsv_update(self._h, xf.ctypes.data, None, int(cf), xf.size, 0, 0, 0,
+                                        stream), "update")
+
+    def topk(self, k, astuples=False):
+        """topk(self, k, astuples=False)
+
+        Estimate the top k elements: a record array with fields item / count / error
+        (``count - error <= actual <= count``), or a list of ``TopKResult`` tuples.
+        """  # space_saving.pyx:304-341
+        k = _as_int(k, "k")
+        if k < 0:
+            raise ValueError("k must be >= 0")
+        k = min(self.size(), k)
+        out = np.empty(k, dtype=COUNTER_INT64_DTYPE)
+        if k:
+            check(lib.crick_spsv_counters(self._h, out.ctypes.data, k), "topk")
+        if self.dtype.kind == "f":
+            out = out.view(COUNTER_FLOAT64_DTYPE)
+        if astuples:
+            return [TopKResult(*i) for i in out.tolist()]
+        return out
+
+    def merge(self, *args):
+        """merge(self, *args)
+
+        Update this summary in-place with data from other summaries.
+        """  # space_saving.pyx:343-365
+        if not all(isinstance(i, SpaceSaving) for i in args):
+            raise TypeError("All arguments to merge must be SpaceSavings")
+        if not all(i.dtype == self.dtype for i in args):
+            raise ValueError("All arguments to merge must have same dtype")
+        if not args:
+            return
+        arr = handle_array([s._h for s in args])
+        check(lib.crick_spsv_merge(self._h, arr, len(args)), "merge")
+
+
+SpaceSaving.__module__ = "crick.space_saving"
+TopKResult.__module__ = "crick.space_saving"

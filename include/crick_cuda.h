@@ -1,0 +1,190 @@
+/* include/crick_cuda.h -- C ABI of libcrick_cuda.so (sm_100a, CUDA 12.9).
+ *
+ * The drop-in boundary for crick's hot path.  In the reference the boundary is
+ * the `cdef extern from "*_stubs.c"` blocks of the Cython classes
+ * (crick/tdigest.pyx:13-40, crick/stats.pyx:8-31, crick/space_saving.pyx:10-68):
+ * C structs malloc'ed per sketch and `static inline` functions #included into
+ * the extension.  Here every one of those functions has a plain-C, opaque-handle
+ * equivalent that runs on the GPU.  No Python.h, no NumPy C-API, no PyTorch types:
+ * plain pointers and sizes only.  Pointers flagged `on_device` are CUDA device
+ * pointers (from __cuda_array_interface__ / DLPack / cudaMalloc); otherwise they
+ * are host pointers (pageable or pinned) and the library stages the copy.
+ *
+ * Conventions
+ *   - int-returning functions: 0 = ok, <0 = error; crick_last_error() gives the
+ *     text (thread-local).  NULL from a constructor = allocation/CUDA failure.
+ *   - `stream`: a cudaStream_t passed as void*; NULL = the handle's own stream.
+ *     Work is enqueued asynchronously; getters and host-destination copies
+ *     synchronise that stream.
+ *   - one handle = one thread at a time (as in the reference); different
+ *     handles may be used concurrently from different threads.
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef CRICK_CUDA_H
+#define CRICK_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crick_tdigest crick_tdigest_t;
+typedef struct crick_tdigest_group crick_tdigest_group_t;
+typedef struct crick_stats crick_stats_t;
+typedef struct crick_spsv crick_spsv_t;
+
+/* ---- library ---------------------------------------------------------- */
+const char *crick_last_error(void);
+const char *crick_version(void);
+/* number of CUDA devices visible (0 => nothing will work), current device, SM count */
+int crick_device_count(void);
+int crick_set_device(int device);
+int crick_sm_count(void);
+/* kernels launched by this library since load (all threads) -- bench.py's gpu_launches */
+int64_t crick_launch_count(void);
+/* pinned host memory for callers that want true async H2D (bench e2e leg) */
+void *crick_host_alloc(int64_t bytes);
+void crick_host_free(void *p);
+/* plain device memory + copies, so that callers need no other CUDA binding */
+void *crick_device_alloc(int64_t bytes);
+void crick_device_free(void *p);
+int crick_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+int crick_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
+int crick_stream_synchronize(void *stream);
+int crick_device_synchronize(void);
+/* synthetic counter-based streams for benchmarks/tests: element i depends only on
+ * (seed, offset + i).  kind 0 lognormal(0,1) + U(.5,1.5) weights, 1 uniform, 2 normal,
+ * 3 zipf(1.1)-like integers.  w_dev may be NULL. */
+int crick_synth_fill(double *x_dev, double *w_dev, int64_t n, uint64_t seed, int64_t offset,
+                     int kind, void *stream);
+
+/* ---- TDigest ------------------------------------------------------------
+ * update modes */
+#define CRICK_MODE_AUTO 0      /* reference-compatible below CRICK_PARALLEL_MIN values, else parallel */
+#define CRICK_MODE_REFERENCE 1 /* bit-exact with the reference's sequential algorithm */
+#define CRICK_MODE_PARALLEL 2  /* k-bucket pre-aggregation (needs n >= CRICK_PARALLEL_MIN) */
+#define CRICK_PARALLEL_MIN 65536
+
+/* tdigest_new, tdigest_stubs.c:50-99 (compression clipped to [20, 1000]) */
+crick_tdigest_t *crick_tdigest_new(double compression);
+/* tdigest_free, tdigest_stubs.c:102-108 */
+void crick_tdigest_free(crick_tdigest_t *t);
+/* tdigest_add, tdigest_stubs.c:276-298 (queued on the host, applied in order at the next
+ * device operation) */
+int crick_tdigest_add(crick_tdigest_t *t, double x, double w);
+/* tdigest_update_ndarray, tdigest_stubs.c:632-710, for contiguous float64 input that the
+ * wrapper has already flattened in K-order.  w == NULL => scalar weight w_scalar. */
+int crick_tdigest_update(crick_tdigest_t *t, const double *x, const double *w, double w_scalar,
+                         int64_t n, int x_on_device, int w_on_device, int mode, void *stream);
+/* tdigest_flush, tdigest_stubs.c:219-273 */
+int crick_tdigest_flush(crick_tdigest_t *t);
+/* tdigest_merge, tdigest_stubs.c:592-606, for each of `others` in order (flushes them) */
+int crick_tdigest_merge(crick_tdigest_t *t, crick_tdigest_t *const *others, int n_others);
+/* tdigest_scale, tdigest_stubs.c:609-629 (in place; the wrapper copies first, tdigest.pyx:338) */
+int crick_tdigest_scale(crick_tdigest_t *t, double factor);
+/* tdigest_quantile_ndarray / tdigest_cdf_ndarray, tdigest_stubs.c:519-589 / :410-480 */
+int crick_tdigest_quantile(crick_tdigest_t *t, const double *q, double *out, int64_t n,
+                           int on_device, void *stream);
+int crick_tdigest_cdf(crick_tdigest_t *t, const double *x, double *out, int64_t n,
+                      int on_device, void *stream);
+/* struct fields read by tdigest.pyx:98,105-106,122,239-243.  min/max/ncentroids/total flush
+ * nothing by themselves: call crick_tdigest_flush first where the reference does. */
+double crick_tdigest_compression(crick_tdigest_t *t);
+int crick_tdigest_size(crick_tdigest_t *t);        /* centroid slots, 2*ceil(c) */
+int crick_tdigest_buffer_size(crick_tdigest_t *t); /* buffer slots */
+double crick_tdigest_min(crick_tdigest_t *t);
+double crick_tdigest_max(crick_tdigest_t *t);
+int crick_tdigest_ncentroids(crick_tdigest_t *t);
+int crick_tdigest_buffer_ncentroids(crick_tdigest_t *t);
+double crick_tdigest_total_weight(crick_tdigest_t *t);
+double crick_tdigest_buffer_total_weight(crick_tdigest_t *t);
+/* centroids() copy-out, tdigest.pyx:231-244: out holds 2*ncentroids doubles (mean, weight) */
+int crick_tdigest_get_centroids(crick_tdigest_t *t, double *out, int on_device);
+/* device pointer of the live centroid array (zero-copy view, valid until the next mutation) */
+const double *crick_tdigest_centroids_device(crick_tdigest_t *t);
+/* __setstate__, tdigest.pyx:253-263 (bounds-checked here: n <= size) */
+int crick_tdigest_set_state(crick_tdigest_t *t, const double *centroids, int n,
+                            double total_weight, double min, double max);
+/* test hook: bucket edges chosen by the last parallel-mode update (returns their count) */
+int crick_tdigest_debug_edges(crick_tdigest_t *t, double *out, int max_out);
+
+/* fixed-size wire record for the multi-GPU all-gather:
+ * doubles [ncentroids, total_weight, min, max, mean0, weight0, mean1, ...], padded to
+ * crick_tdigest_record_doubles(t) = 4 + 2*size.  export flushes first; the record lives on
+ * the device.  merge_records feeds `n_records` records (device, contiguous, in order)
+ * through tdigest_merge semantics, skipping index `skip` (pass -1 to keep all). */
+int crick_tdigest_record_doubles(crick_tdigest_t *t);
+int crick_tdigest_export_record(crick_tdigest_t *t, double *record_dev, void *stream);
+int crick_tdigest_merge_records(crick_tdigest_t *t, const double *records_dev, int n_records,
+                                int skip, void *stream);
+
+/* ---- grouped digests: many independent digests, one warp each ------------
+ * (the added entry point; semantics per group are exactly
+ *  `t = TDigest(c); t.update(values_g, weights_g)` in reference-compatible mode) */
+crick_tdigest_group_t *crick_tdigest_group_new(double compression, int64_t n_groups);
+void crick_tdigest_group_free(crick_tdigest_group_t *g);
+int64_t crick_tdigest_group_count(crick_tdigest_group_t *g);
+/* values: n_groups rows of row_len doubles, row r at values + r*row_stride (fixed-length
+ * form, offsets == NULL) or group r = values[offsets[r] .. offsets[r+1]) (ragged form;
+ * offsets has n_groups+1 int64 entries, same residency as values).  weights NULL => scalar. */
+int crick_tdigest_group_update(crick_tdigest_group_t *g, const double *values,
+                               const double *weights, double w_scalar, const int64_t *offsets,
+                               int64_t row_len, int64_t row_stride, int on_device, void *stream);
+int crick_tdigest_group_flush(crick_tdigest_group_t *g);
+/* pairwise, level-by-level tree merge (left operand = self, right = other, exactly a nest of
+ * tdigest_merge calls); the result lands in group 0 and is copied into `out` */
+int crick_tdigest_group_merge_tree(crick_tdigest_group_t *g, crick_tdigest_t *out);
+/* per-group queries: out[g*nq + j]; q on host or device per on_device */
+int crick_tdigest_group_quantile(crick_tdigest_group_t *g, const double *q, int nq, double *out,
+                                 int on_device, void *stream);
+int crick_tdigest_group_cdf(crick_tdigest_group_t *g, const double *x, int nq, double *out,
+                            int on_device, void *stream);
+/* headers: out_meta[g*4 + {0,1,2,3}] = ncentroids, total_weight, min, max (host) */
+int crick_tdigest_group_meta(crick_tdigest_group_t *g, double *out_meta);
+/* centroids of group i (flushes it): up to 2*size doubles to host; returns ncentroids */
+int crick_tdigest_group_get_centroids(crick_tdigest_group_t *g, int64_t i, double *out);
+/* copy group i into a standalone digest handle (same compression) */
+int crick_tdigest_group_extract(crick_tdigest_group_t *g, int64_t i, crick_tdigest_t *out);
+
+/* ---- SummaryStats (stats_stubs.c) ----------------------------------------- */
+crick_stats_t *crick_stats_new(void);                 /* stats_new :25-39  */
+void crick_stats_free(crick_stats_t *s);              /* stats_free :42-44 */
+int crick_stats_add(crick_stats_t *s, double x, int64_t count);      /* stats_add :92-95 */
+/* stats_update_ndarray :139-226; count == NULL => scalar.  x is float64, or int64 when
+ * x_is_int64 (converted on the fly as the NumPy safe cast does). */
+int crick_stats_update(crick_stats_t *s, const void *x, int x_is_int64, const int64_t *count,
+                       int64_t count_scalar, int64_t n, int x_on_device, int count_on_device,
+                       void *stream);
+int crick_stats_merge(crick_stats_t *s, crick_stats_t *const *others, int n_others); /* :78-90 */
+/* state = count + (sum, min, max, m2, m3, m4, first_value) + homogeneous, stats.pyx:77-91 */
+int crick_stats_getstate(crick_stats_t *s, int64_t *count, double *f7, int *homogeneous);
+int crick_stats_setstate(crick_stats_t *s, int64_t count, const double *f7, int homogeneous);
+double crick_stats_mean(crick_stats_t *s);                       /* :98-100  */
+double crick_stats_var(crick_stats_t *s, int64_t ddof);          /* :103-105 */
+double crick_stats_std(crick_stats_t *s, int64_t ddof);          /* :108-110 */
+double crick_stats_skew(crick_stats_t *s, int bias);             /* :113-123 */
+double crick_stats_kurt(crick_stats_t *s, int fisher, int bias); /* :126-136 */
+/* 9-double wire record for all-gather: count, sum, min, max, m2, m3, m4, homogeneous, first */
+int crick_stats_export_record(crick_stats_t *s, double *record9_host);
+int crick_stats_merge_record(crick_stats_t *s, const double *record9_host);
+
+/* ---- SpaceSaving, int64 / float64-bit-pattern items (space_saving_stubs.c.in) ---- */
+crick_spsv_t *crick_spsv_new(int64_t capacity);                  /* spsv_int64_new :75-95 */
+void crick_spsv_free(crick_spsv_t *s);                           /* :98-109 */
+int crick_spsv_add(crick_spsv_t *s, int64_t item, int64_t count);            /* :213-250 */
+/* spsv_int64_update_ndarray :367-451; count == NULL => scalar */
+int crick_spsv_update(crick_spsv_t *s, const int64_t *item, const int64_t *count,
+                      int64_t count_scalar, int64_t n, int item_on_device, int count_on_device,
+                      int mode, void *stream);
+int crick_spsv_merge(crick_spsv_t *s, crick_spsv_t *const *others, int n_others); /* :289-364 */
+int crick_spsv_set_state(crick_spsv_t *s, const int64_t *counters3, int64_t n);   /* :253-286 */
+int64_t crick_spsv_size(crick_spsv_t *s);
+int64_t crick_spsv_capacity(crick_spsv_t *s);
+/* int64_counters walk, space_saving.pyx:368-386: out = k x (item, count, error); returns rows */
+int64_t crick_spsv_counters(crick_spsv_t *s, int64_t *out3, int64_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRICK_CUDA_H */
