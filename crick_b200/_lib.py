@@ -27,6 +27,8 @@ _SIG = {
     "crick_set_device": (c_int, [c_int]),
     "crick_sm_count": (c_int, []),
     "crick_launch_count": (c_int64, []),
+    "crick_profile_enable": (c_int, [c_int]),
+    "crick_profile_collect": (c_int, [_P, _P]),
     "crick_host_alloc": (_P, [c_int64]),
     "crick_host_free": (None, [_P]),
     "crick_device_alloc": (_P, [c_int64]),
@@ -59,6 +61,7 @@ _SIG = {
     "crick_tdigest_centroids_device": (_P, [_P]),
     "crick_tdigest_set_state": (c_int, [_P, _P, c_int, c_double, c_double, c_double]),
     "crick_tdigest_debug_edges": (c_int, [_P, _P, c_int]),
+    "crick_tdigest_debug_buckets": (c_int, [_P, _P, _P, _P, c_int]),
     "crick_tdigest_record_doubles": (c_int, [_P]),
     "crick_tdigest_export_record": (c_int, [_P, _P, _P]),
     "crick_tdigest_merge_records": (c_int, [_P, _P, c_int, c_int, _P]),

@@ -191,6 +191,13 @@ int crick_device_synchronize(void) {
     cudaError_t e = cudaDeviceSynchronize();
     return e == cudaSuccess ? 0 : fail("cudaDeviceSynchronize", e);
 }
+int crick_profile_enable(int on) { profile_enable(on); return 0; }
+int crick_profile_collect(double* total_ms, int64_t* launches) {
+    long long n = 0;
+    int rc = profile_collect(total_ms, &n);
+    *launches = n;
+    return rc;
+}
 int crick_synth_fill(double* x, double* w, int64_t n, uint64_t seed, int64_t offset, int kind,
                      void* stream) {
     cudaError_t e = launch_synth(x, w, n, seed, offset, kind, reinterpret_cast<cudaStream_t>(stream));
@@ -463,6 +470,13 @@ int crick_tdigest_set_state(crick_tdigest_t* t, const double* centroids, int n, 
 int crick_tdigest_debug_edges(crick_tdigest_t* t, double* out, int max_out) {
     if (!t->scratch) return 0;
     return parallel_debug_edges(t->scratch, out, max_out, td_stream(t, nullptr));
+}
+
+int crick_tdigest_debug_buckets(crick_tdigest_t* t, double* out_w, double* out_s, double* out_minmax,
+                                int max_out) {
+    if (!t->scratch) return 0;
+    return parallel_debug_buckets(t->scratch, t->s.v.comp, sm_count(), out_w, out_s, out_minmax,
+                                  max_out, td_stream(t, nullptr));
 }
 
 int crick_tdigest_record_doubles(crick_tdigest_t* t) { return 4 + 2 * t->s.v.cap; }

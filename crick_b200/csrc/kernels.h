@@ -44,12 +44,17 @@ cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_
                               cudaStream_t st);
 // debug/test accessor: copy the bucket edges of the last parallel update to the host
 int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st);
+int parallel_debug_buckets(void* scratch, double comp, int sm_count, double* out_w, double* out_s,
+                           double* out_minmax, int max_out, cudaStream_t st);
 double* parallel_sample_x(void* scratch);
 double* parallel_sample_w(void* scratch);
 long parallel_sample_capacity(void* scratch);
 // host mirrors of the device sampler, so that host-resident input picks the same sample
 long parallel_sample_len(long n);
 long parallel_sample_pos(long i, long n, long S);
+
+void profile_enable(int on);
+int profile_collect(double* total_ms, long long* launches);
 
 // ---- synthetic data (synth.cu)
 cudaError_t launch_synth(double* x, double* w, long n, unsigned long long seed, long offset,

@@ -32,6 +32,10 @@
 #include "kernels.h"
 #include "tdigest_ref.cuh"
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace crick {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -707,6 +711,33 @@ static int acc_warps(int bmax) {
     return nw;
 }
 
+// ---- optional per-launch timing of the hot kernel (bench.py's roofline leg) ------------
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
+
+void profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+}
+// synchronises the recorded events, returns summed milliseconds and the launch count
+int profile_collect(double* total_ms, long long* launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double tot = 0.0;
+    long long n = 0;
+    for (auto& pr : g_prof_ev) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; ++n; }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof_ev.clear();
+    *total_ms = tot;
+    *launches = n;
+    return 0;
+}
+
 static cudaError_t accumulate_impl(const BatchView& v, const double* X, const double* W, double wsc,
                                    long n, void* scratch, int sm_count, cudaStream_t st,
                                    int accumulate_into) {
@@ -719,6 +750,12 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
     const unsigned grid = (unsigned)sm_count;
     const unsigned block = (unsigned)nw * 32;
     cudaError_t e;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_prof_on && cudaEventCreate(&pe0) == cudaSuccess && cudaEventCreate(&pe1) == cudaSuccess)
+            cudaEventRecord(pe0, st);
+    }
 #define CRICK_LAUNCH_ACC(HW, VC)                                                                  \
     e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)smem);                                                          \
@@ -729,6 +766,11 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
     if (W) { if (vec) { CRICK_LAUNCH_ACC(true, true); } else { CRICK_LAUNCH_ACC(true, false); } }
     else { if (vec) { CRICK_LAUNCH_ACC(false, true); } else { CRICK_LAUNCH_ACC(false, false); } }
 #undef CRICK_LAUNCH_ACC
+    if (pe0 && pe1) {
+        cudaEventRecord(pe1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_ev.emplace_back(pe0, pe1);
+    }
     return cudaGetLastError();
 }
 
@@ -767,6 +809,31 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
     e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0);
     if (e != cudaSuccess) return e;
     return parallel_finalize(v, d, scratch, sm_count, st);
+}
+
+// test hook: per-bucket (sum w, sum w*x) of the last update, reduced over CTAs in the same
+// order k_finalize uses; also min/max.  Returns the bucket count.
+int parallel_debug_buckets(void* scratch, double comp, int sm_count, double* out_w, double* out_s,
+                           double* out_minmax, int max_out, cudaStream_t st) {
+    ParLayout L = carve(scratch, comp, sm_count);
+    ParHeader h;
+    if (cudaMemcpyAsync(&h, L.hdr, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    const int B = h.E + 1;
+    if (h.ncta <= 0 || B > max_out) return -1;
+    std::vector<double2> rows((size_t)h.ncta * kBPad), mm((size_t)h.ncta);
+    if (cudaMemcpyAsync(rows.data(), L.partial, rows.size() * sizeof(double2), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(mm.data(), L.minmax, mm.size() * sizeof(double2), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    for (int b = 0; b < B; ++b) {
+        double w = 0.0, s = 0.0;
+        for (int c = 0; c < h.ncta; ++c) { w += rows[(size_t)c * kBPad + b].x; s += rows[(size_t)c * kBPad + b].y; }
+        out_w[b] = w; out_s[b] = s;
+    }
+    double mn = INFINITY, mx = -INFINITY;
+    for (int c = 0; c < h.ncta; ++c) { mn = fmin(mn, mm[c].x); mx = fmax(mx, mm[c].y); }
+    out_minmax[0] = mn; out_minmax[1] = mx;
+    return B;
 }
 
 int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st) {

@@ -1,0 +1,63 @@
+"""Multi-GPU reduction of sketches: one process per GPU, each builds its partial
+sketch over its shard, the small fixed-size records are all-gathered, and every rank merges them
+in rank order with the on-device merge kernel -- enqueued on the same stream directly behind the
+collective, no host synchronisation in between.
+
+torch.distributed is the plumbing here (NCCL over NVLink on GPUs, gloo on CPU for the tests);
+libcrick_cuda itself stays free of any PyTorch dependency.
+"""
+import numpy as np
+
+from .stats import SummaryStats
+from .tdigest import TDigest
+
+
+def allgather_merge_tdigest(digest, group=None):
+    """Return a new TDigest equal to ``TDigest(c).merge(*[digest of rank 0, 1, ...])``."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    nd = digest.record_doubles()
+    stream = torch.cuda.current_stream()
+    rec = torch.empty(nd, dtype=torch.float64, device="cuda")
+    digest.export_record(rec.data_ptr(), stream=stream.cuda_stream or None)
+    if stream.cuda_stream == 0:
+        # the legacy default stream cannot be named through the C ABI (NULL = handle's own)
+        from ._lib import lib
+        lib.crick_device_synchronize()
+    gathered = torch.empty(world * nd, dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(gathered, rec, group=group)
+    out = TDigest(digest.compression)
+    out.merge_records(gathered.data_ptr(), world, stream=stream.cuda_stream or None)
+    if stream.cuda_stream == 0:
+        torch.cuda.synchronize()
+    out._keepalive = gathered  # the merge kernel reads it asynchronously
+    return out
+
+
+def merge_tdigest_records_host(compression, records):
+    """CPU-side plumbing test helper: merge records (list of 1-D float64 arrays laid out as
+    [n, total, min, max, mean0, w0, ...]) in order into a fresh TDigest via the device kernel."""
+    from ._arrays import DeviceArray
+    recs = np.ascontiguousarray(np.stack(records), dtype=np.float64)
+    d = DeviceArray.from_numpy(recs)
+    out = TDigest(compression)
+    out.merge_records(d.ptr, recs.shape[0])
+    out.centroids()  # synchronise before `d` goes away
+    return out
+
+
+def allgather_merge_stats(stats, group=None, backend_device="cuda"):
+    """All-gather the 9-double SummaryStats records and merge them in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rec = torch.from_numpy(stats.export_record()).to(backend_device)
+    gathered = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(gathered, rec, group=group)
+    out = SummaryStats()
+    for r in gathered:
+        out.merge_record(r.cpu().numpy())
+    return out

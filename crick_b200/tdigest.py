@@ -44,7 +44,7 @@ class TDigest:
         262144 values per ``update`` call, parallel at or above.
     """
 
-    __slots__ = ("_h", "_mode", "__weakref__")
+    __slots__ = ("_h", "_mode", "_keepalive", "__weakref__")
 
     def __init__(self, compression=100.0, mode="auto"):
         self._h = None
@@ -385,6 +385,14 @@ class TDigest:
         buf = np.empty(2048, dtype=np.float64)
         n = check(lib.crick_tdigest_debug_edges(self._h, buf.ctypes.data, buf.size), "debug_edges")
         return buf[:n].copy()
+
+    def _debug_buckets(self):
+        w = np.empty(2048, dtype=np.float64)
+        s = np.empty(2048, dtype=np.float64)
+        mm = np.empty(2, dtype=np.float64)
+        n = check(lib.crick_tdigest_debug_buckets(self._h, w.ctypes.data, s.ctypes.data,
+                                                  mm.ctypes.data, 2048), "debug_buckets")
+        return w[:n].copy(), s[:n].copy(), mm
 
 
 # Pickles name `crick.tdigest.TDigest` (tdigest.pyx:246-247) so digests move between the

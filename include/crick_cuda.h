@@ -43,6 +43,10 @@ int crick_set_device(int device);
 int crick_sm_count(void);
 /* kernels launched by this library since load (all threads) -- bench.py's gpu_launches */
 int64_t crick_launch_count(void);
+/* per-launch CUDA-event timing of the hot kernel (k_bin_accumulate), on the stream it is
+ * launched on: enable, run, then collect (synchronises) -> summed ms and launch count */
+int crick_profile_enable(int on);
+int crick_profile_collect(double *total_ms, int64_t *launches);
 /* pinned host memory for callers that want true async H2D (bench e2e leg) */
 void *crick_host_alloc(int64_t bytes);
 void crick_host_free(void *p);
@@ -108,6 +112,10 @@ int crick_tdigest_set_state(crick_tdigest_t *t, const double *centroids, int n,
                             double total_weight, double min, double max);
 /* test hook: bucket edges chosen by the last parallel-mode update (returns their count) */
 int crick_tdigest_debug_edges(crick_tdigest_t *t, double *out, int max_out);
+/* test hook: per-bucket (sum w, sum w*x) and (min, max) of the last parallel-mode update,
+ * reduced in the kernel's own order (returns the bucket count = edges + 1) */
+int crick_tdigest_debug_buckets(crick_tdigest_t *t, double *out_w, double *out_s,
+                                double *out_minmax, int max_out);
 
 /* fixed-size wire record for the multi-GPU all-gather:
  * doubles [ncentroids, total_weight, min, max, mean0, weight0, mean1, ...], padded to

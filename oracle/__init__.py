@@ -192,6 +192,14 @@ class _Namespace:
                 f["tdigest_set_state"](self._h, c.ctypes.data, len(c), float(state[1]),
                                        float(state[2]), float(state[3]))
 
+            def absorb_sorted(self, items, vmin, vmax):
+                """Parallel-mode finalize restated (restated namespace only)."""
+                it = np.ascontiguousarray(items, dtype=np.float64).reshape(-1, 2)
+                fn = ns.lib.orc_tdigest_absorb_sorted
+                fn.restype = None
+                fn.argtypes = [_c_dp, _c_dp, _int, _dbl, _dbl]
+                fn(self._h, it.ctypes.data, it.shape[0], float(vmin), float(vmax))
+
             @staticmethod
             def update_sharded(compression, x, w=1.0, nthreads=1):
                 """One digest per contiguous shard (one thread each), merged in shard order."""
