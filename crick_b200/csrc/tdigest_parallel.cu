@@ -32,6 +32,7 @@
 #include "kernels.h"
 #include "tdigest_ref.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -52,14 +53,17 @@ struct ParHeader {
     unsigned long long ubase;
     long S;      // sample length (power of two)
     int ncta;    // CTAs that wrote partials
-    int pad;
+    int grid;    // lookup grid: 0 = linear in the ordered bit pattern, 1 = linear in x
     double sample_total;
+    double x0;   // grid 1: cell = (int)((x - x0) * inv) + 1
+    double inv;
 };
 
 struct ParLayout {
     ParHeader* hdr;
     double* edges;       // [kEMax]
-    unsigned* tab;       // [kNC]   lo | hi << 16
+    unsigned* tab;       // [kNC]   lo | hi << 16 (the grid k_make_edges chose)
+    unsigned* tab2;      // [kNC]   scratch: candidate table of the other grid
     double* sx;          // [kSMax]
     double* sw;          // [kSMax]
     double* cw;          // [kSMax]
@@ -69,10 +73,13 @@ struct ParLayout {
     size_t fin_bytes;
 };
 
+// Sub-buckets per unit of k.  2 is enough: on 1e7 lognormal / normal / gamma values the rank
+// error with ov = 2, 3, 4 is the same within noise and at or below the reference's
+// (DESIGN.md 4), and the per-warp tables of the hot kernel shrink with it.
 static int ov_for(double comp) {
     int c = (int)ceil(comp);
     int ov = kEMax / c;
-    if (ov > 4) ov = 4;
+    if (ov > 2) ov = 2;
     if (ov < 1) ov = 1;
     return ov;
 }
@@ -91,6 +98,7 @@ size_t parallel_scratch_bytes(double comp, int sm_count) {
     size_t b = 256;
     b += sizeof(double) * kEMax + sizeof(unsigned) * kNC;
     b += 3 * sizeof(double) * kSMax;
+    b += sizeof(unsigned) * kNC;
     b += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     b += sizeof(double2) * (size_t)(2 * sm_count);
     b += fin_ws_bytes(cap, mmax_for(comp)) + 64;
@@ -106,6 +114,7 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
     L.sx = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.sw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.cw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.tab2 = reinterpret_cast<unsigned*>(p); p += sizeof(unsigned) * kNC;
     L.partial = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     L.minmax = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count);
     L.fin = p;
@@ -242,10 +251,18 @@ __device__ __forceinline__ int cell_of(unsigned long long key, unsigned long lon
     return c > (unsigned long long)(kNC - 1) ? (kNC - 1) : (int)c;
 }
 
+__device__ __forceinline__ int cell_lin(double x, double x0, double inv) {
+    if (x < x0) return 0;
+    // cvt.rzi.s32.f64 saturates (NaN -> 0): any finite or infinite x gives a valid cell
+    int c = __double2int_rz(__dmul_rn(__dadd_rn(x, -x0), inv));
+    return (c > kNC - 2 ? kNC - 2 : c) + 1;
+}
+
 __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const double* __restrict__ sx,
                                                      const double* __restrict__ sw,
                                                      double* __restrict__ cw, double* __restrict__ edges,
-                                                     unsigned* __restrict__ tab, double comp, int ov) {
+                                                     unsigned* __restrict__ tab,
+                                                     unsigned* __restrict__ tab2, double comp, int ov) {
     __shared__ double s_part[1024];
     __shared__ double s_raw[kEMax];
     __shared__ int s_cnt[kEMax];
@@ -328,165 +345,287 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     }
     __syncthreads();
     const int E = s_E;
-    // d. lookup table over the ordered bit pattern
+    // d. lookup tables.  Two candidate grids of kNC cells: linear in the order-preserving bit
+    // pattern (~ log x: good for heavy-tailed positive data) and linear in x (good for data
+    // that crosses zero, where the bit pattern spends its cells on the denormal range).
+    // cost = sum over cells of m * ceil(log2(m + 1)), m = edges in the cell, ~ expected
+    // compares per value; the cheaper grid goes to `tab`.
+    __shared__ unsigned long long s_cost[2];
     unsigned long long ubase = 0;
     int shift = 0;
+    double x0 = 0.0, inv = 0.0;
+    bool lin_ok = false;
     if (E > 0) {
         ubase = ordered_key(edges[0]);
         unsigned long long span = ordered_key(edges[E - 1]) - ubase;
         while (shift < 63 && ((span >> shift) + 1ull) > (unsigned long long)(kNC - 2)) ++shift;
+        x0 = edges[0];
+        double width = edges[E - 1] - x0;
+        inv = (double)(kNC - 2) / width;
+        lin_ok = E >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv);
     }
-    for (int cell = tid; cell < kNC; cell += blockDim.x) {
-        // lo = #edges with cell_of(e) < cell ; hi = #edges with cell_of(e) <= cell
-        int a = 0, b = E;
-        while (a < b) {
-            int mid = (a + b) >> 1;
-            if (cell_of(ordered_key(edges[mid]), ubase, shift) < cell) a = mid + 1; else b = mid;
+    if (tid < 2) s_cost[tid] = 0ull;
+    __syncthreads();
+    for (int g = 0; g < 2; ++g) {
+        unsigned* out = g == 0 ? tab : tab2;
+        if (g == 1 && !lin_ok) break;
+        unsigned long long local = 0;
+        for (int cell = tid; cell < kNC; cell += blockDim.x) {
+            // lo = #edges with cell(e) < cell ; hi = #edges with cell(e) <= cell
+            int a = 0, b = E;
+            while (a < b) {
+                int mid = (a + b) >> 1;
+                int ce_ = g == 0 ? cell_of(ordered_key(edges[mid]), ubase, shift)
+                                 : cell_lin(edges[mid], x0, inv);
+                if (ce_ < cell) a = mid + 1; else b = mid;
+            }
+            int lo = a;
+            b = E;
+            while (a < b) {
+                int mid = (a + b) >> 1;
+                int ce_ = g == 0 ? cell_of(ordered_key(edges[mid]), ubase, shift)
+                                 : cell_lin(edges[mid], x0, inv);
+                if (ce_ <= cell) a = mid + 1; else b = mid;
+            }
+            out[cell] = (unsigned)lo | ((unsigned)a << 16);
+            int m = a - lo, lg = 0;
+            while ((1 << lg) < m + 1) ++lg;
+            local += (unsigned long long)m * (unsigned long long)lg;
         }
-        int lo = a;
-        b = E;
-        while (a < b) {
-            int mid = (a + b) >> 1;
-            if (cell_of(ordered_key(edges[mid]), ubase, shift) <= cell) a = mid + 1; else b = mid;
-        }
-        tab[cell] = (unsigned)lo | ((unsigned)a << 16);
+        atomicAdd(&s_cost[g], local);
     }
+    __syncthreads();
+    const int grid = (lin_ok && s_cost[1] < s_cost[0]) ? 1 : 0;
+    if (grid == 1)
+        for (int cell = tid; cell < kNC; cell += blockDim.x) tab[cell] = tab2[cell];
     if (tid == 0) {
         hdr->E = E;
         hdr->shift = shift;
         hdr->ubase = ubase;
         hdr->sample_total = Wt;
         hdr->ncta = 0;
+        hdr->grid = grid;
+        hdr->x0 = x0;
+        hdr->inv = inv;
     }
 }
 
 // 4. THE HOT KERNEL -----------------------------------------------------------
-struct AccCtx {
-    const double* edges;   // shared
+//
+// Weighted histogram of (sum w, sum w*x) over B <= bmax buckets, one pass over HBM.
+// round-1 profile (profiles/r1_a_*): resolving intra-warp bucket collisions with
+// __match_any_sync saturates the ADU pipe (92 %) at ~0.5 value/clk/SM.  This version needs
+// neither MATCH nor atomics:
+//   * every warp owns a private table acc[bucket][C] of double2 in shared memory,
+//     C = 8 (or 4/2/1 for large compressions) COLUMNS per bucket;
+//   * lane l only ever touches column l % C, and the 32/C lanes that share a column take
+//     turns in P = 32/C passes separated by __syncwarp().  Inside a pass the C active lanes
+//     form (part of) one quarter-warp and hit C distinct 16-byte slots: every LDS.128/STS.128
+//     is a single conflict-free wavefront;
+//   * a lane's U = 4 values of one group are de-duplicated in registers first (equal buckets
+//     are folded, the later one is redirected to a dummy row), so the 4 read-modify-writes of
+//     a pass are independent and overlap.
+// Bucket lookup: one probe of a 4096-cell table over a grid that is linear either in x or in
+// the order-preserving bit pattern of x (k_make_edges picks the cheaper one), then 0-2
+// compares against the edges that fall into the cell.
+struct Lookup {
     const unsigned* tab;   // shared
-    double2* acc;          // shared, this warp's private bucket sums
+    const double* edges;   // shared
     unsigned long long ubase;
+    double x0, inv;
     int shift;
     int E;
 };
 
-__device__ __forceinline__ int bucket_of(const AccCtx& c, double xx) {
-    unsigned long long key = ordered_key(xx);
-    int cell = cell_of(key, c.ubase, c.shift);
-    unsigned t = c.tab[cell];
+template <int GRID>
+__device__ __forceinline__ int bucket_of(const Lookup& L, double x) {
+    int cell;
+    if (GRID == 1) cell = cell_lin(x, L.x0, L.inv);
+    else cell = cell_of(ordered_key(x + 0.0), L.ubase, L.shift);  // -0.0 -> +0.0: zeros tie
+    unsigned t = L.tab[cell];
     int lo = (int)(t & 0xffffu), hi = (int)(t >> 16);
-    while (lo < hi) {  // #edges <= xx, restricted to the cell's candidates
+    while (lo < hi) {  // #edges <= x, restricted to the cell's candidates
         int mid = (lo + hi) >> 1;
-        if (c.edges[mid] <= xx) lo = mid + 1; else hi = mid;
+        if (L.edges[mid] <= x) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-// Add (x, w) of every lane into the warp-private bucket sums.  Lanes that land in
-// the same bucket are serialised by rank inside their __match_any_sync group.
-__device__ __forceinline__ void warp_accumulate(const AccCtx& c, double x, double w, bool ok,
-                                                int lane, double& vmin, double& vmax) {
-    __syncwarp();       // order this step's shared-memory updates after the previous step's
-    int b = -1 - lane;  // unique per lane => never matches
-    double xx = x + 0.0;  // -0.0 -> +0.0 so both zeros share a bucket
-    if (ok) {
-        b = bucket_of(c, xx);
-        vmin = fmin(vmin, x);
-        vmax = fmax(vmax, x);
-    }
-    unsigned peers = __match_any_sync(CRICK_FULL, b);
-    int rank = __popc(peers & ((1u << lane) - 1u));
-    int maxrank = __popc(peers) - 1;
-    for (int r = 0;; ++r) {
-        if (ok && rank == r) {
-            double2 a = c.acc[b];
-            a.x = __dadd_rn(a.x, w);
-            a.y = __fma_rn(w, xx, a.y);
-            c.acc[b] = a;
+constexpr int kU = 4;  // values per lane per group
+
+// One group: lane holds kU (x, w) pairs.  acc_col = this warp's table + (lane % C).
+template <bool HAS_W, int C, int GRID>
+__device__ __forceinline__ void accumulate_group(const Lookup& L, double2* acc_col, int dummy,
+                                                 const double* xs, const double* ws, double wsc,
+                                                 unsigned valid_mask, int pass, double& vmin,
+                                                 double& vmax) {
+    constexpr int P = 32 / C;
+    int idx[kU];
+    double ww[kU], ss[kU];
+    const int top = L.E - 1;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        const double x = xs[u];
+        const double w = HAS_W ? ws[u] : wsc;
+        bool ok = is_finite_d(x) && !(w <= DBL_EPSILON) && ((valid_mask >> u) & 1u);  // :285
+        int b = bucket_of<GRID>(L, x);
+        // the minimum lies in bucket 0 or 1 and the maximum in bucket E-1 or E (edges are data
+        // values, or nextafter of one): only those values need the fp64 min/max
+        if (ok && (b <= 1 || b >= top)) {
+            vmin = x < vmin ? x : vmin;
+            vmax = x > vmax ? x : vmax;
         }
-        if (!__any_sync(CRICK_FULL, ok && maxrank > r)) break;
+        // rejected values go to the dummy row (never read back), whatever their w / w*x
+        idx[u] = (ok ? b : dummy) * C;
+        ww[u] = w;
+        ss[u] = __dmul_rn(w, x);
+    }
+    // fold equal buckets of this lane (fixed order => deterministic sums)
+#pragma unroll
+    for (int i = 1; i < kU; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            if (idx[i] == idx[j]) {
+                ww[j] = __dadd_rn(ww[j], ww[i]);
+                ss[j] = __dadd_rn(ss[j], ss[i]);
+                idx[i] = dummy * C;
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if (pass == p) {
+            double2 a[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) a[u] = acc_col[idx[u]];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                a[u].x = __dadd_rn(a[u].x, ww[u]);
+                a[u].y = __dadd_rn(a[u].y, ss[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) acc_col[idx[u]] = a[u];
+        }
         __syncwarp();
     }
 }
 
 template <bool HAS_W, bool VEC>
-__global__ void __launch_bounds__(1024, 1) k_bin_accumulate(const double* __restrict__ X,
-                                                            const double* __restrict__ W, double wsc,
-                                                            long n, ParHeader* hdr,
-                                                            const double* __restrict__ g_edges,
-                                                            const unsigned* __restrict__ g_tab,
-                                                            double2* __restrict__ partial,
-                                                            double2* __restrict__ minmax, int bmax,
-                                                            int accumulate_into) {
-    // shared: tab[kNC] | edges[bmax] | acc[nwarps][bmax]
+__device__ __forceinline__ void load_tile(const double* __restrict__ X, const double* __restrict__ W,
+                                          long base, int lane, double* xs, double* ws) {
+    // tile = 2 groups x 4 values x 32 lanes; lane's values: VEC -> double2 k*32+lane, k = 0..3
+    if (VEC) {
+        const double2* x2 = reinterpret_cast<const double2*>(X + base);
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+            double2 a = ldg_stream2(x2 + k * 32 + lane);
+            xs[2 * k] = a.x; xs[2 * k + 1] = a.y;
+        }
+        if (HAS_W) {
+            const double2* w2 = reinterpret_cast<const double2*>(W + base);
+#pragma unroll
+            for (int k = 0; k < kU; ++k) {
+                double2 a = ldg_stream2(w2 + k * 32 + lane);
+                ws[2 * k] = a.x; ws[2 * k + 1] = a.y;
+            }
+        }
+    } else {
+        // 8-byte aligned input: same element -> lane mapping as the vector variant, so the
+        // result does not depend on the alignment of the caller's pointer
+#pragma unroll
+        for (int k = 0; k < 2 * kU; ++k)
+            xs[k] = ldg_stream1(X + base + (k >> 1) * 64 + 2 * lane + (k & 1));
+        if (HAS_W) {
+#pragma unroll
+            for (int k = 0; k < 2 * kU; ++k)
+                ws[k] = ldg_stream1(W + base + (k >> 1) * 64 + 2 * lane + (k & 1));
+        }
+    }
+}
+
+template <bool HAS_W, bool VEC, int C, int GRID>
+__device__ __forceinline__ void accumulate_stream(const Lookup& L, double2* acc_col, int dummy,
+                                                  const double* __restrict__ X,
+                                                  const double* __restrict__ W, double wsc, long n,
+                                                  long gw, long tw, int lane, double& vmin,
+                                                  double& vmax) {
+    constexpr long TILE = 32L * 2 * kU;  // values per warp iteration
+    const int pass = lane / C;
+    const long ntiles = n / TILE;
+    double xa[2 * kU], wa[2 * kU], xb[2 * kU], wb[2 * kU];
+    double* xs = xa;
+    double* ws = wa;
+    // register ping-pong: the loads of tile t + tw are in flight while tile t is processed
+    long t = gw;
+    if (t < ntiles) load_tile<HAS_W, VEC>(X, W, t * TILE, lane, xa, wa);
+    while (t < ntiles) {
+        long tn = t + tw;
+        if (tn < ntiles) load_tile<HAS_W, VEC>(X, W, tn * TILE, lane, xb, wb);
+        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xa, wa, wsc, 0xfu, pass, vmin, vmax);
+        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xa + kU, wa + kU, wsc, 0xfu, pass,
+                                         vmin, vmax);
+        t = tn;
+        if (t >= ntiles) break;
+        tn = t + tw;
+        if (tn < ntiles) load_tile<HAS_W, VEC>(X, W, tn * TILE, lane, xa, wa);
+        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xb, wb, wsc, 0xfu, pass, vmin, vmax);
+        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xb + kU, wb + kU, wsc, 0xfu, pass,
+                                         vmin, vmax);
+        t = tn;
+    }
+    // ragged tail (< TILE values): the warp whose turn it would be
+    if (gw == ntiles % tw) {
+        for (long i0 = ntiles * TILE; i0 < n; i0 += 32 * kU) {
+            unsigned m = 0;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                long i = i0 + u * 32 + lane;
+                bool in = i < n;
+                xs[u] = in ? X[i] : 0.0;
+                if (HAS_W) ws[u] = in ? W[i] : 0.0;
+                m |= in ? (1u << u) : 0u;
+            }
+            accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xs, ws, wsc, m, pass, vmin, vmax);
+        }
+    }
+}
+
+template <bool HAS_W, bool VEC, int C>
+__global__ void __launch_bounds__(512, 1) k_bin_accumulate(const double* __restrict__ X,
+                                                           const double* __restrict__ W, double wsc,
+                                                           long n, ParHeader* hdr,
+                                                           const double* __restrict__ g_edges,
+                                                           const unsigned* __restrict__ g_tab,
+                                                           double2* __restrict__ partial,
+                                                           double2* __restrict__ minmax, int bmax,
+                                                           int accumulate_into) {
+    // shared: tab[kNC] | edges[bmax even] | acc[nwarps][bmax + 1][C]
     unsigned* s_tab = reinterpret_cast<unsigned*>(smem_raw);
     double* s_edges = reinterpret_cast<double*>(smem_raw + sizeof(unsigned) * kNC);
-    double2* s_acc = reinterpret_cast<double2*>(s_edges + bmax);
+    double2* s_acc = reinterpret_cast<double2*>(s_edges + ((bmax + 1) & ~1));
     __shared__ double s_min[32], s_max[32];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     const int E = hdr->E;
     const int B = E + 1;
+    const int rows = bmax + 1;  // last row = dummy
     for (int i = threadIdx.x; i < kNC; i += blockDim.x) s_tab[i] = g_tab[i];
     for (int i = threadIdx.x; i < E; i += blockDim.x) s_edges[i] = g_edges[i];
-    for (int i = threadIdx.x; i < nwarps * bmax; i += blockDim.x) s_acc[i] = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < nwarps * rows * C; i += blockDim.x) s_acc[i] = make_double2(0.0, 0.0);
     __syncthreads();
-    AccCtx c;
-    c.edges = s_edges; c.tab = s_tab; c.acc = s_acc + (size_t)warp * bmax;
-    c.ubase = hdr->ubase; c.shift = hdr->shift; c.E = E;
+    Lookup L;
+    L.tab = s_tab; L.edges = s_edges; L.ubase = hdr->ubase; L.shift = hdr->shift; L.E = E;
+    L.x0 = hdr->x0; L.inv = hdr->inv;
+    double2* acc_col = s_acc + (size_t)warp * rows * C + (lane % C);
     double vmin = INFINITY, vmax = -INFINITY;
-
-    constexpr int U = 4;                       // loads in flight per lane per array
-    constexpr int PER = VEC ? 2 : 1;           // doubles per load
-    constexpr long TILE = 32L * PER * U;       // values per warp iteration
-    const long ntiles = n / TILE;
     const long gw = (long)blockIdx.x * nwarps + warp;
     const long tw = (long)gridDim.x * nwarps;
-    for (long t = gw; t < ntiles; t += tw) {
-        const long base = t * TILE;
-        double xs[U * PER], ws[U * PER];
-        if (VEC) {
-            const double2* x2 = reinterpret_cast<const double2*>(X + base);
-            const double2* w2 = reinterpret_cast<const double2*>(W + base);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                double2 a = ldg_stream2(x2 + u * 32 + lane);
-                xs[2 * u] = a.x; xs[2 * u + 1] = a.y;
-            }
-            if (HAS_W) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    double2 a = ldg_stream2(w2 + u * 32 + lane);
-                    ws[2 * u] = a.x; ws[2 * u + 1] = a.y;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u) xs[u] = ldg_stream1(X + base + u * 32 + lane);
-            if (HAS_W) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) ws[u] = ldg_stream1(W + base + u * 32 + lane);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U * PER; ++u) {
-            double w = HAS_W ? ws[u] : wsc;
-            bool ok = is_finite_d(xs[u]) && !(w <= DBL_EPSILON);
-            warp_accumulate(c, xs[u], w, ok, lane, vmin, vmax);
-        }
-    }
-    // ragged tail (< TILE values): warp 0 of CTA 0
-    if (gw == 0) {
-        for (long i = ntiles * TILE + lane; i < ((n + 31) / 32) * 32; i += 32) {
-            bool in = i < n;
-            double x = in ? X[i] : 0.0;
-            double w = HAS_W ? (in ? W[i] : 0.0) : wsc;
-            bool ok = in && is_finite_d(x) && !(w <= DBL_EPSILON);
-            warp_accumulate(c, x, w, ok, lane, vmin, vmax);
-        }
-    }
-    // CTA reduction in fixed warp order -> deterministic partials
+    if (hdr->grid == 1)
+        accumulate_stream<HAS_W, VEC, C, 1>(L, acc_col, bmax, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+    else
+        accumulate_stream<HAS_W, VEC, C, 0>(L, acc_col, bmax, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+    // CTA reduction in fixed (warp, column) order -> deterministic partials
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         vmin = fmin(vmin, shfl_xor_d(vmin, d));
@@ -498,8 +637,9 @@ __global__ void __launch_bounds__(1024, 1) k_bin_accumulate(const double* __rest
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         double sw_ = 0.0, sx_ = 0.0;
         for (int wv = 0; wv < nwarps; ++wv) {
-            double2 a = s_acc[(size_t)wv * bmax + b];
-            sw_ += a.x; sx_ += a.y;
+            const double2* r = s_acc + ((size_t)wv * rows + b) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { sw_ += r[c].x; sx_ += r[c].y; }
         }
         if (accumulate_into) { double2 o = row[b]; sw_ += o.x; sx_ += o.y; }
         row[b] = make_double2(sw_, sx_);
@@ -675,7 +815,7 @@ static cudaError_t edges_from_sorted_sample(const BatchView& v, ParLayout& L, lo
     cudaError_t e = sort_sample(L.sx, L.sw, S, st);
     if (e != cudaSuccess) return e;
     count_launch();
-    k_make_edges<<<1, 1024, 0, st>>>(L.hdr, L.sx, L.sw, L.cw, L.edges, L.tab, v.comp,
+    k_make_edges<<<1, 1024, 0, st>>>(L.hdr, L.sx, L.sw, L.cw, L.edges, L.tab, L.tab2, v.comp,
                                      ov_for(v.comp));
     return cudaGetLastError();
 }
@@ -701,14 +841,29 @@ cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratc
     return edges_from_sorted_sample(v, L, S, st);
 }
 
-static int acc_warps(int bmax) {
-    size_t fixed = sizeof(unsigned) * kNC + sizeof(double) * (size_t)bmax + 1024;
-    size_t budget = 200 * 1024;
-    int nw = (int)((budget - fixed) / ((size_t)bmax * 16));
-    if (nw > 32) nw = 32;
-    nw &= ~3;
-    if (nw < 4) nw = 4;
-    return nw;
+// Shape of the hot kernel for a bucket capacity: C columns per warp table, nw warps.
+struct AccCfg { int C, nw; size_t smem; };
+static AccCfg acc_cfg(int bmax) {
+    const size_t fixed = sizeof(unsigned) * kNC + sizeof(double) * (size_t)((bmax + 1) & ~1);
+    const size_t budget = 230000;                       // of 232448 B opt-in, 512 B are static
+    const size_t col = (size_t)(bmax + 1) * 16;         // one column incl. the dummy row
+    int cols = (int)((budget - fixed) / col);
+    AccCfg c;
+    c.C = 8;
+    while (c.C > 1 && cols / c.C < 8) c.C >>= 1;        // prefer >= 8 warps
+    c.nw = cols / c.C;
+    if (c.nw > 16) c.nw = 16;
+    if (c.nw < 1) c.nw = 1;
+    if (const char* e = getenv("CRICK_ACC_C")) {        // tuning hook (bench sweeps)
+        int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) { c.C = v; c.nw = cols / v > 16 ? 16 : cols / v; }
+    }
+    if (const char* e = getenv("CRICK_ACC_W")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= 16 && v * c.C <= cols) c.nw = v;
+    }
+    c.smem = (fixed + (size_t)c.nw * c.C * col + 15) & ~(size_t)15;
+    return c;
 }
 
 // ---- optional per-launch timing of the hot kernel (bench.py's roofline leg) ------------
@@ -742,13 +897,12 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
                                    long n, void* scratch, int sm_count, cudaStream_t st,
                                    int accumulate_into) {
     ParLayout L = carve(scratch, v.comp, sm_count);
-    const int bmax = (bmax_for(v.comp) + 2) & ~1;  // even: keeps the double2 rows 16-byte aligned
-    const int nw = acc_warps(bmax);
-    size_t smem = sizeof(unsigned) * kNC + sizeof(double) * (size_t)bmax + (size_t)nw * bmax * 16;
-    smem = (smem + 15) & ~(size_t)15;
+    const int bmax = bmax_for(v.comp);
+    const AccCfg cfg = acc_cfg(bmax);
+    const size_t smem = cfg.smem;
     const bool vec = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
     const unsigned grid = (unsigned)sm_count;
-    const unsigned block = (unsigned)nw * 32;
+    const unsigned block = (unsigned)cfg.nw * 32;
     cudaError_t e;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     {
@@ -756,15 +910,25 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
         if (g_prof_on && cudaEventCreate(&pe0) == cudaSuccess && cudaEventCreate(&pe1) == cudaSuccess)
             cudaEventRecord(pe0, st);
     }
-#define CRICK_LAUNCH_ACC(HW, VC)                                                                  \
-    e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)smem);                                                          \
-    if (e != cudaSuccess) return e;                                                               \
-    count_launch();                                                                               \
-    k_bin_accumulate<HW, VC><<<grid, block, smem, st>>>(X, W, wsc, n, L.hdr, L.edges, L.tab,      \
-                                                        L.partial, L.minmax, bmax, accumulate_into)
-    if (W) { if (vec) { CRICK_LAUNCH_ACC(true, true); } else { CRICK_LAUNCH_ACC(true, false); } }
-    else { if (vec) { CRICK_LAUNCH_ACC(false, true); } else { CRICK_LAUNCH_ACC(false, false); } }
+#define CRICK_LAUNCH_ACC(HW, VC, CC)                                                              \
+    do {                                                                                          \
+        e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC, CC>,                                    \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                           \
+        count_launch();                                                                           \
+        k_bin_accumulate<HW, VC, CC><<<grid, block, smem, st>>>(                                  \
+            X, W, wsc, n, L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, accumulate_into);     \
+    } while (0)
+#define CRICK_LAUNCH_ACC_C(HW, VC)                                                                \
+    switch (cfg.C) {                                                                              \
+        case 8: CRICK_LAUNCH_ACC(HW, VC, 8); break;                                               \
+        case 4: CRICK_LAUNCH_ACC(HW, VC, 4); break;                                               \
+        case 2: CRICK_LAUNCH_ACC(HW, VC, 2); break;                                               \
+        default: CRICK_LAUNCH_ACC(HW, VC, 1); break;                                              \
+    }
+    if (W) { if (vec) { CRICK_LAUNCH_ACC_C(true, true) } else { CRICK_LAUNCH_ACC_C(true, false) } }
+    else { if (vec) { CRICK_LAUNCH_ACC_C(false, true) } else { CRICK_LAUNCH_ACC_C(false, false) } }
+#undef CRICK_LAUNCH_ACC_C
 #undef CRICK_LAUNCH_ACC
     if (pe0 && pe1) {
         cudaEventRecord(pe1, st);

@@ -1,0 +1,205 @@
+"""GPU parity tests, parallel (k-bucket) mode -- the path BASELINE.json's metric is quoted on.
+
+The clustering differs from the reference's sequential one by construction, so parity is
+checked the way SURVEY.md 8c prescribes:
+  (a) the kernel's partition is recomputed on the CPU from the kernel's own bucket edges:
+      per-bucket (sum w, sum w*x) within 1e-12 relative, exact min / max, and the digest equals
+      the oracle's greedy merge of those bucket points BIT FOR BIT;
+  (b) weighted rank error at the 9 standard q's <= the reference's on the same data (plus the
+      absolute caps of crick/tests/test_tdigest.py:99-107);
+  (c) size-independent properties at full size (1e9 values on the device): exact total weight
+      by linearity, exact min/max, monotone quantiles.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import QS9, accepted, restate_parallel_items, weighted_rank_fn
+
+pytestmark = pytest.mark.gpu
+R = oracle.restated
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import crick_b200
+    if crick_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return crick_b200
+
+
+def check_partition(cb, x, w, comp=100.0, device=False):
+    """(a): run one parallel update, then restate it on the CPU from the kernel's edges."""
+    t = cb.TDigest(comp, mode="parallel")
+    if device:
+        t.update(cb.DeviceArray.from_numpy(x),
+                 cb.DeviceArray.from_numpy(w) if np.ndim(w) else float(w))
+    else:
+        t.update(x, w)
+    edges = t._debug_edges()
+    bw, bs, mm = t._debug_buckets()
+    xa, wa = accepted(x, w)
+    assert (np.diff(edges) > 0).all()
+    assert len(bw) == len(edges) + 1
+    b = np.searchsorted(edges, xa, side="right")          # bucket = #edges <= x
+    cw = np.bincount(b, weights=wa, minlength=len(bw))
+    cs = np.bincount(b, weights=wa * xa, minlength=len(bw))
+    assert np.allclose(bw, cw, rtol=1e-12, atol=0)
+    scale = np.bincount(b, weights=np.abs(wa * xa), minlength=len(bw))
+    assert (np.abs(bs - cs) <= 1e-12 * np.maximum(scale, 1e-300)).all()
+    assert mm[0] == xa.min() and mm[1] == xa.max()
+    # finalize: bucket points -> the reference's greedy merge (tdigest_flush phases 2-5)
+    items = restate_parallel_items(edges, bw, bs, mm[0], mm[1], t.compression)
+    o = R.TDigest(comp)
+    o.absorb_sorted(items, mm[0], mm[1])
+    assert t.centroids().tobytes() == o.centroids().tobytes()
+    assert t.min() == xa.min() and t.max() == xa.max()
+    assert abs(t.size() - wa.sum()) <= 1e-12 * wa.sum()
+    return t
+
+
+@pytest.mark.parametrize("dist", ["lognormal_w", "normal", "uniform", "gamma", "ties", "zeros",
+                                  "narrow", "bimodal", "negative", "nonfinite"])
+def test_partition_restated_on_cpu(cb, dist):
+    rng = np.random.default_rng(17)
+    n = 300000
+    w = 1.0
+    if dist == "lognormal_w":
+        x, w = rng.lognormal(size=n), rng.uniform(0.5, 1.5, n)
+    elif dist == "normal":
+        x = rng.normal(size=n)
+    elif dist == "uniform":
+        x = rng.uniform(0, 1, n)
+    elif dist == "gamma":
+        x = rng.gamma(0.1, 0.1, n)
+    elif dist == "ties":
+        x, w = rng.integers(0, 7, n).astype(float), rng.uniform(0.5, 1.5, n)
+    elif dist == "zeros":
+        x = rng.choice([0.0, -0.0, 1.0, -1.0, 1e-300, -1e-300], n)
+    elif dist == "narrow":
+        x = rng.normal(50, 1e-9, n)
+    elif dist == "bimodal":
+        x = np.concatenate([rng.normal(-1e6, 1e-3, n // 2), rng.normal(1e6, 1e-3, n - n // 2)])
+        rng.shuffle(x)
+    elif dist == "negative":
+        x, w = -rng.lognormal(size=n), rng.uniform(0.5, 1.5, n)
+    else:
+        x = rng.normal(size=n)
+        x[::7] = np.nan
+        x[3::11] = np.inf
+        x[5::13] = -np.inf
+    check_partition(cb, x, w)
+
+
+@pytest.mark.parametrize("n", [65536, 65537, 100003, 262144 + 255, 1 << 20])
+def test_ragged_sizes_and_unaligned_views(cb, n):
+    rng = np.random.default_rng(n)
+    x = rng.lognormal(size=n + 1)
+    w = rng.uniform(0.5, 1.5, n + 1)
+    check_partition(cb, x[:n], w[:n], device=True)
+    # 8-byte (not 16-byte) aligned device views take the scalar-load variant of the kernel
+    dx, dw = cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w)
+
+    class View:
+        def __init__(self, d, off, m):
+            self.__cuda_array_interface__ = {"shape": (m,), "typestr": "<f8", "version": 3,
+                                             "data": (d.ptr + 8 * off, False), "strides": None}
+            self._keep = d
+    t = cb.TDigest(100, mode="parallel")
+    t.update(View(dx, 1, n), View(dw, 1, n))
+    u = cb.TDigest(100, mode="parallel")
+    u.update(x[1:], w[1:])
+    assert t.centroids().tobytes() == u.centroids().tobytes()
+
+
+@pytest.mark.parametrize("comp", [20, 100, 200, 500, 1000])
+def test_compressions(cb, comp):
+    rng = np.random.default_rng(comp)
+    n = 400000
+    check_partition(cb, rng.lognormal(size=n), rng.uniform(0.5, 1.5, n), comp=float(comp))
+
+
+def test_rank_error_not_worse_than_reference(cb):
+    """(b) on config-2 data (lognormal x, U(.5,1.5) w, c=100), 1e7-value subset."""
+    rng = np.random.default_rng(1234)
+    n = 10**7
+    x = rng.lognormal(0, 1, n)
+    w = rng.uniform(0.5, 1.5, n)
+    rank = weighted_rank_fn(x, w)
+    ref = R.TDigest(100)
+    ref.update(x, w)
+    err_ref = np.abs(rank(ref.quantile(QS9)) - QS9).max()
+    t = cb.TDigest(100, mode="parallel")
+    t.update(x, w)
+    err = np.abs(rank(t.quantile(QS9)) - QS9).max()
+    assert err <= max(err_ref, 2.5e-4), (err, err_ref)
+    assert err <= 0.012
+    xs = np.quantile(x, QS9)
+    assert np.abs(t.cdf(xs) - rank(xs)).max() <= max(np.abs(ref.cdf(xs) - rank(xs)).max(), 2.5e-4)
+    assert t.min() == x.min() and t.max() == x.max()
+    assert abs(t.size() - w.sum()) <= 1e-12 * w.sum()
+    # sharded: 8 partial digests merged in rank order (the multi-GPU reduction)
+    parts, refs = [], []
+    for k in range(8):
+        sl = slice(k * n // 8, (k + 1) * n // 8)
+        p = cb.TDigest(100, mode="parallel")
+        p.update(x[sl], w[sl])
+        parts.append(p)
+        r = R.TDigest(100)
+        r.update(x[sl], w[sl])
+        refs.append(r)
+    m = cb.TDigest(100)
+    m.merge(*parts)
+    mr = R.TDigest(100)
+    mr.merge(*refs)
+    e8 = np.abs(rank(m.quantile(QS9)) - QS9).max()
+    e8r = np.abs(rank(mr.quantile(QS9)) - QS9).max()
+    assert e8 <= max(2 * e8r, 1e-3), (e8, e8r)
+
+
+def test_incremental_updates_accumulate(cb):
+    rng = np.random.default_rng(6)
+    x = rng.normal(size=600000)
+    t = cb.TDigest(100, mode="parallel")
+    for k in range(3):
+        t.update(x[k * 200000:(k + 1) * 200000])
+    assert t.size() == 600000 and t.min() == x.min() and t.max() == x.max()
+    rank = weighted_rank_fn(x, 1.0)
+    assert np.abs(rank(t.quantile(QS9)) - QS9).max() < 1e-3
+    a = cb.TDigest(100, mode="auto")     # auto: reference below 262144 values, parallel above
+    a.update(x[:1000])
+    a.update(x)
+    assert a.size() == 601000
+
+
+def test_full_size_properties_on_device(cb):
+    """(c) BASELINE configs[1] at full size on one GPU: 1e9 lognormal + weights, generated on
+    the device by the counter-based generator (element i depends on (seed, i) only)."""
+    from crick_b200._lib import lib
+    n = 10**9
+    dx, dw = cb.DeviceArray((n,)), cb.DeviceArray((n,))
+    lib.crick_synth_fill(dx.ptr, dw.ptr, n, 1234, 0, 0, None)
+    t = cb.TDigest(100, mode="parallel")
+    t.update(dx, dw)
+    # weights are U(0.5, 1.5): total within 5 sigma of n; exact value from a stats pass
+    s = cb.SummaryStats()
+    s.update(dw)
+    assert s.count() == n
+    assert abs(t.size() - s.sum()) <= 1e-9 * s.sum()
+    sx = cb.SummaryStats()
+    sx.update(dx)
+    assert t.min() == sx.min() and t.max() == sx.max()
+    q = np.linspace(0.0005, 0.9995, 2000)
+    est = t.quantile(q)
+    assert (np.diff(est) > 0).all()
+    # lognormal(0,1): quantile(q) = exp(ndtri(q)); rank error of the estimate in q-space
+    from scipy.special import ndtr
+    assert np.abs(ndtr(np.log(est)) - q).max() < 5e-4
+    # linearity: a second pass doubles every weight and leaves the means where they were
+    c1 = t.centroids()
+    t2 = cb.TDigest(100, mode="parallel")
+    t2.update(dx, dw)
+    t2.update(dx, dw)
+    assert abs(t2.size() - 2 * t.size()) <= 1e-9 * t.size()
+    assert np.abs(ndtr(np.log(t2.quantile(QS9))) - QS9).max() < 5e-4
+    assert len(c1) > 90

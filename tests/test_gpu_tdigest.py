@@ -1,0 +1,366 @@
+"""GPU parity tests (reference-compatible mode): the CUDA path, called through the C ABI of
+libcrick_cuda.so by the drop-in wrappers, against (a) the committed golden vectors made from
+the built reference (tests/golden/make_golden.py) and (b) the oracle on the same seeded inputs.
+The bar is BIT-EXACT centroids / min / max / size and bit-exact quantile / cdf answers.
+
+Edge cases follow the reference's own tests (crick/tests/test_tdigest.py): empty digest -> NaN
+:129-136, single value :139-152, NaN/inf silently dropped :155-180, tiny weights dropped
+:183-193, output shapes :230-251, histogram :254-344, weights :347-361, pickle :364-374,
+merge :377-408, scale :411-444.
+"""
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import (QS5, QS9, check_digest_against_golden, kat_d_parts, kat_inputs,
+                     quantiles_to_q, q_to_x, sha)
+
+pytestmark = pytest.mark.gpu
+R = oracle.restated
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import crick_b200
+    if crick_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return crick_b200
+
+
+def same(a, b):
+    """Digest `a` (ours) and `b` (oracle) are identical bit for bit."""
+    assert a.centroids().tobytes() == b.centroids().tobytes()
+    assert a.size() == b.size()
+    assert np.array_equal([a.min(), a.max()], [b.min(), b.max()], equal_nan=True)
+
+
+# ---- golden vectors from the built reference -----------------------------------------
+@pytest.mark.parametrize("name", ["kat_a", "kat_b", "kat_c"])
+def test_kats_bit_exact(cb, golden, name):
+    g, _ = golden
+    c, x, w, cdf_x = kat_inputs()[name]
+    t = cb.TDigest(c, mode="reference")
+    t.update(x, w)
+    check_digest_against_golden(t, g[name], cdf_x)
+
+
+def test_kat_d_merge_bit_exact(cb, golden):
+    g, _ = golden
+    parts = []
+    for x in kat_d_parts():
+        p = cb.TDigest(100, mode="reference")
+        p.update(x)
+        parts.append(p)
+    t = cb.TDigest(100)
+    t.merge(*parts)
+    check_digest_against_golden(t, g["kat_d"], [0.5, 4, 7.5])
+
+
+def test_config1_bit_exact(cb, golden):
+    """BASELINE.json configs[0]: TDigest(100).update of 1e6 uniform then 5 quantiles."""
+    g, _ = golden
+    t = cb.TDigest(100, mode="reference")
+    t.update(np.random.default_rng(0).uniform(0, 1, 10**6))
+    check_digest_against_golden(t, g["config1"], [0.1, 0.5, 0.9])
+
+
+def test_config2_small_bit_exact(cb, golden):
+    g, _ = golden
+    rng = np.random.default_rng(1234)
+    x = rng.lognormal(0, 1, 200000)
+    w = rng.uniform(0.5, 1.5, 200000)
+    t = cb.TDigest(100, mode="reference")
+    t.update(x, w)
+    check_digest_against_golden(t, g["config2_small"], [0.5, 1.0, 3.0])
+
+
+# ---- oracle on the same seeded inputs --------------------------------------------------
+@pytest.mark.parametrize("c", [20, 50.5, 100, 200, 500, 1000])
+def test_weighted_stream_vs_oracle(cb, c):
+    rng = np.random.default_rng(int(c))
+    x = rng.lognormal(size=30000)
+    w = rng.uniform(0.5, 1.5, 30000)
+    a = cb.TDigest(c, mode="reference")
+    b = R.TDigest(c)
+    a.update(x, w)
+    b.update(x, w)
+    same(a, b)
+    qs = np.concatenate([rng.uniform(-0.1, 1.1, 1000), [0.0, 1.0, 1e-12, 1 - 1e-12]])
+    assert a.quantile(qs).tobytes() == b.quantile(qs).tobytes()
+    cm = b.centroids()["mean"]
+    xs = np.concatenate([rng.lognormal(size=1000), cm, np.nextafter(cm, np.inf),
+                         np.nextafter(cm, -np.inf), [b.min(), b.max(), -1.0, 1e9]])
+    assert a.cdf(xs).tobytes() == b.cdf(xs).tobytes()
+
+
+@pytest.mark.parametrize("kind", ["sorted", "reversed", "ties", "zeros", "step", "narrow"])
+def test_hard_orders_vs_oracle(cb, kind):
+    rng = np.random.default_rng(7)
+    n = 20000
+    x = {"sorted": np.sort(rng.normal(size=n)),
+         "reversed": np.sort(rng.normal(size=n))[::-1].copy(),
+         "ties": rng.integers(0, 13, n).astype(float),
+         "zeros": rng.choice([0.0, -0.0, 1.0, -1.0], n),
+         "step": np.concatenate([rng.uniform(0, 1, n // 2), rng.uniform(100, 101, n // 2)]),
+         "narrow": rng.normal(50, 1e-9, n)}[kind]
+    a = cb.TDigest(100, mode="reference")
+    b = R.TDigest(100)
+    a.update(x)
+    b.update(x)
+    same(a, b)
+    assert a.quantile(QS9).tobytes() == b.quantile(QS9).tobytes()
+
+
+def test_buffer_phase_carries_across_calls(cb):
+    """tdigest_add's flush-before-append phase (tdigest_stubs.c:288-290) must carry across
+    update()/add()/merge() calls of any size, including sizes that straddle buffer_size."""
+    rng = np.random.default_rng(11)
+    a = cb.TDigest(100, mode="reference")
+    b = R.TDigest(100)
+    for n in [1, 41, 1, 1, 42, 43, 0, 7, 500, 84, 3]:
+        x = rng.normal(size=n)
+        a.update(x)
+        b.update(x)
+        assert a.size() == b.size()
+    for v in rng.normal(size=50):
+        a.add(v, 2.0)
+        b.add(v, 2.0)
+    same(a, b)
+
+
+def test_nonfinite_dropped_and_tiny_weights(cb):
+    x = np.array([1.0, np.nan, 2.0, np.inf, 3.0, -np.inf, 4.0])
+    a = cb.TDigest(mode="reference")
+    b = R.TDigest()
+    a.update(x)
+    b.update(x)
+    same(a, b)
+    assert a.size() == 4
+    eps = np.finfo("f8").eps
+    a = cb.TDigest(mode="reference")
+    a.update([1.0, 2.0, 3.0], [eps, 1.0, eps / 2])  # w <= eps dropped (tdigest_stubs.c:285)
+    assert a.size() == 1.0 and len(a.centroids()) == 1
+    with pytest.raises(ValueError):
+        a.update([1.0], [0.0])
+    with pytest.raises(ValueError):
+        a.update([1.0], [np.nan])
+    with pytest.raises(TypeError):
+        a.update(["a"])
+
+
+def test_empty_single_and_shapes(cb):
+    t = cb.TDigest()
+    assert np.isnan(t.min()) and np.isnan(t.max()) and t.size() == 0
+    assert np.isnan(t.quantile(0.5)) and np.isnan(t.cdf(1.0))
+    assert len(t.centroids()) == 0
+    t.update([])
+    assert t.size() == 0
+    t.add(10)
+    assert [t.quantile(q) for q in (0, 0.5, 1)] == [10, 10, 10]
+    assert [t.cdf(x) for x in (9, 10, 11)] == [0, 0.5, 1]
+    assert isinstance(t.quantile(0.5), np.float64)
+    assert t.quantile(np.zeros((2, 3))).shape == (2, 3)
+    assert t.cdf(np.zeros((0,))).shape == (0,)
+    assert repr(t) == "TDigest<compression=100.0, size=1.0>"
+    assert cb.TDigest(5).compression == 20.0 and cb.TDigest(5000).compression == 1000.0
+
+
+def test_korder_inputs(cb, golden):
+    """Non-contiguous inputs are consumed in memory (K) order like NpyIter does
+    (tdigest_stubs.c:652-666); shas recorded from the built reference."""
+    g, a = golden
+    base, wv = a["korder_base"], a["korder_w"]
+    cases = {"rev": (base.ravel()[::-1], 1), "fortran": (np.asfortranarray(base), 1),
+             "transposed": (base.T, 1), "strided": (base.ravel()[::2], 1),
+             "rev_fw": (base.ravel()[::-1], wv.ravel()), "bcast_w": (base, wv[0]),
+             "t_w": (base.T, wv.T), "scalar_x": (1.5, wv.ravel()[:100])}
+    for name, (x, w) in cases.items():
+        t = cb.TDigest(100, mode="reference")
+        t.update(x, w)
+        assert sha(t) == g["korder"][name], name
+
+
+def test_merge_semantics_vs_oracle(cb):
+    rng = np.random.default_rng(3)
+    ours, theirs = [], []
+    for k, c in enumerate([100, 100, 500, 50, 100]):
+        x = rng.normal(k, 1 + k, 3000 + 17 * k)
+        p, o = cb.TDigest(c, mode="reference"), R.TDigest(c)
+        p.update(x)
+        o.update(x)
+        ours.append(p)
+        theirs.append(o)
+    a, b = cb.TDigest(100, mode="reference"), R.TDigest(100)
+    # 10 values stay in the buffer: merge feeds through it and does not flush T (:592-606)
+    x0 = rng.normal(size=10)
+    a.update(x0)
+    b.update(x0)
+    a.merge(*ours)
+    b.merge(*theirs)
+    assert a.size() == b.size()
+    same(a, b)
+    for p, o in zip(ours, theirs):   # merge flushes the others but does not change them
+        same(p, o)
+    empty = cb.TDigest()
+    a.merge(empty)
+    same(a, b)
+    with pytest.raises(TypeError):
+        a.merge(1)
+
+
+def test_scale_pickle_histogram(cb):
+    rng = np.random.default_rng(5)
+    x = rng.gamma(2.0, size=50000)
+    a, b = cb.TDigest(mode="reference"), R.TDigest()
+    a.update(x)
+    b.update(x)
+    for f in (0.5, 2, 1e-3, np.finfo("f8").eps):
+        same(a.scale(f), b.scale(f))
+    with pytest.raises(ValueError):
+        a.scale(0)
+    a2 = pickle.loads(pickle.dumps(a))
+    same(a2, b)
+    assert a2.compression == a.compression
+    # quirk: compaction copies weight but not mean (tdigest_stubs.c:621)
+    t = cb.TDigest()
+    t.update([1, 2, 3, 4, 5], [1, 1000, 1, 10000, 1])
+    c = t.scale(np.finfo("f8").eps).centroids()
+    assert c["mean"].tolist() == [1.0, 2.0] and len(c) == 2
+    h, e = a.histogram(20)
+    cdf = b.cdf(e)
+    assert np.array_equal(h, (cdf[1:] - cdf[:-1]) * b.size())
+    assert abs(h.sum() - a.size()) < 1e-6 * a.size()
+    h2, e2 = a.histogram([0.0, 1.0, 2.0, 100.0])
+    assert h2.shape == (3,)
+    with pytest.raises(ValueError):
+        a.histogram([2.0, 1.0])
+
+
+@pytest.mark.parametrize("dist", ["gamma", "uniform", "normal", "sequential", "step"])
+def test_rank_error_bounds_of_the_reference_tests(cb, dist):
+    """crick/tests/test_tdigest.py:72-107: monotone quantiles, rank error <= 0.012,
+    cdf error <= 0.005, exact size/min/max -- on both update modes."""
+    rng = np.random.default_rng(21)
+    n = 100000
+    data = {"gamma": rng.gamma(0.1, 0.1, n), "uniform": rng.uniform(0, 1, n),
+            "normal": rng.normal(0, 1e-5, n), "sequential": np.arange(n) * 1e-5,
+            "step": np.concatenate([rng.uniform(0, 1, n // 2), rng.uniform(2, 3, n // 2)])}[dist]
+    for mode in ("reference", "parallel"):
+        t = cb.TDigest(mode=mode)
+        t.update(data)
+        assert t.size() == n and t.min() == data.min() and t.max() == data.max()
+        qs = np.linspace(0.001, 0.999, 100)
+        est = t.quantile(qs)
+        assert (np.diff(est) > 0).all()
+        c = t.cdf(est)
+        assert ((c >= 0) & (c <= 1)).all()
+        assert np.abs(quantiles_to_q(data, t.quantile(QS9)) - QS9).max() <= 0.012, mode
+        assert np.abs(t.cdf(q_to_x(data, QS9)) - QS9).max() <= 0.005, mode
+
+
+def test_device_array_inputs_match_host_inputs(cb):
+    rng = np.random.default_rng(9)
+    x = rng.lognormal(size=70000)
+    w = rng.uniform(0.5, 1.5, 70000)
+    a, b = cb.TDigest(mode="reference"), cb.TDigest(mode="reference")
+    a.update(x, w)
+    b.update(cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w))
+    assert a.centroids().tobytes() == b.centroids().tobytes()
+    qd = cb.DeviceArray.from_numpy(QS9)
+    assert a.quantile(qd).to_numpy().tobytes() == a.quantile(QS9).tobytes()
+    import torch
+    tx = torch.from_numpy(x).cuda()
+    c = cb.TDigest(mode="reference")
+    c.update(tx, 2.0)           # __cuda_array_interface__ / DLPack of a foreign library
+    d = R.TDigest()
+    d.update(x, 2.0)
+    assert c.centroids().tobytes() == d.centroids().tobytes()
+
+
+# ---- grouped digests and the merge tree (BASELINE configs[2], [3]) ---------------------
+def test_grouped_fixed_rows_vs_oracle(cb):
+    rng = np.random.default_rng(2)
+    vals = rng.normal(size=(3000, 1000))
+    g = cb.TDigestGroup(3000, 100)
+    g.update(vals)
+    rows = list(range(0, 3000, 53))
+    for r in rows:
+        b = R.TDigest(100)
+        b.update(vals[r])
+        assert g.centroids(r).tobytes() == b.centroids().tobytes(), r
+    q = g.quantile([0.1, 0.5, 0.9])
+    c = g.cdf([-1.0, 0.0, 1.0])
+    for r in rows[:10]:
+        b = R.TDigest(100)
+        b.update(vals[r])
+        assert q[r].tobytes() == b.quantile([0.1, 0.5, 0.9]).tobytes()
+        assert c[r].tobytes() == b.cdf([-1.0, 0.0, 1.0]).tobytes()
+    meta = g.meta()
+    assert (meta[:, 1] + 0 >= 0).all()
+
+
+def test_grouped_ragged_weighted_and_incremental(cb):
+    rng = np.random.default_rng(4)
+    lens = rng.integers(0, 400, 500)
+    lens[7] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    v = rng.lognormal(size=off[-1])
+    w = rng.uniform(0.5, 2.0, off[-1])
+    g = cb.TDigestGroup(500, 200)
+    g.update(v, w, offsets=off)
+    g.update(v, w, offsets=off)          # second batch continues each group's buffer phase
+    for r in range(0, 500, 11):
+        b = R.TDigest(200)
+        sl = slice(off[r], off[r + 1])
+        if lens[r]:
+            b.update(v[sl], w[sl])
+            b.update(v[sl], w[sl])
+        assert g.centroids(r).tobytes() == b.centroids().tobytes(), r
+    d = g.digest(3)
+    assert d.centroids().tobytes() == g.centroids(3).tobytes()
+
+
+@pytest.mark.parametrize("ngroups", [1, 2, 37, 64])
+def test_tree_merge_vs_nested_oracle_merges(cb, ngroups):
+    rng = np.random.default_rng(ngroups)
+    v = rng.normal(size=(ngroups, 2000))
+    g = cb.TDigestGroup(ngroups, 200)
+    g.update(v)
+    tm = g.merge_tree()
+    ds = []
+    for r in range(ngroups):
+        b = R.TDigest(200)
+        b.update(v[r])
+        ds.append(b)
+    s = 1
+    while s < ngroups:
+        for k in range(0, ngroups, 2 * s):
+            if k + s < ngroups:
+                ds[k].merge(ds[k + s])
+        s *= 2
+    same(tm, ds[0])
+    qs = rng.uniform(0, 1, 5000)
+    assert tm.quantile(qs).tobytes() == ds[0].quantile(qs).tobytes()
+    xs = rng.normal(size=5000)
+    assert tm.cdf(xs).tobytes() == ds[0].cdf(xs).tobytes()
+
+
+def test_large_query_batch_vs_oracle(cb):
+    """Config-4 query shape: millions of device-resident queries, bit-exact vs the oracle, plus
+    the size-independent properties (monotone, cdf(quantile(q)) ~ q)."""
+    rng = np.random.default_rng(8)
+    x = rng.normal(size=200000)
+    t, o = cb.TDigest(200, mode="reference"), R.TDigest(200)
+    t.update(x)
+    o.update(x)
+    q = np.sort(rng.uniform(0.0005, 0.9995, 2 * 10**6))
+    dq = cb.DeviceArray.from_numpy(q)
+    dx = t.quantile(dq)
+    xs = dx.to_numpy()
+    assert xs.tobytes() == o.quantile(q).tobytes()
+    back = t.cdf(dx).to_numpy()
+    assert back.tobytes() == o.cdf(xs).tobytes()
+    assert (np.diff(xs) >= 0).all()
+    assert np.abs(back - q).max() < 1e-3
