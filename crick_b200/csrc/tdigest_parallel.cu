@@ -41,7 +41,9 @@ namespace crick {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-constexpr int kNC = 4096;        // lookup-table cells
+constexpr int kNC = 8192;        // lookup-table cells (uint16 entries, + 2 sentinels)
+constexpr int kTabLen = kNC + 2;
+constexpr size_t kTabBytes = ((size_t)kTabLen * 2 + 15) & ~(size_t)15;
 constexpr int kEMax = 1024;      // max edges (buckets - 1)
 constexpr int kBPad = kEMax + 8; // row stride of the per-CTA partial sums
 constexpr long kSMax = 65536;    // max sample size
@@ -49,11 +51,14 @@ constexpr int kSortChunk = 4096; // elements sorted per CTA in shared memory
 
 struct ParHeader {
     int E;       // number of edges; buckets = E + 1, bucket b = [edge[b-1], edge[b])
-    int shift;   // cell = ((key - ubase) >> shift) + 1
-    unsigned long long ubase;
+    int shift;   // grid 0: cell = (((skey(x) >> 1) - kbase) >> shift) + 1
+    int kbase;
+    int pad0;
     long S;      // sample length (power of two)
     int ncta;    // CTAs that wrote partials
     int grid;    // lookup grid: 0 = linear in the ordered bit pattern, 1 = linear in x
+    int kmax;    // most edges in any one cell of that grid
+    int pad;
     double sample_total;
     double x0;   // grid 1: cell = (int)((x - x0) * inv) + 1
     double inv;
@@ -62,8 +67,8 @@ struct ParHeader {
 struct ParLayout {
     ParHeader* hdr;
     double* edges;       // [kEMax]
-    unsigned* tab;       // [kNC]   lo | hi << 16 (the grid k_make_edges chose)
-    unsigned* tab2;      // [kNC]   scratch: candidate table of the other grid
+    unsigned short* tab;   // [kTabLen] tab[c] = #edges in cells < c (the grid k_make_edges chose)
+    unsigned short* tab2;  // [kTabLen] scratch: candidate table of the other grid
     double* sx;          // [kSMax]
     double* sw;          // [kSMax]
     double* cw;          // [kSMax]
@@ -96,9 +101,8 @@ static size_t fin_ws_bytes(int cap, int mmax) {
 size_t parallel_scratch_bytes(double comp, int sm_count) {
     int cap = 2 * (int)ceil(comp);
     size_t b = 256;
-    b += sizeof(double) * kEMax + sizeof(unsigned) * kNC;
+    b += sizeof(double) * kEMax + 2 * kTabBytes;
     b += 3 * sizeof(double) * kSMax;
-    b += sizeof(unsigned) * kNC;
     b += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     b += sizeof(double2) * (size_t)(2 * sm_count);
     b += fin_ws_bytes(cap, mmax_for(comp)) + 64;
@@ -110,11 +114,11 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
     unsigned char* p = reinterpret_cast<unsigned char*>(scratch);
     L.hdr = reinterpret_cast<ParHeader*>(p); p += 256;
     L.edges = reinterpret_cast<double*>(p); p += sizeof(double) * kEMax;
-    L.tab = reinterpret_cast<unsigned*>(p); p += sizeof(unsigned) * kNC;
+    L.tab = reinterpret_cast<unsigned short*>(p); p += kTabBytes;
+    L.tab2 = reinterpret_cast<unsigned short*>(p); p += kTabBytes;
     L.sx = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.sw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.cw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
-    L.tab2 = reinterpret_cast<unsigned*>(p); p += sizeof(unsigned) * kNC;
     L.partial = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     L.minmax = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count);
     L.fin = p;
@@ -124,7 +128,7 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
 
 double* parallel_sample_x(void* scratch) {
     return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256 +
-                                     sizeof(double) * kEMax + sizeof(unsigned) * kNC);
+                                     sizeof(double) * kEMax + 2 * kTabBytes);
 }
 double* parallel_sample_w(void* scratch) { return parallel_sample_x(scratch) + kSMax; }
 long parallel_sample_capacity(void*) { return kSMax; }
@@ -245,24 +249,35 @@ static cudaError_t sort_sample(double* keys, double* vals, long L, cudaStream_t 
 }
 
 // 3. edges + lookup table.  Single CTA, 1024 threads.
-__device__ __forceinline__ int cell_of(unsigned long long key, unsigned long long ubase, int shift) {
-    if (key < ubase) return 0;
-    unsigned long long c = ((key - ubase) >> shift) + 1ull;
-    return c > (unsigned long long)(kNC - 1) ? (kNC - 1) : (int)c;
+//
+// Two candidate grids of kNC cells over [edges[0], edges[E-1]]; cell 0 = below the first edge.
+// Both maps are monotone non-decreasing in x, which is all the lookup needs.
+//  grid 0: linear in the (signed-orderable) HIGH WORD of the bit pattern, i.e. ~ log|x| with
+//          2^-20 relative resolution -- good for heavy-tailed data of one sign;
+//  grid 1: linear in x -- good for data that crosses zero or sits in a narrow band.
+__device__ __forceinline__ int skey_half(double x) {
+    int hi = __double2hiint(x + 0.0);                  // -0.0 -> +0.0: zeros tie
+    return (hi ^ ((hi >> 31) & 0x7fffffff)) >> 1;      // signed order == order of x; >> 1: no overflow below
 }
-
+__device__ __forceinline__ int clamp_cell(int c) {     // c = -1 (below) .. -> cell 0 .. kNC - 1
+    c += 1;
+    c = c < 0 ? 0 : c;
+    return c > kNC - 1 ? kNC - 1 : c;
+}
+__device__ __forceinline__ int cell_key(double x, int kbase, int shift) {
+    return clamp_cell((skey_half(x) - kbase) >> shift);
+}
 __device__ __forceinline__ int cell_lin(double x, double x0, double inv) {
-    if (x < x0) return 0;
-    // cvt.rzi.s32.f64 saturates (NaN -> 0): any finite or infinite x gives a valid cell
-    int c = __double2int_rz(__dmul_rn(__dadd_rn(x, -x0), inv));
-    return (c > kNC - 2 ? kNC - 2 : c) + 1;
+    // cvt.rmi.s32.f64 saturates (NaN -> 0): any finite or infinite x gives a valid cell
+    return clamp_cell(__double2int_rd(__dmul_rn(__dadd_rn(x, -x0), inv)));
 }
 
 __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const double* __restrict__ sx,
                                                      const double* __restrict__ sw,
                                                      double* __restrict__ cw, double* __restrict__ edges,
-                                                     unsigned* __restrict__ tab,
-                                                     unsigned* __restrict__ tab2, double comp, int ov) {
+                                                     unsigned short* __restrict__ tab,
+                                                     unsigned short* __restrict__ tab2, double comp,
+                                                     int ov) {
     __shared__ double s_part[1024];
     __shared__ double s_raw[kEMax];
     __shared__ int s_cnt[kEMax];
@@ -345,66 +360,70 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     }
     __syncthreads();
     const int E = s_E;
-    // d. lookup tables.  Two candidate grids of kNC cells: linear in the order-preserving bit
-    // pattern (~ log x: good for heavy-tailed positive data) and linear in x (good for data
-    // that crosses zero, where the bit pattern spends its cells on the denormal range).
-    // cost = sum over cells of m * ceil(log2(m + 1)), m = edges in the cell, ~ expected
-    // compares per value; the cheaper grid goes to `tab`.
+    // d. lookup tables: tab[c] = #edges whose cell is < c (so the edges of cell c are
+    // tab[c] .. tab[c+1]-1), for both grids; keep the one whose fullest cell holds fewer edges
+    // (ties: fewer expected compares).
     __shared__ unsigned long long s_cost[2];
-    unsigned long long ubase = 0;
-    int shift = 0;
+    __shared__ int s_kmax[2];
+    int kbase = 0, shift = 0;
     double x0 = 0.0, inv = 0.0;
     bool lin_ok = false;
     if (E > 0) {
-        ubase = ordered_key(edges[0]);
-        unsigned long long span = ordered_key(edges[E - 1]) - ubase;
-        while (shift < 63 && ((span >> shift) + 1ull) > (unsigned long long)(kNC - 2)) ++shift;
+        kbase = skey_half(edges[0]);
+        long long span = (long long)skey_half(edges[E - 1]) - (long long)kbase;
+        while (shift < 31 && ((span >> shift) + 1ll) > (long long)(kNC - 2)) ++shift;
         x0 = edges[0];
         double width = edges[E - 1] - x0;
         inv = (double)(kNC - 2) / width;
         lin_ok = E >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv);
     }
-    if (tid < 2) s_cost[tid] = 0ull;
+    if (tid < 2) { s_cost[tid] = 0ull; s_kmax[tid] = 0; }
     __syncthreads();
     for (int g = 0; g < 2; ++g) {
-        unsigned* out = g == 0 ? tab : tab2;
+        unsigned short* out = g == 0 ? tab : tab2;
         if (g == 1 && !lin_ok) break;
         unsigned long long local = 0;
-        for (int cell = tid; cell < kNC; cell += blockDim.x) {
+        int lmax = 0;
+        for (int cell = tid; cell < kTabLen; cell += blockDim.x) {
             // lo = #edges with cell(e) < cell ; hi = #edges with cell(e) <= cell
             int a = 0, b = E;
             while (a < b) {
                 int mid = (a + b) >> 1;
-                int ce_ = g == 0 ? cell_of(ordered_key(edges[mid]), ubase, shift)
-                                 : cell_lin(edges[mid], x0, inv);
+                int ce_ = g == 0 ? cell_key(edges[mid], kbase, shift) : cell_lin(edges[mid], x0, inv);
                 if (ce_ < cell) a = mid + 1; else b = mid;
             }
             int lo = a;
             b = E;
             while (a < b) {
                 int mid = (a + b) >> 1;
-                int ce_ = g == 0 ? cell_of(ordered_key(edges[mid]), ubase, shift)
-                                 : cell_lin(edges[mid], x0, inv);
+                int ce_ = g == 0 ? cell_key(edges[mid], kbase, shift) : cell_lin(edges[mid], x0, inv);
                 if (ce_ <= cell) a = mid + 1; else b = mid;
             }
-            out[cell] = (unsigned)lo | ((unsigned)a << 16);
+            out[cell] = (unsigned short)lo;
             int m = a - lo, lg = 0;
             while ((1 << lg) < m + 1) ++lg;
             local += (unsigned long long)m * (unsigned long long)lg;
+            lmax = m > lmax ? m : lmax;
         }
         atomicAdd(&s_cost[g], local);
+        atomicMax(&s_kmax[g], lmax);
     }
     __syncthreads();
-    const int grid = (lin_ok && s_cost[1] < s_cost[0]) ? 1 : 0;
+    int grid = 0;
+    if (lin_ok) {
+        if (s_kmax[0] != s_kmax[1]) grid = s_kmax[1] < s_kmax[0] ? 1 : 0;
+        else grid = s_cost[1] <= s_cost[0] ? 1 : 0;
+    }
     if (grid == 1)
-        for (int cell = tid; cell < kNC; cell += blockDim.x) tab[cell] = tab2[cell];
+        for (int cell = tid; cell < kTabLen; cell += blockDim.x) tab[cell] = tab2[cell];
     if (tid == 0) {
         hdr->E = E;
         hdr->shift = shift;
-        hdr->ubase = ubase;
+        hdr->kbase = kbase;
         hdr->sample_total = Wt;
         hdr->ncta = 0;
         hdr->grid = grid;
+        hdr->kmax = s_kmax[grid];
         hdr->x0 = x0;
         hdr->inv = inv;
     }
@@ -413,107 +432,187 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
 // 4. THE HOT KERNEL -----------------------------------------------------------
 //
 // Weighted histogram of (sum w, sum w*x) over B <= bmax buckets, one pass over HBM.
-// round-1 profile (profiles/r1_a_*): resolving intra-warp bucket collisions with
-// __match_any_sync saturates the ADU pipe (92 %) at ~0.5 value/clk/SM.  This version needs
-// neither MATCH nor atomics:
-//   * every warp owns a private table acc[bucket][C] of double2 in shared memory,
-//     C = 8 (or 4/2/1 for large compressions) COLUMNS per bucket;
-//   * lane l only ever touches column l % C, and the 32/C lanes that share a column take
-//     turns in P = 32/C passes separated by __syncwarp().  Inside a pass the C active lanes
-//     form (part of) one quarter-warp and hit C distinct 16-byte slots: every LDS.128/STS.128
-//     is a single conflict-free wavefront;
-//   * a lane's U = 4 values of one group are de-duplicated in registers first (equal buckets
-//     are folded, the later one is redirected to a dummy row), so the 4 read-modify-writes of
-//     a pass are independent and overlap.
-// Bucket lookup: one probe of a 4096-cell table over a grid that is linear either in x or in
-// the order-preserving bit pattern of x (k_make_edges picks the cheaper one), then 0-2
-// compares against the edges that fall into the cell.
-struct Lookup {
-    const unsigned* tab;   // shared
-    const double* edges;   // shared
-    unsigned long long ubase;
-    double x0, inv;
-    int shift;
-    int E;
-};
+// History (profiles/): (r1_a) resolving intra-warp bucket collisions with __match_any_sync
+// saturates the ADU pipe (92 %) at ~0.5 value/clk/SM; (r1_b) per-warp tables with 8 columns and
+// 4 lane passes: 103 instructions per 32 values on 8 warps, latency bound.  This version:
+//   * ONE table acc[bucket][C] of double2 in shared memory, C = 32 columns when it fits
+//     (c <= 100), else 16 / 8: lane l owns column l % C, so LDS.128 / STS.128 of a warp are
+//     conflict-free and need neither MATCH nor atomics (C < 32: the 32/C lanes that share a
+//     column take turns in passes);
+//   * the warps take turns on the table: a token travels round-robin over named barriers
+//     (bar.sync / bar.arrive on 64 threads) and only the holder does its read-modify-writes,
+//     4 LDS + 8 DADD + 4 STS per 128 values; loads, bucket lookup and de-duplication run
+//     outside the critical section on all 12 warps.  The fixed order makes sums deterministic;
+//   * a lane's 4 values of one group are de-duplicated in registers first (equal buckets are
+//     folded, the later one is redirected to a dummy row), so the 4 read-modify-writes are
+//     independent and overlap.
+// Bucket lookup: one uint16 probe of the 16384-cell table (k_make_edges picks the grid), then a
+// branch-free count of the <= kmax edges of that cell that are <= x.  Shared memory is
+// addressed with 32-bit shared-window addresses (inline PTX) to keep the integer work short.
+constexpr int kU = 4;         // values per lane per group
+constexpr int kKFast = 8;     // branch-free lookup when no cell holds more edges than this
+constexpr int kEdgePad = 8;   // +inf edges after the last one (the branch-free scan overruns)
 
-template <int GRID>
-__device__ __forceinline__ int bucket_of(const Lookup& L, double x) {
-    int cell;
-    if (GRID == 1) cell = cell_lin(x, L.x0, L.inv);
-    else cell = cell_of(ordered_key(x + 0.0), L.ubase, L.shift);  // -0.0 -> +0.0: zeros tie
-    unsigned t = L.tab[cell];
-    int lo = (int)(t & 0xffffu), hi = (int)(t >> 16);
-    while (lo < hi) {  // #edges <= x, restricted to the cell's candidates
-        int mid = (lo + hi) >> 1;
-        if (L.edges[mid] <= x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64x2(unsigned addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void bar_sync64(int id) {
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void bar_arrive64(int id) {
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
 }
 
-constexpr int kU = 4;  // values per lane per group
+// if (ai == aj) { wj += wi; sj += si; ai = daddr; } without branches: f = 1.0 or 0.0 from one
+// 32-bit select, then two fused multiply-adds (exact: the product is wi or 0).  ptxas turns a
+// predicated add.f64 into DADD + 2 FSEL per double (r1_g profile: 14 FSEL per value).
+// Caveat: a non-finite wi / si (w*x overflow) times 0 is NaN.
+__device__ __forceinline__ void fold_if_equal(unsigned& ai, unsigned aj, double& wj, double& sj,
+                                              double wi, double si, unsigned daddr) {
+    const bool eq = ai == aj;
+    const double f = __hiloint2double(eq ? 0x3ff00000 : 0, 0);
+    wj = __fma_rn(wi, f, wj);
+    sj = __fma_rn(si, f, sj);
+    ai = eq ? daddr : ai;
+}
 
-// One group: lane holds kU (x, w) pairs.  acc_col = this warp's table + (lane % C).
-template <bool HAS_W, int C, int GRID>
-__device__ __forceinline__ void accumulate_group(const Lookup& L, double2* acc_col, int dummy,
-                                                 const double* xs, const double* ws, double wsc,
-                                                 unsigned valid_mask, int pass, double& vmin,
-                                                 double& vmax) {
-    constexpr int P = 32 / C;
-    int idx[kU];
-    double ww[kU], ss[kU];
-    const int top = L.E - 1;
+struct Lookup {
+    unsigned tab;     // shared-window byte addresses
+    unsigned edges;
+    unsigned acc;     // this lane's column: acc base + (lane % C) * 16
+    int row_shift;    // log2(C * 16): byte stride of a bucket row
+    int dummy;        // dummy bucket index (= bmax)
+    int kbase, shift; // grid 0
+    double x0, inv;   // grid 1
+    int E, kmax;
+    unsigned ext_lo, ext_span;  // bucket b may hold the min/max iff (b - ext_lo) >= ext_span (unsigned)
+};
+
+// One group: kU (x, w) pairs of this lane -> shared addresses of the accumulators + the
+// (w, w*x) to add, equal buckets folded.  Returns true if some value may be the min / max.
+template <bool HAS_W, int GRID, bool FAST>
+__device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs, const double* ws,
+                                               double wsc, unsigned valid_mask, unsigned* addr,
+                                               double* ww, double* ss) {
+    int b[kU];
+    unsigned ea[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-        const double x = xs[u];
-        const double w = HAS_W ? ws[u] : wsc;
-        bool ok = is_finite_d(x) && !(w <= DBL_EPSILON) && ((valid_mask >> u) & 1u);  // :285
-        int b = bucket_of<GRID>(L, x);
-        // the minimum lies in bucket 0 or 1 and the maximum in bucket E-1 or E (edges are data
-        // values, or nextafter of one): only those values need the fp64 min/max
-        if (ok && (b <= 1 || b >= top)) {
-            vmin = x < vmin ? x : vmin;
-            vmax = x > vmax ? x : vmax;
+        int cell = GRID == 1 ? cell_lin(xs[u], L.x0, L.inv) : cell_key(xs[u], L.kbase, L.shift);
+        unsigned ta = L.tab + 2u * (unsigned)cell;
+        b[u] = (int)lds_u16(ta);
+        if (FAST) ea[u] = L.edges + 8u * (unsigned)b[u];
+        else ea[u] = lds_u16(ta + 2u);                     // hi = first edge of the next cell
+    }
+    if (FAST) {
+        // edges of later cells are > x and the pad is +inf: counting kmax entries is exact
+#pragma unroll 1
+        for (int j = 0; j < L.kmax; ++j) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                // b += (edge <= x): a predicated add (the compiler's select costs 3 moves)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .f64 e;\n\t"
+                    "ld.shared.f64 e, [%1];\n\t"
+                    "setp.le.f64 p, e, %2;\n\t"
+                    "@p add.s32 %0, %0, 1;\n\t}"
+                    : "+r"(b[u]) : "r"(ea[u]), "d"(xs[u]));
+                ea[u] += 8u;
+            }
         }
-        // rejected values go to the dummy row (never read back), whatever their w / w*x
-        idx[u] = (ok ? b : dummy) * C;
+    } else {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            int lo = b[u], hi = (int)ea[u];
+            while (lo < hi) {  // #edges <= x among the cell's candidates
+                int mid = (lo + hi) >> 1;
+                if (lds_f64(L.edges + 8u * (unsigned)mid) <= xs[u]) lo = mid + 1; else hi = mid;
+            }
+            b[u] = lo;
+        }
+    }
+    bool ext = false;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        const double w = HAS_W ? ws[u] : wsc;
+        // tdigest_add's filter (:285): finite x, and not (w <= eps)
+        const bool finite = fabs(xs[u]) <= DBL_MAX;
+        const bool ok = finite && !(w <= DBL_EPSILON) && ((valid_mask >> u) & 1u);
+        ext |= ok && ((unsigned)b[u] - L.ext_lo >= L.ext_span);
+        // rejected values go to the dummy row (never read back), whatever their w / w*x --
+        // but w*x must stay finite: fold_if_equal multiplies it by 0 (a NaN or infinite x
+        // becomes a denormal: high word cleared)
+        addr[u] = L.acc + ((unsigned)(ok ? b[u] : L.dummy) << L.row_shift);
         ww[u] = w;
-        ss[u] = __dmul_rn(w, x);
+        const double xf = __hiloint2double(finite ? __double2hiint(xs[u]) : 0, __double2loint(xs[u]));
+        ss[u] = __dmul_rn(w, xf);
     }
     // fold equal buckets of this lane (fixed order => deterministic sums)
+    const unsigned daddr = L.acc + ((unsigned)L.dummy << L.row_shift);
 #pragma unroll
     for (int i = 1; i < kU; ++i) {
 #pragma unroll
         for (int j = 0; j < i; ++j) {
-            if (idx[i] == idx[j]) {
-                ww[j] = __dadd_rn(ww[j], ww[i]);
-                ss[j] = __dadd_rn(ss[j], ss[i]);
-                idx[i] = dummy * C;
-            }
+            fold_if_equal(addr[i], addr[j], ww[j], ss[j], ww[i], ss[i], daddr);
         }
     }
+    return ext;
+}
+
+// exact min / max: only values of buckets 0, 1, E-1, E can be it (edges are data values, or
+// nextafter of one), so this runs for ~1 warp-step in 100
+template <bool HAS_W>
+__device__ __forceinline__ void minmax_group(const Lookup& L, const double* xs, const double* ws,
+                                          double wsc, unsigned valid_mask, double& vmin,
+                                          double& vmax) {
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        if (pass == p) {
-            double2 a[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) a[u] = acc_col[idx[u]];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                a[u].x = __dadd_rn(a[u].x, ww[u]);
-                a[u].y = __dadd_rn(a[u].y, ss[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) acc_col[idx[u]] = a[u];
+    for (int u = 0; u < kU; ++u) {
+        const double w = HAS_W ? ws[u] : wsc;
+        const bool ok = (fabs(xs[u]) <= DBL_MAX) && !(w <= DBL_EPSILON) && ((valid_mask >> u) & 1u);
+        if (ok) {
+            vmin = xs[u] < vmin ? xs[u] : vmin;
+            vmax = xs[u] > vmax ? xs[u] : vmax;
         }
-        __syncwarp();
     }
 }
+
+// read-modify-write of N accumulators with pairwise distinct addresses (or the dummy row):
+// all loads first, so the token holder pays one LDS latency, not N
+template <int N>
+__device__ __forceinline__ void rmw(const unsigned* addr, const double* ww, const double* ss) {
+    double2 a[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) a[u] = lds_f64x2(addr[u]);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        a[u].x = __dadd_rn(a[u].x, ww[u]);
+        a[u].y = __dadd_rn(a[u].y, ss[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < N; ++u) sts_f64x2(addr[u], a[u]);
+}
+
+// tile = 2 groups x 4 values x 32 lanes; lane's values are the double2s k*32 + lane, k = 0..3
+constexpr long kTile = 32L * 2 * kU;
 
 template <bool HAS_W, bool VEC>
 __device__ __forceinline__ void load_tile(const double* __restrict__ X, const double* __restrict__ W,
                                           long base, int lane, double* xs, double* ws) {
-    // tile = 2 groups x 4 values x 32 lanes; lane's values: VEC -> double2 k*32+lane, k = 0..3
     if (VEC) {
         const double2* x2 = reinterpret_cast<const double2*>(X + base);
 #pragma unroll
@@ -543,89 +642,240 @@ __device__ __forceinline__ void load_tile(const double* __restrict__ X, const do
     }
 }
 
-template <bool HAS_W, bool VEC, int C, int GRID>
-__device__ __forceinline__ void accumulate_stream(const Lookup& L, double2* acc_col, int dummy,
-                                                  const double* __restrict__ X,
-                                                  const double* __restrict__ W, double wsc, long n,
-                                                  long gw, long tw, int lane, double& vmin,
-                                                  double& vmax) {
-    constexpr long TILE = 32L * 2 * kU;  // values per warp iteration
-    const int pass = lane / C;
-    const long ntiles = n / TILE;
-    double xa[2 * kU], wa[2 * kU], xb[2 * kU], wb[2 * kU];
-    double* xs = xa;
-    double* ws = wa;
-    // register ping-pong: the loads of tile t + tw are in flight while tile t is processed
-    long t = gw;
-    if (t < ntiles) load_tile<HAS_W, VEC>(X, W, t * TILE, lane, xa, wa);
-    while (t < ntiles) {
-        long tn = t + tw;
-        if (tn < ntiles) load_tile<HAS_W, VEC>(X, W, tn * TILE, lane, xb, wb);
-        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xa, wa, wsc, 0xfu, pass, vmin, vmax);
-        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xa + kU, wa + kU, wsc, 0xfu, pass,
-                                         vmin, vmax);
-        t = tn;
-        if (t >= ntiles) break;
-        tn = t + tw;
-        if (tn < ntiles) load_tile<HAS_W, VEC>(X, W, tn * TILE, lane, xa, wa);
-        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xb, wb, wsc, 0xfu, pass, vmin, vmax);
-        accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xb + kU, wb + kU, wsc, 0xfu, pass,
-                                         vmin, vmax);
-        t = tn;
-    }
-    // ragged tail (< TILE values): the warp whose turn it would be
-    if (gw == ntiles % tw) {
-        for (long i0 = ntiles * TILE; i0 < n; i0 += 32 * kU) {
-            unsigned m = 0;
+// the last, partial tile: guarded loads, same element -> lane mapping; returns the valid mask
+template <bool HAS_W>
+__device__ __forceinline__ unsigned load_partial(const double* __restrict__ X,
+                                              const double* __restrict__ W, long base, long n,
+                                              int lane, double* xs, double* ws) {
+    unsigned m = 0;
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                long i = i0 + u * 32 + lane;
-                bool in = i < n;
-                xs[u] = in ? X[i] : 0.0;
-                if (HAS_W) ws[u] = in ? W[i] : 0.0;
-                m |= in ? (1u << u) : 0u;
-            }
-            accumulate_group<HAS_W, C, GRID>(L, acc_col, dummy, xs, ws, wsc, m, pass, vmin, vmax);
+    for (int k = 0; k < 2 * kU; ++k) {
+        long i = base + (k >> 1) * 64 + 2 * lane + (k & 1);
+        bool in = i < n;
+        xs[k] = in ? X[i] : 0.0;
+        if (HAS_W) ws[k] = in ? W[i] : 0.0;
+        m |= in ? (1u << k) : 0u;
+    }
+    return m;
+}
+
+struct Ring {
+    int id_in, id_out;  // named barriers: token into this warp / into the next one
+    bool first;         // ring position 0 starts with the token
+    int passes;         // 32 / C
+    int pass;           // lane / C
+};
+
+// ---- TMA staging: one 4 KB stage (2 KB of x + 2 KB of w) and one mbarrier per warp ---------
+// The next tile is fetched by cp.async.bulk (SASS: UBLKCP) while the current one is classified;
+// completion is signalled on the mbarrier, so the prefetch shares no register scoreboard with
+// the tile in flight (the r1_d/r1_e profiles: with LDG prefetch into registers 32 % of the warp
+// time went to long-scoreboard waits on the *newer* load).
+constexpr int kStageBytes = 2 * (int)kTile * 8;
+
+__device__ __forceinline__ void mbar_init(unsigned mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE_%=;\n\t"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n\t}"
+        ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes,
+                                            unsigned mbar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+template <bool HAS_W>
+__device__ __forceinline__ void stage_issue(const double* __restrict__ X, const double* __restrict__ W,
+                                            long base, unsigned stage, unsigned mbar) {
+    mbar_expect_tx(mbar, HAS_W ? kStageBytes : kStageBytes / 2);
+    tma_load_1d(stage, X + base, kStageBytes / 2, mbar);
+    if (HAS_W) tma_load_1d(stage + kStageBytes / 2, W + base, kStageBytes / 2, mbar);
+}
+
+// stage-free alternative: pull the next tile into L2; the LDGs of the next round then wait for
+// an L2 hit, not for DRAM, and no shared memory is spent on staging.  One 128-byte line per
+// lane: lanes 0-15 cover the 2 KB of x, lanes 16-31 the 2 KB of w.
+template <bool HAS_W>
+__device__ __forceinline__ void l2_prefetch(const double* __restrict__ X, const double* __restrict__ W,
+                                            long base, int lane) {
+    const double* p = (HAS_W && lane >= 16) ? W + base + (lane - 16) * 16 : X + base + lane * 16;
+    if (HAS_W || lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <bool HAS_W>
+__device__ __forceinline__ void stage_read(unsigned stage, int lane, double* xs, double* ws) {
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+        double2 a = lds_f64x2(stage + 16u * (unsigned)(k * 32 + lane));
+        xs[2 * k] = a.x; xs[2 * k + 1] = a.y;
+    }
+    if (HAS_W) {
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+            double2 a = lds_f64x2(stage + kStageBytes / 2 + 16u * (unsigned)(k * 32 + lane));
+            ws[2 * k] = a.x; ws[2 * k + 1] = a.y;
         }
     }
 }
 
-template <bool HAS_W, bool VEC, int C>
-__global__ void __launch_bounds__(512, 1) k_bin_accumulate(const double* __restrict__ X,
+// VEC: 16-byte aligned input.  STAGE: tiles arrive through the per-warp TMA stage; otherwise
+// they are prefetched into L2 and loaded with LDG.128 (VEC) or plain loads (!VEC).
+template <bool HAS_W, bool VEC, bool STAGE, int GRID, bool FAST>
+__device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ring, unsigned stage,
+                                                  unsigned mbar, const double* __restrict__ X,
+                                                  const double* __restrict__ W, double wsc, long n,
+                                                  long gw, long tw, int lane, double& vmin,
+                                                  double& vmax) {
+    const long nfull = n / kTile;
+    const long ntiles = (n + kTile - 1) / kTile;
+    const long rounds = (ntiles + tw - 1) / tw;  // the same for every warp: the token needs all
+    double xs[2 * kU], ws[2 * kU];
+    unsigned addr[2 * kU];
+    double ww[2 * kU], ss[2 * kU];
+    unsigned parity = 0;
+    long t = gw;
+    if (STAGE) {
+        if (lane == 0 && t < nfull) stage_issue<HAS_W>(X, W, t * kTile, stage, mbar);
+    } else if (t < nfull) {
+        // !STAGE pipeline: the tile of round r + 1 is loaded into the (by then dead) registers
+        // at the end of round r, its latency hidden behind the wait for the token, and the tile
+        // of round r + 2 is pulled into L2 at the same time
+        load_tile<HAS_W, VEC>(X, W, t * kTile, lane, xs, ws);
+        if (VEC && t + tw < nfull) l2_prefetch<HAS_W>(X, W, (t + tw) * kTile, lane);
+    }
+    for (long r = 0; r < rounds; ++r, t += tw) {
+        const long tn = t + tw;
+        const bool have = t < ntiles;   // warp-uniform; m is per lane
+        unsigned m = 0;
+        if (t < nfull) {
+            m = 0xffu;
+            if (STAGE) {
+                mbar_wait(mbar, parity);
+                parity ^= 1u;
+                stage_read<HAS_W>(stage, lane, xs, ws);
+                __syncwarp();  // every lane has read the stage before it is refilled
+                if (lane == 0 && tn < nfull) stage_issue<HAS_W>(X, W, tn * kTile, stage, mbar);
+            }
+        } else if (have) {
+            m = load_partial<HAS_W>(X, W, t * kTile, n, lane, xs, ws);
+        }
+        if (have) {
+            bool e0 = classify_group<HAS_W, GRID, FAST>(L, xs, ws, wsc, m & 0xfu, addr, ww, ss);
+            bool e1 = classify_group<HAS_W, GRID, FAST>(L, xs + kU, ws + kU, wsc, m >> kU,
+                                                        addr + kU, ww + kU, ss + kU);
+            if (__any_sync(CRICK_FULL, e0 || e1)) {
+                minmax_group<HAS_W>(L, xs, ws, wsc, m & 0xfu, vmin, vmax);
+                minmax_group<HAS_W>(L, xs + kU, ws + kU, wsc, m >> kU, vmin, vmax);
+            }
+        }
+        if (!STAGE && tn < nfull) {
+            load_tile<HAS_W, VEC>(X, W, tn * kTile, lane, xs, ws);
+            if (VEC && tn + tw < nfull) l2_prefetch<HAS_W>(X, W, (tn + tw) * kTile, lane);
+        }
+        if (!(ring.first && r == 0)) bar_sync64(ring.id_in);
+        if (have) {
+            // two groups of 4 independent read-modify-writes; a bucket shared by the groups is
+            // ordered by the thread's own program order
+            if (ring.passes == 1) {
+                rmw<kU>(addr, ww, ss);
+                rmw<kU>(addr + kU, ww + kU, ss + kU);
+            } else {
+                for (int p_ = 0; p_ < ring.passes; ++p_) {
+                    if (ring.pass == p_) {
+                        rmw<kU>(addr, ww, ss);
+                        rmw<kU>(addr + kU, ww + kU, ss + kU);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        bar_arrive64(ring.id_out);
+    }
+    if (ring.first && rounds > 0) bar_sync64(ring.id_in);  // absorb the last hand-over
+}
+
+template <bool HAS_W, bool VEC, bool STAGE>
+__global__ void __launch_bounds__(448, 1) k_bin_accumulate(const double* __restrict__ X,
                                                            const double* __restrict__ W, double wsc,
                                                            long n, ParHeader* hdr,
                                                            const double* __restrict__ g_edges,
-                                                           const unsigned* __restrict__ g_tab,
+                                                           const unsigned short* __restrict__ g_tab,
                                                            double2* __restrict__ partial,
                                                            double2* __restrict__ minmax, int bmax,
-                                                           int accumulate_into) {
-    // shared: tab[kNC] | edges[bmax even] | acc[nwarps][bmax + 1][C]
-    unsigned* s_tab = reinterpret_cast<unsigned*>(smem_raw);
-    double* s_edges = reinterpret_cast<double*>(smem_raw + sizeof(unsigned) * kNC);
-    double2* s_acc = reinterpret_cast<double2*>(s_edges + ((bmax + 1) & ~1));
+                                                           int cols, int ntab, int accumulate_into) {
+    // shared: stage[nwarps][4 KB] (STAGE only) | acc[ntab][bmax + 1][cols] double2 |
+    //         edges[bmax + kEdgePad] | tab[kTabLen] uint16 | mbar[nwarps]
+    const int nwarps = blockDim.x >> 5;   // a multiple of ntab, <= 14 (one named barrier each)
+    unsigned char* s_stage = smem_raw;
+    double2* s_acc = reinterpret_cast<double2*>(smem_raw + (STAGE ? (size_t)nwarps * kStageBytes : 0));
+    const int rows = bmax + 1;  // last row = dummy
+    double* s_edges = reinterpret_cast<double*>(s_acc + (size_t)ntab * rows * cols);
+    unsigned short* s_tab = reinterpret_cast<unsigned short*>(s_edges + bmax + kEdgePad);
+    unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<unsigned char*>(s_tab) + kTabBytes);
     __shared__ double s_min[32], s_max[32];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
     const int E = hdr->E;
     const int B = E + 1;
-    const int rows = bmax + 1;  // last row = dummy
-    for (int i = threadIdx.x; i < kNC; i += blockDim.x) s_tab[i] = g_tab[i];
-    for (int i = threadIdx.x; i < E; i += blockDim.x) s_edges[i] = g_edges[i];
-    for (int i = threadIdx.x; i < nwarps * rows * C; i += blockDim.x) s_acc[i] = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < kTabLen / 2; i += blockDim.x)
+        reinterpret_cast<unsigned*>(s_tab)[i] = reinterpret_cast<const unsigned*>(g_tab)[i];
+    for (int i = threadIdx.x; i < bmax + kEdgePad; i += blockDim.x)
+        s_edges[i] = i < E ? g_edges[i] : INFINITY;
+    for (int i = threadIdx.x; i < ntab * rows * cols; i += blockDim.x)
+        s_acc[i] = make_double2(0.0, 0.0);
+    const unsigned stage = (unsigned)__cvta_generic_to_shared(s_stage) + (unsigned)warp * kStageBytes;
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_mbar) + 8u * (unsigned)warp;
+    if (STAGE) {
+        if (lane == 0) mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     Lookup L;
-    L.tab = s_tab; L.edges = s_edges; L.ubase = hdr->ubase; L.shift = hdr->shift; L.E = E;
-    L.x0 = hdr->x0; L.inv = hdr->inv;
-    double2* acc_col = s_acc + (size_t)warp * rows * C + (lane % C);
+    L.tab = (unsigned)__cvta_generic_to_shared(s_tab);
+    L.edges = (unsigned)__cvta_generic_to_shared(s_edges);
+    // table and ring of this warp: warps w, w + ntab, w + 2 ntab, ... share table w % ntab
+    const int tab_id = warp % ntab, pos = warp / ntab, rsize = nwarps / ntab;
+    L.acc = (unsigned)__cvta_generic_to_shared(s_acc + (size_t)tab_id * rows * cols) +
+            16u * (unsigned)(lane & (cols - 1));
+    L.row_shift = 4 + __ffs(cols) - 1;
+    L.dummy = bmax;
+    L.kbase = hdr->kbase; L.shift = hdr->shift; L.x0 = hdr->x0; L.inv = hdr->inv;
+    L.E = E; L.kmax = hdr->kmax;
+    // buckets that may hold the extremes: b <= 1 or b >= E - 1; fewer than 4 edges: all
+    L.ext_lo = E >= 4 ? 2u : 0u;
+    L.ext_span = E >= 4 ? (unsigned)(E - 3) : 0u;
+    Ring ring;
+    ring.id_in = 1 + tab_id * rsize + pos;
+    ring.id_out = 1 + tab_id * rsize + (pos + 1 == rsize ? 0 : pos + 1);
+    ring.first = pos == 0;
+    ring.passes = 32 / cols;
+    ring.pass = lane / cols;
     double vmin = INFINITY, vmax = -INFINITY;
     const long gw = (long)blockIdx.x * nwarps + warp;
     const long tw = (long)gridDim.x * nwarps;
-    if (hdr->grid == 1)
-        accumulate_stream<HAS_W, VEC, C, 1>(L, acc_col, bmax, X, W, wsc, n, gw, tw, lane, vmin, vmax);
-    else
-        accumulate_stream<HAS_W, VEC, C, 0>(L, acc_col, bmax, X, W, wsc, n, gw, tw, lane, vmin, vmax);
-    // CTA reduction in fixed (warp, column) order -> deterministic partials
+    const bool fast = L.kmax <= kKFast;
+    if (hdr->grid == 1) {
+        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 1, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+        else accumulate_stream<HAS_W, VEC, STAGE, 1, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+    } else {
+        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 0, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+        else accumulate_stream<HAS_W, VEC, STAGE, 0, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+    }
+    // CTA reduction in fixed column order -> deterministic partials
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         vmin = fmin(vmin, shfl_xor_d(vmin, d));
@@ -633,16 +883,25 @@ __global__ void __launch_bounds__(512, 1) k_bin_accumulate(const double* __restr
     }
     if (lane == 0) { s_min[warp] = vmin; s_max[warp] = vmax; }
     __syncthreads();
+    // one warp per bucket: lanes read the columns (conflict-free), xor-shuffle tree
     double2* row = partial + (size_t)blockIdx.x * kBPad;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    for (int b = warp; b < B; b += nwarps) {
         double sw_ = 0.0, sx_ = 0.0;
-        for (int wv = 0; wv < nwarps; ++wv) {
-            const double2* r = s_acc + ((size_t)wv * rows + b) * C;
-#pragma unroll
-            for (int c = 0; c < C; ++c) { sw_ += r[c].x; sx_ += r[c].y; }
+        if (lane < cols) {
+            for (int tb = 0; tb < ntab; ++tb) {
+                double2 a = s_acc[((size_t)tb * rows + b) * cols + lane];
+                sw_ += a.x; sx_ += a.y;
+            }
         }
-        if (accumulate_into) { double2 o = row[b]; sw_ += o.x; sx_ += o.y; }
-        row[b] = make_double2(sw_, sx_);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            sw_ += shfl_xor_d(sw_, d);
+            sx_ += shfl_xor_d(sx_, d);
+        }
+        if (lane == 0) {
+            if (accumulate_into) { double2 o = row[b]; sw_ += o.x; sx_ += o.y; }
+            row[b] = make_double2(sw_, sx_);
+        }
     }
     if (threadIdx.x == 0) {
         double mn = INFINITY, mx = -INFINITY;
@@ -841,28 +1100,33 @@ cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratc
     return edges_from_sorted_sample(v, L, S, st);
 }
 
-// Shape of the hot kernel for a bucket capacity: C columns per warp table, nw warps.
-struct AccCfg { int C, nw; size_t smem; };
+// Shape of the hot kernel for a bucket capacity.  Preferred: two tables of 32 columns, each
+// with its own token ring of 7 warps, tiles prefetched into L2 (c <= 100).  When two tables do
+// not fit: one table (32 columns, or 16 / 8 / 4 for large compressions), one ring of 12
+// warps, tiles staged through shared memory by TMA.
+struct AccCfg { int cols, ntab, nw, stage; size_t smem; };
 static AccCfg acc_cfg(int bmax) {
-    const size_t fixed = sizeof(unsigned) * kNC + sizeof(double) * (size_t)((bmax + 1) & ~1);
     const size_t budget = 230000;                       // of 232448 B opt-in, 512 B are static
-    const size_t col = (size_t)(bmax + 1) * 16;         // one column incl. the dummy row
-    int cols = (int)((budget - fixed) / col);
+    const size_t fixed = kTabBytes + sizeof(double) * (size_t)(bmax + kEdgePad) + 16 * 8;
+    const size_t table32 = (size_t)(bmax + 1) * 32 * 16;
     AccCfg c;
-    c.C = 8;
-    while (c.C > 1 && cols / c.C < 8) c.C >>= 1;        // prefer >= 8 warps
-    c.nw = cols / c.C;
-    if (c.nw > 16) c.nw = 16;
-    if (c.nw < 1) c.nw = 1;
-    if (const char* e = getenv("CRICK_ACC_C")) {        // tuning hook (bench sweeps)
-        int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) { c.C = v; c.nw = cols / v > 16 ? 16 : cols / v; }
+    int want_tab = 0;
+    if (const char* e = getenv("CRICK_ACC_T")) want_tab = atoi(e);   // tuning hooks (bench sweeps)
+    if (want_tab != 1 && fixed + 2 * table32 <= budget) {
+        c.ntab = 2; c.cols = 32; c.nw = 14; c.stage = 0;
+    } else {
+        c.ntab = 1; c.nw = 12; c.stage = 1; c.cols = 32;
+        while (c.cols > 1 &&
+               fixed + (size_t)c.nw * kStageBytes + (size_t)(bmax + 1) * c.cols * 16 > budget)
+            c.cols >>= 1;
     }
     if (const char* e = getenv("CRICK_ACC_W")) {
         int v = atoi(e);
-        if (v >= 1 && v <= 16 && v * c.C <= cols) c.nw = v;
+        if (v >= c.ntab && v <= 14) c.nw = v - v % c.ntab;
     }
-    c.smem = (fixed + (size_t)c.nw * c.C * col + 15) & ~(size_t)15;
+    c.smem = fixed + (c.stage ? (size_t)c.nw * kStageBytes : 0) +
+             (size_t)c.ntab * (bmax + 1) * c.cols * 16;
+    c.smem = (c.smem + 15) & ~(size_t)15;
     return c;
 }
 
@@ -910,25 +1174,26 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
         if (g_prof_on && cudaEventCreate(&pe0) == cudaSuccess && cudaEventCreate(&pe1) == cudaSuccess)
             cudaEventRecord(pe0, st);
     }
-#define CRICK_LAUNCH_ACC(HW, VC, CC)                                                              \
+#define CRICK_LAUNCH_ACC(HW, VC, SG)                                                              \
     do {                                                                                          \
-        e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC, CC>,                                    \
+        e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC, SG>,                                    \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                           \
         count_launch();                                                                           \
-        k_bin_accumulate<HW, VC, CC><<<grid, block, smem, st>>>(                                  \
-            X, W, wsc, n, L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, accumulate_into);     \
+        k_bin_accumulate<HW, VC, SG><<<grid, block, smem, st>>>(                                  \
+            X, W, wsc, n, L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, cfg.cols, cfg.ntab,   \
+            accumulate_into);                                                                     \
     } while (0)
-#define CRICK_LAUNCH_ACC_C(HW, VC)                                                                \
-    switch (cfg.C) {                                                                              \
-        case 8: CRICK_LAUNCH_ACC(HW, VC, 8); break;                                               \
-        case 4: CRICK_LAUNCH_ACC(HW, VC, 4); break;                                               \
-        case 2: CRICK_LAUNCH_ACC(HW, VC, 2); break;                                               \
-        default: CRICK_LAUNCH_ACC(HW, VC, 1); break;                                              \
+    const bool stage = vec && cfg.stage;   // unaligned input: plain loads, no staging
+    if (W) {
+        if (!vec) CRICK_LAUNCH_ACC(true, false, false);
+        else if (stage) CRICK_LAUNCH_ACC(true, true, true);
+        else CRICK_LAUNCH_ACC(true, true, false);
+    } else {
+        if (!vec) CRICK_LAUNCH_ACC(false, false, false);
+        else if (stage) CRICK_LAUNCH_ACC(false, true, true);
+        else CRICK_LAUNCH_ACC(false, true, false);
     }
-    if (W) { if (vec) { CRICK_LAUNCH_ACC_C(true, true) } else { CRICK_LAUNCH_ACC_C(true, false) } }
-    else { if (vec) { CRICK_LAUNCH_ACC_C(false, true) } else { CRICK_LAUNCH_ACC_C(false, false) } }
-#undef CRICK_LAUNCH_ACC_C
 #undef CRICK_LAUNCH_ACC
     if (pe0 && pe1) {
         cudaEventRecord(pe1, st);
