@@ -200,11 +200,13 @@ def main():
 
     digest = cb.TDigest(COMPRESSION, mode="parallel")
     merged = None
+    # clocks are sampled every 100 ms from before the warm-up (the same load) to the end of
+    # the timed region, which by itself may be shorter than one sample period
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         merged = step(digest)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = cb.launch_count()
     lib.crick_profile_enable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

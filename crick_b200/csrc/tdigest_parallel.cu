@@ -46,7 +46,7 @@ constexpr int kTabLen = kNC + 2;
 constexpr size_t kTabBytes = ((size_t)kTabLen * 2 + 15) & ~(size_t)15;
 constexpr int kEMax = 1024;      // max edges (buckets - 1)
 constexpr int kBPad = kEMax + 8; // row stride of the per-CTA partial sums
-constexpr long kSMax = 65536;    // max sample size
+constexpr long kSMax = 16384;    // max sample size (rank error with 16 Ki = with 64 Ki)
 constexpr int kSortChunk = 4096; // elements sorted per CTA in shared memory
 
 struct ParHeader {
@@ -278,29 +278,46 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
                                                      unsigned short* __restrict__ tab,
                                                      unsigned short* __restrict__ tab2, double comp,
                                                      int ov) {
-    __shared__ double s_part[1024];
-    __shared__ double s_raw[kEMax];
-    __shared__ int s_cnt[kEMax];
-    __shared__ int s_scan[1024];
+    // phases b-c use s_raw / s_cnt / s_scan, phase d reuses the same bytes as s_cnt2
+    __shared__ __align__(16) unsigned char s_buf[(kTabLen + 6) * 4];
+    static_assert(sizeof(s_buf) >= kEMax * 8 + kEMax * 4 + 1024 * 4, "phase b-c arrays must fit");
+    double* s_raw = reinterpret_cast<double*>(s_buf);
+    int* s_cnt = reinterpret_cast<int*>(s_buf + kEMax * 8);
+    int* s_scan = s_cnt + kEMax;
     __shared__ int s_E;
     const int tid = threadIdx.x;
     const long S = hdr->S;
-    const long per = S / 1024 > 0 ? S / 1024 : 1;
-    // a. inclusive scan of sample weights (fixed order => deterministic)
+    // a. inclusive scan of sample weights (fixed order => deterministic): 4 consecutive
+    // elements per thread and chunk, warp shuffles + one pass over the 32 warp totals
     {
-        long lo = (long)tid * per, hi = lo + per;
-        if (hi > S) hi = S;
-        double s = 0.0;
-        for (long i = lo; i < hi; ++i) s += sw[i];
-        s_part[tid] = (lo < S) ? s : 0.0;
+        __shared__ double s_wtot[32];
+        __shared__ double s_run;
+        if (tid == 0) s_run = 0.0;
         __syncthreads();
-        if (tid == 0) {
-            double run = 0.0;
-            for (int t = 0; t < 1024; ++t) { double v = s_part[t]; s_part[t] = run; run += v; }
+        const int lane = tid & 31, wid = tid >> 5;
+        for (long base = 0; base < S; base += 4096) {
+            const long i0 = base + 4L * tid;
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (i0 + k < S) ? sw[i0 + k] : 0.0;
+            v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+            double inc = v[3];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double o = shfl_up_d(inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) s_wtot[wid] = inc;
+            __syncthreads();
+            double off = s_run;
+            for (int k = 0; k < wid; ++k) off += s_wtot[k];
+            off += inc - v[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i0 + k < S) cw[i0 + k] = off + v[k];
+            __syncthreads();
+            if (tid == 1023) s_run = off + v[3];
+            __syncthreads();
         }
-        __syncthreads();
-        double run = s_part[tid];
-        for (long i = lo; i < hi; ++i) { run += sw[i]; cw[i] = run; }
     }
     __syncthreads();
     const double Wt = cw[S - 1];
@@ -379,34 +396,55 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     }
     if (tid < 2) { s_cost[tid] = 0ull; s_kmax[tid] = 0; }
     __syncthreads();
+    // per grid: count the edges of every cell (edges are sorted and cell() is monotone), then
+    // an inclusive scan over the cells: tab[c] = sum of counts of cells < c
+    int* s_cnt2 = reinterpret_cast<int*>(s_buf);
+    __shared__ int s_wsum[32];
+    constexpr int kPer = (kTabLen + 1023) / 1024;   // cells per thread
     for (int g = 0; g < 2; ++g) {
         unsigned short* out = g == 0 ? tab : tab2;
         if (g == 1 && !lin_ok) break;
+        for (int c = tid; c < kTabLen + 6; c += blockDim.x) s_cnt2[c] = 0;
+        __syncthreads();
+        for (int j = tid; j < E; j += blockDim.x) {
+            int ce_ = g == 0 ? cell_key(edges[j], kbase, shift) : cell_lin(edges[j], x0, inv);
+            atomicAdd(&s_cnt2[ce_ + 1], 1);          // counted at index cell + 1
+        }
+        __syncthreads();
         unsigned long long local = 0;
-        int lmax = 0;
-        for (int cell = tid; cell < kTabLen; cell += blockDim.x) {
-            // lo = #edges with cell(e) < cell ; hi = #edges with cell(e) <= cell
-            int a = 0, b = E;
-            while (a < b) {
-                int mid = (a + b) >> 1;
-                int ce_ = g == 0 ? cell_key(edges[mid], kbase, shift) : cell_lin(edges[mid], x0, inv);
-                if (ce_ < cell) a = mid + 1; else b = mid;
-            }
-            int lo = a;
-            b = E;
-            while (a < b) {
-                int mid = (a + b) >> 1;
-                int ce_ = g == 0 ? cell_key(edges[mid], kbase, shift) : cell_lin(edges[mid], x0, inv);
-                if (ce_ <= cell) a = mid + 1; else b = mid;
-            }
-            out[cell] = (unsigned short)lo;
-            int m = a - lo, lg = 0;
+        int lmax = 0, run = 0;
+        int vals[kPer];
+        const int c0 = tid * kPer;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            int c = c0 + k;
+            int m = c < kTabLen ? s_cnt2[c] : 0;    // = edges in cell c - 1
+            int lg = 0;
             while ((1 << lg) < m + 1) ++lg;
             local += (unsigned long long)m * (unsigned long long)lg;
             lmax = m > lmax ? m : lmax;
+            run += m;
+            vals[k] = run;
+        }
+        int inc = run;
+        const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(CRICK_FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        int off = inc - run;
+        for (int k = 0; k < wid; ++k) off += s_wsum[k];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            int c = c0 + k;
+            if (c < kTabLen) out[c] = (unsigned short)(off + vals[k]);
         }
         atomicAdd(&s_cost[g], local);
         atomicMax(&s_kmax[g], lmax);
+        __syncthreads();
     }
     __syncthreads();
     int grid = 0;
@@ -1064,7 +1102,7 @@ long parallel_sample_pos(long i, long n, long S) {
 long parallel_sample_len(long n);
 static long sample_len(long n) { return parallel_sample_len(n); }
 long parallel_sample_len(long n) {
-    long S = (n >= (1L << 22)) ? kSMax : 16384;
+    long S = kSMax;
     while (S > kSortChunk && S * 4 > n) S >>= 1;
     return S;
 }

@@ -112,7 +112,9 @@ class TDigest:
             raise TypeError("%s must be numeric" % name)
         if not np.isfinite(x).all():  # :137,158
             raise ValueError("%s must be finite" % name)
-        xin = np.ascontiguousarray(x, dtype=np.float64)
+        xin = np.asarray(x, dtype=np.float64)
+        if not xin.flags.c_contiguous:  # (ascontiguousarray would turn a 0-d input into 1-d)
+            xin = np.ascontiguousarray(xin)
         out = np.empty(xin.shape, dtype=np.float64)
         check(fn(self._h, xin.ctypes.data, out.ctypes.data, xin.size, 0, None), name)
         if out.ndim == 0:  # :140-142
