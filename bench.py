@@ -239,9 +239,11 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms_per_launch": k_ms, "kernel_share_of_step": (kms.value / ms) if ms else None,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VALUE * n}
-    try:
+    try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to n
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get("k_bin_accumulate_bytes_per_value_x_n", None)
+            tj = json.load(f)
+        roofline["traffic"] = tj["k_bin_accumulate_dram_bytes_per_value"] * n
+        roofline["traffic_source"] = tj["source"]
     except Exception:
         pass
 

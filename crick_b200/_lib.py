@@ -43,6 +43,7 @@ _SIG = {
     "crick_tdigest_free": (None, [_P]),
     "crick_tdigest_add": (c_int, [_P, c_double, c_double]),
     "crick_tdigest_update": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P]),
+    "crick_tdigest_update_checked": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P, _P]),
     "crick_tdigest_flush": (c_int, [_P]),
     "crick_tdigest_merge": (c_int, [_P, _P, c_int]),
     "crick_tdigest_scale": (c_int, [_P, c_double]),

@@ -238,7 +238,7 @@ int crick_tdigest_add(crick_tdigest_t* t, double x, double w) {
 // host-resident input, parallel mode: same sample positions as the device sampler, then
 // double-buffered chunks (copy of chunk k+1 overlaps the accumulate of chunk k)
 static int td_update_host_parallel(crick_tdigest* t, const double* x, const double* w, double wsc,
-                                   int64_t n, cudaStream_t st) {
+                                   int64_t n, cudaStream_t st, int* bad_weights) {
     if (td_scratch(t)) return -1;
     cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
     if (e != cudaSuccess) return fail("flush", e);
@@ -290,7 +290,10 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
                                         t->scratch, sm_count(), st, k == 0);
             if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
         }
-        if (e == cudaSuccess) e = parallel_finalize(t->s.v, 0, t->scratch, sm_count(), st);
+        if (e == cudaSuccess && bad_weights && w)
+            e = parallel_bad_weights(t->scratch, st, bad_weights);
+        if (e == cudaSuccess && !(bad_weights && *bad_weights))
+            e = parallel_finalize(t->s.v, 0, t->scratch, sm_count(), st);
     }
     if (e != cudaSuccess) rc = fail("host-chunked parallel update", e);
     // buffers are freed only after the work that reads them has finished
@@ -304,8 +307,26 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     return rc;
 }
 
+static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
+                     int64_t n, int x_on_device, int w_on_device, int mode, void* stream,
+                     int* bad_weights);
+
 int crick_tdigest_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                          int64_t n, int x_on_device, int w_on_device, int mode, void* stream) {
+    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, mode, stream, nullptr);
+}
+
+int crick_tdigest_update_checked(crick_tdigest_t* t, const double* x, const double* w,
+                                 double w_scalar, int64_t n, int x_on_device, int w_on_device,
+                                 int mode, void* stream, int* bad_weights) {
+    if (!bad_weights) return fail_msg("update_checked: bad_weights must not be NULL");
+    *bad_weights = 0;
+    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, mode, stream, bad_weights);
+}
+
+static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
+                     int64_t n, int x_on_device, int w_on_device, int mode, void* stream,
+                     int* bad_weights) {
     if (n <= 0) return 0;  // tdigest_stubs.c:648-650
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
@@ -318,7 +339,7 @@ int crick_tdigest_update(crick_tdigest_t* t, const double* x, const double* w, d
     if (w_arr && (x_on_device != w_on_device))
         return fail_msg("x and w must both be host or both be device arrays");
     if (!x_on_device) {
-        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st);
+        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st, bad_weights);
         // reference mode from host memory: stage the whole (small) input
         double* d = nullptr;
         size_t bytes = (size_t)n * sizeof(double) * (w_arr ? 2 : 1);
@@ -341,7 +362,8 @@ int crick_tdigest_update(crick_tdigest_t* t, const double* x, const double* w, d
         if (td_scratch(t)) return -1;
         e = launch_flush(t->s.v, 0, 1, 1, st);
         if (e == cudaSuccess)
-            e = launch_parallel_update(t->s.v, 0, x, w, w_scalar, n, t->scratch, sm_count(), st);
+            e = launch_parallel_update(t->s.v, 0, x, w, w_scalar, n, t->scratch, sm_count(), st,
+                                       bad_weights);
     } else {
         e = launch_ingest(t->s.v, 1, x, w, w_scalar, 1, 1, nullptr, n, 0, nullptr, 0, st);
     }

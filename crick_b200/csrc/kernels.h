@@ -31,9 +31,12 @@ size_t parallel_scratch_bytes(double compression, int sm_count);
 // X/W device pointers (W may be null -> scalar wsc). Accumulates the whole array
 // into digest `d` of `v` (which must have an empty buffer): sample -> edges ->
 // accumulate -> finalize, all on `st`, no host synchronisation.
+// bad_weights != nullptr: validate w on the device (finite and > 0, tdigest.pyx:304-305);
+// synchronises, and leaves the digest untouched when *bad_weights comes back non-zero.
 cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
                                    double wsc, long n, void* scratch, int sm_count,
-                                   cudaStream_t st);
+                                   cudaStream_t st, int* bad_weights);
+cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad);
 // The same pipeline in pieces, for host-resident input streamed in chunks: edges
 // from a caller-provided sample (copied to parallel_sample_x/w), any number of
 // accumulate calls (first = 1 on the first), then one finalize.

@@ -58,7 +58,7 @@ struct ParHeader {
     int ncta;    // CTAs that wrote partials
     int grid;    // lookup grid: 0 = linear in the ordered bit pattern, 1 = linear in x
     int kmax;    // most edges in any one cell of that grid
-    int pad;
+    int badw;    // set by k_bin_accumulate: some weight is not finite or not > 0 (tdigest.pyx:304)
     double sample_total;
     double x0;   // grid 1: cell = (int)((x - x0) * inv) + 1
     double inv;
@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         hdr->sample_total = Wt;
         hdr->ncta = 0;
         hdr->grid = grid;
+        hdr->badw = 0;
         hdr->kmax = s_kmax[grid];
         hdr->x0 = x0;
         hdr->inv = inv;
@@ -546,7 +547,7 @@ struct Lookup {
 template <bool HAS_W, int GRID, bool FAST>
 __device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs, const double* ws,
                                                double wsc, unsigned valid_mask, unsigned* addr,
-                                               double* ww, double* ss) {
+                                               double* ww, double* ss, bool& badw) {
     int b[kU];
     unsigned ea[kU];
 #pragma unroll
@@ -590,7 +591,10 @@ __device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs
         const double w = HAS_W ? ws[u] : wsc;
         // tdigest_add's filter (:285): finite x, and not (w <= eps)
         const bool finite = fabs(xs[u]) <= DBL_MAX;
-        const bool ok = finite && !(w <= DBL_EPSILON) && ((valid_mask >> u) & 1u);
+        const bool valid = (valid_mask >> u) & 1u;
+        const bool ok = finite && !(w <= DBL_EPSILON) && valid;
+        // the wrapper's check of w (tdigest.pyx:304-305), done here instead of on the host
+        if (HAS_W) badw |= valid && !(w > 0.0 && w <= DBL_MAX);
         ext |= ok && ((unsigned)b[u] - L.ext_lo >= L.ext_span);
         // rejected values go to the dummy row (never read back), whatever their w / w*x --
         // but w*x must stay finite: fold_if_equal multiplies it by 0 (a NaN or infinite x
@@ -776,7 +780,7 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
                                                   unsigned mbar, const double* __restrict__ X,
                                                   const double* __restrict__ W, double wsc, long n,
                                                   long gw, long tw, int lane, double& vmin,
-                                                  double& vmax) {
+                                                  double& vmax, int* badw_flag) {
     const long nfull = n / kTile;
     const long ntiles = (n + kTile - 1) / kTile;
     const long rounds = (ntiles + tw - 1) / tw;  // the same for every warp: the token needs all
@@ -784,6 +788,7 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
     unsigned addr[2 * kU];
     double ww[2 * kU], ss[2 * kU];
     unsigned parity = 0;
+    bool badw = false;
     long t = gw;
     if (STAGE) {
         if (lane == 0 && t < nfull) stage_issue<HAS_W>(X, W, t * kTile, stage, mbar);
@@ -811,9 +816,10 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
             m = load_partial<HAS_W>(X, W, t * kTile, n, lane, xs, ws);
         }
         if (have) {
-            bool e0 = classify_group<HAS_W, GRID, FAST>(L, xs, ws, wsc, m & 0xfu, addr, ww, ss);
+            bool e0 = classify_group<HAS_W, GRID, FAST>(L, xs, ws, wsc, m & 0xfu, addr, ww, ss,
+                                                        badw);
             bool e1 = classify_group<HAS_W, GRID, FAST>(L, xs + kU, ws + kU, wsc, m >> kU,
-                                                        addr + kU, ww + kU, ss + kU);
+                                                        addr + kU, ww + kU, ss + kU, badw);
             if (__any_sync(CRICK_FULL, e0 || e1)) {
                 minmax_group<HAS_W>(L, xs, ws, wsc, m & 0xfu, vmin, vmax);
                 minmax_group<HAS_W>(L, xs + kU, ws + kU, wsc, m >> kU, vmin, vmax);
@@ -843,6 +849,7 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
         bar_arrive64(ring.id_out);
     }
     if (ring.first && rounds > 0) bar_sync64(ring.id_in);  // absorb the last hand-over
+    if (HAS_W && __any_sync(CRICK_FULL, badw) && lane == 0) atomicOr(badw_flag, 1);
 }
 
 template <bool HAS_W, bool VEC, bool STAGE>
@@ -907,11 +914,11 @@ __global__ void __launch_bounds__(448, 1) k_bin_accumulate(const double* __restr
     const long tw = (long)gridDim.x * nwarps;
     const bool fast = L.kmax <= kKFast;
     if (hdr->grid == 1) {
-        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 1, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
-        else accumulate_stream<HAS_W, VEC, STAGE, 1, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 1, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
+        else accumulate_stream<HAS_W, VEC, STAGE, 1, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
     } else {
-        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 0, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
-        else accumulate_stream<HAS_W, VEC, STAGE, 0, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax);
+        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 0, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
+        else accumulate_stream<HAS_W, VEC, STAGE, 0, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
     }
     // CTA reduction in fixed column order -> deterministic partials
 #pragma unroll
@@ -1262,9 +1269,20 @@ cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_
     return cudaGetLastError();
 }
 
+// reads the "some weight is not > 0 and finite" flag of the accumulate calls since the last
+// edges kernel (synchronises `st`)
+cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad) {
+    ParLayout L = carve(scratch, 100.0, 1);
+    ParHeader h;
+    cudaError_t e = cudaMemcpyAsync(&h, L.hdr, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    *bad = (e == cudaSuccess) ? h.badw : 0;
+    return e;
+}
+
 cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
                                    double wsc, long n, void* scratch, int sm_count,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, int* bad_weights) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     long S = sample_len(n);
     count_launch();
@@ -1275,6 +1293,11 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
     if (e != cudaSuccess) return e;
     e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0);
     if (e != cudaSuccess) return e;
+    if (bad_weights && W) {
+        // validated update: the digest is only touched when every weight passed
+        e = parallel_bad_weights(scratch, st, bad_weights);
+        if (e != cudaSuccess || *bad_weights) return e;
+    }
     return parallel_finalize(v, d, scratch, sm_count, st);
 }
 

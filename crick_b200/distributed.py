@@ -12,6 +12,47 @@ from .stats import SummaryStats
 from .tdigest import TDigest
 
 
+def shard_bounds(n, rank, world):
+    """Contiguous equal element ranges, rank r owns [r*n/G, (r+1)*n/G)."""
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+def record_from_state(centroids, total_weight, vmin, vmax, size):
+    """Host mirror of k_pack_record: [n, total, min, max, mean0, w0, ...] padded to 4 + 2*size."""
+    c = np.ascontiguousarray(centroids).view(np.float64).reshape(-1, 2)
+    if len(c) > size:
+        raise ValueError("more centroids than the digest has slots")
+    rec = np.zeros(4 + 2 * size, dtype=np.float64)
+    rec[0], rec[1], rec[2], rec[3] = len(c), total_weight, vmin, vmax
+    rec[4:4 + 2 * len(c)] = c.ravel()
+    return rec
+
+
+def state_from_record(rec):
+    """Inverse of record_from_state: (centroids (n, 2), total_weight, min, max)."""
+    rec = np.asarray(rec, dtype=np.float64)
+    n = int(rec[0])
+    return rec[4:4 + 2 * n].reshape(n, 2).copy(), float(rec[1]), float(rec[2]), float(rec[3])
+
+
+def gather_records(rec, group=None):
+    """All-gather one fixed-size record per rank into a (world, len) tensor in RANK ORDER.
+    Works on CUDA tensors (NCCL) and CPU tensors (gloo, used by the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    out = torch.empty((world, rec.numel()), dtype=rec.dtype, device=rec.device)
+    if rec.is_cuda:
+        dist.all_gather_into_tensor(out.view(-1), rec.contiguous().view(-1), group=group)
+    else:
+        parts = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(parts, rec.contiguous(), group=group)
+        for r, p in enumerate(parts):
+            out[r] = p
+    return out
+
+
 def allgather_merge_tdigest(digest, group=None):
     """Return a new TDigest equal to ``TDigest(c).merge(*[digest of rank 0, 1, ...])``."""
     import torch
@@ -26,8 +67,7 @@ def allgather_merge_tdigest(digest, group=None):
         # the legacy default stream cannot be named through the C ABI (NULL = handle's own)
         from ._lib import lib
         lib.crick_device_synchronize()
-    gathered = torch.empty(world * nd, dtype=torch.float64, device="cuda")
-    dist.all_gather_into_tensor(gathered, rec, group=group)
+    gathered = gather_records(rec, group)
     out = TDigest(digest.compression)
     out.merge_records(gathered.data_ptr(), world, stream=stream.cuda_stream or None)
     if stream.cuda_stream == 0:

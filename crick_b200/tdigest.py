@@ -5,6 +5,7 @@ types (file:line cited per method); the numeric work happens in libcrick_cuda.so
 Additions: ``mode=`` (constructor / ``update``), CUDA-array inputs, and the grouped entry
 point :class:`TDigestGroup` / :func:`grouped_update` for many independent digests.
 """
+import ctypes
 import math
 import numbers
 
@@ -263,7 +264,7 @@ class TDigest:
             raise ValueError("w must be > 0 and finite")
         check(lib.crick_tdigest_add(self._h, x, w), "add")
 
-    def update(self, x, w=1, mode=None, stream=None):
+    def update(self, x, w=1, mode=None, stream=None, check_w=True):
         """update(self, x, w=1)
 
         Add many samples to this digest.
@@ -277,11 +278,15 @@ class TDigest:
             The weight (or weights) of the values to add. Default is 1.
         mode : optional override of the digest's update mode for this call.
         stream : optional ``cudaStream_t`` (int) to enqueue the work on.
+        check_w : CUDA-array weights only.  True (default): raise ValueError like the
+            reference when a weight is not finite or not > 0 -- checked on the device, which
+            synchronises the stream.  False: fully asynchronous, ``w <= eps`` is dropped by
+            the kernel exactly like ``tdigest_add`` does.
         """  # tdigest.pyx:282-308
         m = self._mode if mode is None else _lib.mode_code(mode)
         xd = device_view(x)
         if xd is not None:
-            return self._update_device(xd, w, m, stream)
+            return self._update_device(xd, w, m, stream, check_w)
         x = np.asarray(x)
         check_w = not (np.isscalar(w) and w == 1)
         wd = device_view(w)
@@ -292,23 +297,41 @@ class TDigest:
             raise TypeError("x must be numeric")
         if not np.can_cast(w.dtype, "f8", casting="safe"):
             raise TypeError("w must be numeric")
-        if check_w and (not np.isfinite(w).all() or (w <= 0).any()):
+        # Large weight arrays headed for the parallel path are validated on the device in the
+        # same pass over the data (crick_tdigest_update_checked); the host check alone costs
+        # more than the whole update there.
+        try:
+            n_b = int(np.prod(np.broadcast_shapes(x.shape, w.shape)))
+        except ValueError:  # not broadcastable: korder_pair raises the reference's error below
+            n_b = 0
+        eff = m
+        if m == _lib.MODE_PARALLEL and n_b < _lib.PARALLEL_MIN:
+            eff = _lib.MODE_REFERENCE  # too small to sample: same answer, exact algorithm
+        goes_parallel = eff == _lib.MODE_PARALLEL or (eff == _lib.MODE_AUTO
+                                                      and n_b >= 4 * _lib.PARALLEL_MIN)
+        device_check = check_w and w.ndim > 0 and goes_parallel
+        if check_w and not device_check and (not np.isfinite(w).all() or (w <= 0).any()):
             raise ValueError("w must be > 0 and finite")
         if x.size == 0 or w.size == 0:  # tdigest_stubs.c:648-650
             return
         xf, wf = korder_pair(x, w)
         n = xf.size
-        eff = m
-        if m == _lib.MODE_PARALLEL and n < _lib.PARALLEL_MIN:
-            eff = _lib.MODE_REFERENCE  # too small to sample: same answer, exact algorithm
         if isinstance(wf, np.ndarray):
+            if device_check:
+                bad = ctypes.c_int(0)
+                check(lib.crick_tdigest_update_checked(self._h, xf.ctypes.data, wf.ctypes.data, 0.0,
+                                                       n, 0, 0, eff, stream, ctypes.addressof(bad)),
+                      "update")
+                if bad.value:
+                    raise ValueError("w must be > 0 and finite")
+                return
             check(lib.crick_tdigest_update(self._h, xf.ctypes.data, wf.ctypes.data, 0.0, n, 0, 0,
                                            eff, stream), "update")
         else:
             check(lib.crick_tdigest_update(self._h, xf.ctypes.data, None, float(wf), n, 0, 0,
                                            eff, stream), "update")
 
-    def _update_device(self, xd, w, m, stream):
+    def _update_device(self, xd, w, m, stream, check_w=True):
         if xd.dtype != np.float64:
             raise TypeError("x must be float64 when given as a CUDA array")
         n = xd.size
@@ -323,7 +346,16 @@ class TDigest:
                 raise TypeError("w must be float64 when given as a CUDA array")
             if wd.size != n:
                 raise ValueError("x and w CUDA arrays must have the same number of elements")
-            # device-resident weights are not validated on the host (documented divergence:
+            parallel = eff == _lib.MODE_PARALLEL or (eff == _lib.MODE_AUTO
+                                                     and n >= 4 * _lib.PARALLEL_MIN)
+            if check_w and parallel:
+                bad = ctypes.c_int(0)
+                check(lib.crick_tdigest_update_checked(self._h, xd.ptr, wd.ptr, 0.0, n, 1, 1, eff,
+                                                       stream, ctypes.addressof(bad)), "update")
+                if bad.value:
+                    raise ValueError("w must be > 0 and finite")
+                return
+            # reference-mode sizes: device weights are not validated (documented divergence:
             # w <= eps is dropped by the kernel exactly like tdigest_add does)
             check(lib.crick_tdigest_update(self._h, xd.ptr, wd.ptr, 0.0, n, 1, 1, eff, stream),
                   "update")

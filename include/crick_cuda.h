@@ -81,6 +81,14 @@ int crick_tdigest_add(crick_tdigest_t *t, double x, double w);
  * wrapper has already flattened in K-order.  w == NULL => scalar weight w_scalar. */
 int crick_tdigest_update(crick_tdigest_t *t, const double *x, const double *w, double w_scalar,
                          int64_t n, int x_on_device, int w_on_device, int mode, void *stream);
+/* The same with the wrapper's weight check (tdigest.pyx:304-305, "w must be > 0 and finite")
+ * done on the device in the same pass instead of on the host.  Parallel mode only validates
+ * (other modes leave *bad_weights = 0: validate on the host).  When some weight fails,
+ * *bad_weights is set non-zero and the digest is left as it was (its buffer flushed).
+ * Synchronises the stream. */
+int crick_tdigest_update_checked(crick_tdigest_t *t, const double *x, const double *w,
+                                 double w_scalar, int64_t n, int x_on_device, int w_on_device,
+                                 int mode, void *stream, int *bad_weights);
 /* tdigest_flush, tdigest_stubs.c:219-273 */
 int crick_tdigest_flush(crick_tdigest_t *t);
 /* tdigest_merge, tdigest_stubs.c:592-606, for each of `others` in order (flushes them) */

@@ -205,3 +205,33 @@ def test_full_size_properties_on_device(cb):
     # at 2e-4 .. 5e-4 on this data; the caps of its tests are 0.012 / 0.005)
     assert np.abs(ndtr(np.log(t2.quantile(QS9))) - QS9).max() < 2e-3
     assert len(c1) > 90
+
+
+def test_weights_validated_on_the_device(cb):
+    """tdigest.pyx:304-305 for the parallel path: the check runs inside the accumulate kernel;
+    a bad weight raises ValueError and leaves the digest as it was."""
+    rng = np.random.default_rng(12)
+    n = 300000
+    x = rng.normal(size=n)
+    w = rng.uniform(0.5, 1.5, n)
+    t = cb.TDigest(100, mode="parallel")
+    t.update(x, w)
+    before = t.centroids().tobytes(), t.size()
+    for bad in (0.0, -1.0, np.nan, np.inf):
+        wb = w.copy()
+        wb[n // 3] = bad
+        with pytest.raises(ValueError):
+            t.update(x, wb)
+        with pytest.raises(ValueError):
+            t.update(cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(wb))
+        assert (t.centroids().tobytes(), t.size()) == before
+    # tiny positive weights are legal and dropped by the kernel (tdigest_stubs.c:285)
+    wb = w.copy()
+    wb[::2] = 1e-300
+    t2 = cb.TDigest(100, mode="parallel")
+    t2.update(x, wb)
+    assert abs(t2.size() - wb[1::2].sum()) <= 1e-12 * wb.sum()
+    # check_w=False: asynchronous, no validation
+    t3 = cb.TDigest(100, mode="parallel")
+    t3.update(cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w), check_w=False)
+    assert abs(t3.size() - w.sum()) <= 1e-12 * w.sum()

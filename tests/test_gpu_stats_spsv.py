@@ -1,0 +1,235 @@
+"""GPU parity tests for SummaryStats (stats_stubs.c) and SpaceSaving (space_saving_stubs.c.in),
+through the C ABI, against the oracle and the reference's own known-answer tests
+(crick/tests/test_stats.py, crick/tests/test_space_saving.py).
+
+Bar: SummaryStats bit-exact on the sequential path (n < 65536 per call), `atol 1e-8`-style
+tolerance vs NumPy/SciPy on the parallel path (the reference's own test tolerance,
+test_stats.py:20-21); SpaceSaving counters bit-exact, including list order.
+"""
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+R = oracle.restated
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import crick_b200
+    if crick_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return crick_b200
+
+
+# ---- SummaryStats -------------------------------------------------------------------------
+def test_stats_golden_state(cb, golden):
+    g, _ = golden
+    i = np.arange(10000)
+    s = cb.SummaryStats()
+    s.update(((i * 7919) % 10007) / 10007.0)
+    o = R.SummaryStats()
+    o.update(((i * 7919) % 10007) / 10007.0)
+    assert s.__getstate__() == o.__getstate__()
+    assert (s.var(), s.skew(), s.kurt()) == (o.var(), o.skew(), o.kurt())
+    # SURVEY Appendix A, KAT S
+    assert s.__getstate__()[0] == 10000 and s.sum() == 5000.157689617268
+    assert s.var() == 0.08334254276727161 and s.kurt() == -1.20010745225976
+
+
+@pytest.mark.parametrize("case", ["normal_nan", "empty", "one", "duplicate", "different", "ints"])
+def test_stats_sequential_bit_exact(cb, case):
+    rng = np.random.default_rng(0)
+    x = {"normal_nan": np.where(rng.uniform(size=10000) < 0.1, np.nan, rng.normal(50, 10, 10000)),
+         "empty": np.array([]), "one": np.array([1.5]), "duplicate": np.array([1.5] * 10),
+         "different": np.array([1.0, 2.0]), "ints": rng.integers(-50, 50, 3000)}[case]
+    s, o = cb.SummaryStats(), R.SummaryStats()
+    s.update(x)
+    o.update(x)
+    a, b = s.__getstate__(), o.__getstate__()
+    assert np.array_equal(np.array(a, dtype=float), np.array(b, dtype=float), equal_nan=True)
+    for f in ("mean", "var", "std", "skew", "kurt"):
+        assert np.array_equal(getattr(s, f)(), getattr(o, f)(), equal_nan=True), f
+    assert np.array_equal(s.var(ddof=1), o.var(ddof=1), equal_nan=True)
+    assert np.array_equal(s.skew(bias=False), o.skew(False), equal_nan=True)
+    assert np.array_equal(s.kurt(fisher=False, bias=False), o.kurt(False, False), equal_nan=True)
+
+
+def test_stats_quirks(cb):
+    s = cb.SummaryStats()
+    s.update([-5.0, -3.0])
+    assert s.max() == -2.2250738585072014e-308          # S0: max starts at -DBL_MIN
+    s = cb.SummaryStats()
+    s.add(10, 2)                                        # test_stats.py:112-116
+    assert (s.count(), s.sum(), s.mean(), s.var()) == (2, 10.0, 5.0, 0.0)
+    s = cb.SummaryStats()
+    s.update([1.0, np.nan, 1.0])                        # S2: NaN after the first value
+    assert s.__getstate__() == (2, 2.0, 1.0, 1.0, 0.0, 0.0, 0.0, False, 1.0)
+    assert s.skew() == 0.0 and s.kurt() == -3.0
+    s = cb.SummaryStats()
+    s.update([np.nan, 1.0, 1.0])
+    assert np.isnan(s.skew()) and np.isnan(s.kurt())
+    assert repr(cb.SummaryStats()).startswith("SummaryStats<count=0")
+    with pytest.raises(ValueError):
+        s.add(1, 0)
+    with pytest.raises(TypeError):
+        s.update(np.array(["a"]))
+    with pytest.raises(TypeError):
+        s.merge(1)
+
+
+def test_stats_weights_merge_pickle(cb):
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=4000)
+    c = rng.integers(1, 5, 4000)
+    s, o = cb.SummaryStats(), R.SummaryStats()
+    s.update(x, c)
+    o.update(x, c)
+    assert s.__getstate__() == o.__getstate__()
+    parts, oparts = [], []
+    for k in range(4):
+        p, q = cb.SummaryStats(), R.SummaryStats()
+        p.update(x[k * 1000:(k + 1) * 1000])
+        q.update(x[k * 1000:(k + 1) * 1000])
+        parts.append(p)
+        oparts.append(q)
+    m, mo = cb.SummaryStats(), R.SummaryStats()
+    m.merge(*parts)
+    mo.merge(*oparts)
+    assert m.__getstate__() == mo.__getstate__()
+    m.merge(cb.SummaryStats())                          # merge with empty is the identity
+    assert m.__getstate__() == mo.__getstate__()
+    m2 = pickle.loads(pickle.dumps(m))
+    assert m2.__getstate__() == m.__getstate__()
+    rec = m.export_record()
+    z = cb.SummaryStats()
+    z.merge_record(rec)
+    assert z.__getstate__() == m.__getstate__()
+
+
+def test_stats_parallel_path_vs_numpy_scipy(cb):
+    import scipy.stats
+    rng = np.random.default_rng(2)
+    x = rng.normal(3, 2, 2 * 10**6)
+    x[::1000] = np.nan
+    for src in (x, None):
+        s = cb.SummaryStats()
+        s.update(cb.DeviceArray.from_numpy(x) if src is None else x)
+        ok = x[~np.isnan(x)]
+        assert s.count() == ok.size and s.min() == ok.min() and s.max() == ok.max()
+        assert abs(s.sum() - ok.sum()) <= 1e-9 * abs(ok.sum())
+        np.testing.assert_allclose(s.mean(), ok.mean(), rtol=0, atol=1e-8)
+        np.testing.assert_allclose(s.var(), ok.var(), rtol=0, atol=1e-8)
+        np.testing.assert_allclose(s.skew(), scipy.stats.skew(ok), rtol=0, atol=1e-8)
+        np.testing.assert_allclose(s.kurt(), scipy.stats.kurtosis(ok), rtol=0, atol=1e-8)
+    # where the reference's int64 products wrap (n > 2^21) it is the reference
+    # that is wrong: the oracle with fp64 products agrees with us and with SciPy
+    o = R.SummaryStats()
+    oracle.stats_fp_products(o, True)
+    o.update(x)
+    np.testing.assert_allclose(s.kurt(), o.kurt(), rtol=0, atol=1e-8)
+    # int64 input converts like the NumPy safe cast (2^53 + 1 rounds)
+    xi = rng.zipf(1.1, 500000).astype(np.int64)
+    s = cb.SummaryStats()
+    s.update(cb.DeviceArray.from_numpy(xi))
+    xf = xi.astype(np.float64)
+    assert s.count() == xi.size and s.min() == xf.min() and s.max() == xf.max()
+    assert abs(s.mean() - xf.mean()) <= 1e-9 * abs(xf.mean())
+
+
+# ---- SpaceSaving ----------------------------------------------------------------------------
+def test_spsv_step_by_step_kat(cb):
+    """crick/tests/test_space_saving.py:67-107 and the weights KAT :164-184."""
+    s = cb.SpaceSaving(capacity=3, dtype="i8")
+    o = R.SpaceSaving(3)
+    for it, c in [(1, 1), (2, 1), (3, 1), (2, 1), (4, 1), (4, 1), (5, 3), (1, 2), (6, 1), (2, 5)]:
+        s.add(it, c)
+        o.add(it, c)
+        assert s.counters().tobytes() == o.counters().tobytes()
+    s = cb.SpaceSaving(2, "i8")
+    s.add(1, 5)
+    s.add(2, 3)
+    s.add(3, 100)                                       # eviction ignores the weight (:229-231)
+    assert s.counters().tolist() == [(1, 5, 0), (3, 4, 3)]
+    f = cb.SpaceSaving(5, "f8")
+    f.update([0.0, -0.0, 0.0, np.nan, np.nan])          # keyed by bit pattern
+    c = f.counters()
+    assert c["count"].tolist() == [2, 2, 1] and c["error"].tolist() == [0, 0, 0]
+    assert np.signbit(c["item"][2]) and np.isnan(c["item"][1])
+
+
+@pytest.mark.parametrize("dtype", ["i8", "f8"])
+def test_spsv_stream_vs_oracle_and_topk(cb, dtype):
+    rng = np.random.RandomState(42)                     # test_space_saving.py:11-14
+    data = rng.gamma(0.1, 0.1, size=10000)
+    data = (data * 1e4).astype("i8") if dtype == "i8" else np.round(data, 3)
+    s, o = cb.SpaceSaving(20, dtype), R.SpaceSaving(20)
+    s.update(data)
+    o.update(data.view("i8") if dtype == "f8" else data)
+    assert s.counters().view("i8").tobytes() == o.counters().view("i8").tobytes()
+    vals, counts = np.unique(data, return_counts=True)
+    order = np.argsort(-counts, kind="stable")[:10]
+    top = s.topk(10)
+    assert set(top["item"].tolist()) == set(vals[order].tolist())
+    true = dict(zip(vals.tolist(), counts.tolist()))
+    for it, c, e in s.counters().tolist():
+        assert c - e <= true.get(it, 0) <= c            # the Space-Saving guarantee
+    assert (np.diff(s.counters()["count"]) <= 0).all()
+    t = s.topk(3, astuples=True)
+    assert len(t) == 3 and t[0].count >= t[1].count
+    s2 = pickle.loads(pickle.dumps(s))
+    assert s2.counters().tobytes() == s.counters().tobytes()
+    a = cb.SpaceSaving(20, dtype)
+    for v in data[:500]:
+        a.add(v)
+    b = cb.SpaceSaving(20, dtype)
+    b.update(data[:500])
+    assert a.counters().tobytes() == b.counters().tobytes()      # add == update
+
+
+def test_spsv_exact_when_distinct_fits(cb):
+    """north_star: counts bit-exact whenever #distinct <= capacity; order = (count desc,
+    last-update position asc) as the reference's list gives it."""
+    rng = np.random.default_rng(3)
+    items = rng.zipf(1.3, 50000) % 700
+    w = rng.integers(1, 4, items.size)
+    s, o = cb.SpaceSaving(1000, "i8"), R.SpaceSaving(1000)
+    s.update(items, w)
+    o.update(items, w)
+    assert s.counters().tobytes() == o.counters().tobytes()
+    vals = np.unique(items)
+    got = {it: c for it, c, e in s.counters().tolist()}
+    assert all(got[v] == w[items == v].sum() for v in vals[:50])
+    assert (s.counters()["error"] == 0).all()
+    d = cb.SpaceSaving(1000, "i8")
+    d.update(cb.DeviceArray.from_numpy(items.astype(np.int64)), cb.DeviceArray.from_numpy(w.astype(np.int64)))
+    assert d.counters().tobytes() == s.counters().tobytes()
+
+
+def test_spsv_merge_vs_oracle(cb):
+    rng = np.random.default_rng(4)
+    a_items = rng.zipf(1.2, 20000) % 3000
+    b_items = (rng.zipf(1.2, 20000) % 3000)[::-1].copy()
+    for cap_a, cap_b in [(50, 50), (50, 20), (20, 50), (5000, 5000)]:
+        a, oa = cb.SpaceSaving(cap_a, "i8"), R.SpaceSaving(cap_a)
+        b, ob = cb.SpaceSaving(cap_b, "i8"), R.SpaceSaving(cap_b)
+        a.update(a_items)
+        oa.update(a_items)
+        b.update(b_items)
+        ob.update(b_items)
+        before = b.counters().tobytes()
+        a.merge(b)
+        oa.merge(ob)
+        assert a.counters().tobytes() == oa.counters().tobytes(), (cap_a, cap_b)
+        assert b.counters().tobytes() == before         # merge does not change its argument
+    with pytest.raises(TypeError):
+        a.merge(1)
+    with pytest.raises(ValueError):
+        a.merge(cb.SpaceSaving(5, "f8"))
+    with pytest.raises(ValueError):
+        cb.SpaceSaving(0)
+    with pytest.raises(ValueError):
+        a.add(1, 0)
