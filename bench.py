@@ -185,11 +185,16 @@ def main():
     lib.crick_synth_fill(dx.ptr, dw.ptr, n, SEED, rank * n, 0, None)
     lib.crick_device_synchronize()
 
+    reducer = None
+    if world > 1:
+        from crick_b200.distributed import TDigestAllReduce
+        reducer = TDigestAllReduce(COMPRESSION)
+
     def step(t):
         t.update(dx, dw, mode="parallel", stream=sptr)
         if world > 1:
             with torch.cuda.stream(stream):
-                return allgather_merge_tdigest(t)
+                return reducer(t)
         return t
 
     def barrier():

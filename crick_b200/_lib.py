@@ -44,6 +44,7 @@ _SIG = {
     "crick_tdigest_add": (c_int, [_P, c_double, c_double]),
     "crick_tdigest_update": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P]),
     "crick_tdigest_update_checked": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P, _P]),
+    "crick_tdigest_update_stats": (c_int, [_P, _P, _P, _P, c_double, c_int64, c_int, c_int, _P, _P]),
     "crick_tdigest_flush": (c_int, [_P]),
     "crick_tdigest_merge": (c_int, [_P, _P, c_int]),
     "crick_tdigest_scale": (c_int, [_P, c_double]),
@@ -61,6 +62,7 @@ _SIG = {
     "crick_tdigest_get_centroids": (c_int, [_P, _P, c_int]),
     "crick_tdigest_centroids_device": (_P, [_P]),
     "crick_tdigest_set_state": (c_int, [_P, _P, c_int, c_double, c_double, c_double]),
+    "crick_tdigest_reset": (c_int, [_P, _P]),
     "crick_tdigest_debug_edges": (c_int, [_P, _P, c_int]),
     "crick_tdigest_debug_buckets": (c_int, [_P, _P, _P, _P, c_int]),
     "crick_tdigest_record_doubles": (c_int, [_P]),

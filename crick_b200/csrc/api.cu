@@ -238,7 +238,8 @@ int crick_tdigest_add(crick_tdigest_t* t, double x, double w) {
 // host-resident input, parallel mode: same sample positions as the device sampler, then
 // double-buffered chunks (copy of chunk k+1 overlaps the accumulate of chunk k)
 static int td_update_host_parallel(crick_tdigest* t, const double* x, const double* w, double wsc,
-                                   int64_t n, cudaStream_t st, int* bad_weights) {
+                                   int64_t n, cudaStream_t st, int* bad_weights,
+                                   crick_stats* stats) {
     if (td_scratch(t)) return -1;
     cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
     if (e != cudaSuccess) return fail("flush", e);
@@ -257,6 +258,9 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     if (e == cudaSuccess) e = parallel_begin_from_sample(t->s.v, S, t->scratch, st);
     if (e != cudaSuccess) return fail("parallel edges", e);
 
+    StatsPart* sparts = nullptr;
+    int snparts = 0;
+    if (stats && stats_fused_begin(stats, st, &sparts, &snparts)) return -1;
     const int64_t chunk = 1 << 24;  // 16 Mi values: 128 MiB per array per buffer
     const int nbuf = 2;
     double* dbuf[2] = {nullptr, nullptr};
@@ -287,13 +291,15 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
             if (e == cudaSuccess)
                 e = parallel_accumulate(t->s.v, dbuf[b], w ? dbuf[b] + cw : nullptr, wsc, m,
-                                        t->scratch, sm_count(), st, k == 0);
+                                        t->scratch, sm_count(), st, k == 0, sparts, (long)off);
             if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
         }
         if (e == cudaSuccess && bad_weights && w)
             e = parallel_bad_weights(t->scratch, st, bad_weights);
-        if (e == cudaSuccess && !(bad_weights && *bad_weights))
+        if (e == cudaSuccess && !(bad_weights && *bad_weights)) {
             e = parallel_finalize(t->s.v, 0, t->scratch, sm_count(), st);
+            if (e == cudaSuccess && stats) e = stats_fused_finish(stats, sm_count(), st);
+        }
     }
     if (e != cudaSuccess) rc = fail("host-chunked parallel update", e);
     // buffers are freed only after the work that reads them has finished
@@ -309,11 +315,11 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
 
 static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                      int64_t n, int x_on_device, int w_on_device, int mode, void* stream,
-                     int* bad_weights);
+                     int* bad_weights, crick_stats* stats);
 
 int crick_tdigest_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                          int64_t n, int x_on_device, int w_on_device, int mode, void* stream) {
-    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, mode, stream, nullptr);
+    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, mode, stream, nullptr, nullptr);
 }
 
 int crick_tdigest_update_checked(crick_tdigest_t* t, const double* x, const double* w,
@@ -321,12 +327,23 @@ int crick_tdigest_update_checked(crick_tdigest_t* t, const double* x, const doub
                                  int mode, void* stream, int* bad_weights) {
     if (!bad_weights) return fail_msg("update_checked: bad_weights must not be NULL");
     *bad_weights = 0;
-    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, mode, stream, bad_weights);
+    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, mode, stream, bad_weights,
+                     nullptr);
+}
+
+int crick_tdigest_update_stats(crick_tdigest_t* t, crick_stats_t* stats, const double* x,
+                               const double* w, double w_scalar, int64_t n, int x_on_device,
+                               int w_on_device, void* stream, int* bad_weights) {
+    if (!stats) return fail_msg("update_stats: stats must not be NULL");
+    if (n < CRICK_PARALLEL_MIN) return fail_msg("update_stats needs n >= CRICK_PARALLEL_MIN");
+    if (bad_weights) *bad_weights = 0;
+    return td_update(t, x, w, w_scalar, n, x_on_device, w_on_device, CRICK_MODE_PARALLEL, stream,
+                     bad_weights, stats);
 }
 
 static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                      int64_t n, int x_on_device, int w_on_device, int mode, void* stream,
-                     int* bad_weights) {
+                     int* bad_weights, crick_stats* stats) {
     if (n <= 0) return 0;  // tdigest_stubs.c:648-650
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
@@ -339,7 +356,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     if (w_arr && (x_on_device != w_on_device))
         return fail_msg("x and w must both be host or both be device arrays");
     if (!x_on_device) {
-        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st, bad_weights);
+        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st, bad_weights, stats);
         // reference mode from host memory: stage the whole (small) input
         double* d = nullptr;
         size_t bytes = (size_t)n * sizeof(double) * (w_arr ? 2 : 1);
@@ -361,9 +378,14 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     if (parallel) {
         if (td_scratch(t)) return -1;
         e = launch_flush(t->s.v, 0, 1, 1, st);
+        StatsPart* sparts = nullptr;
+        int snparts = 0;
+        if (stats && stats_fused_begin(stats, st, &sparts, &snparts)) return -1;
         if (e == cudaSuccess)
             e = launch_parallel_update(t->s.v, 0, x, w, w_scalar, n, t->scratch, sm_count(), st,
-                                       bad_weights);
+                                       bad_weights, sparts);
+        if (e == cudaSuccess && stats && !(bad_weights && *bad_weights))
+            e = stats_fused_finish(stats, sm_count(), st);
     } else {
         e = launch_ingest(t->s.v, 1, x, w, w_scalar, 1, 1, nullptr, n, 0, nullptr, 0, st);
     }
@@ -487,6 +509,15 @@ int crick_tdigest_set_state(crick_tdigest_t* t, const double* centroids, int n, 
     if (e != cudaSuccess) return fail("set_state", e);
     t->mirror = h;
     return 0;
+}
+
+int crick_tdigest_reset(crick_tdigest_t* t, void* stream) {
+    cudaStream_t st = td_stream(t, stream);
+    t->px.clear();
+    t->pw.clear();
+    t->mirror_ok = false;
+    cudaError_t e = launch_init_hdr(t->s.v.hdr, 1, st);
+    return e == cudaSuccess ? 0 : fail("reset", e);
 }
 
 int crick_tdigest_debug_edges(crick_tdigest_t* t, double* out, int max_out) {

@@ -2,7 +2,10 @@
 #pragma once
 #include "common.cuh"
 
+struct crick_stats;
 namespace crick {
+
+struct StatsPart;   // stats_dev.cuh
 
 // ---- reference-compatible path (tdigest_kernels.cu)
 cudaError_t launch_ingest(const BatchView& v, long ngroups, const double* X, const double* W,
@@ -35,14 +38,17 @@ size_t parallel_scratch_bytes(double compression, int sm_count);
 // synchronises, and leaves the digest untouched when *bad_weights comes back non-zero.
 cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
                                    double wsc, long n, void* scratch, int sm_count,
-                                   cudaStream_t st, int* bad_weights);
+                                   cudaStream_t st, int* bad_weights, StatsPart* stats_parts);
 cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad);
 // The same pipeline in pieces, for host-resident input streamed in chunks: edges
 // from a caller-provided sample (copied to parallel_sample_x/w), any number of
 // accumulate calls (first = 1 on the first), then one finalize.
 cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratch, cudaStream_t st);
+// stats_parts != nullptr: also accumulate SummaryStats moments of x (count 1 each) into one
+// StatsPart per CTA; idx_base = index of X[0] in the caller's whole array
 cudaError_t parallel_accumulate(const BatchView& v, const double* X, const double* W, double wsc,
-                                long n, void* scratch, int sm_count, cudaStream_t st, int first);
+                                long n, void* scratch, int sm_count, cudaStream_t st, int first,
+                                StatsPart* stats_parts, long idx_base);
 cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_count,
                               cudaStream_t st);
 // debug/test accessor: copy the bucket edges of the last parallel update to the host
@@ -55,6 +61,10 @@ long parallel_sample_capacity(void* scratch);
 // host mirrors of the device sampler, so that host-resident input picks the same sample
 long parallel_sample_len(long n);
 long parallel_sample_pos(long i, long n, long S);
+
+// fused moments: per-CTA StatsPart slots written by k_bin_accumulate, folded by stats.cu
+int stats_fused_begin(crick_stats* s, cudaStream_t st, StatsPart** parts, int* nparts);
+cudaError_t stats_fused_finish(crick_stats* s, int nused, cudaStream_t st);
 
 void profile_enable(int on);
 int profile_collect(double* total_ms, long long* launches);

@@ -17,8 +17,10 @@
 // (where the reference is wrong).  This is a deliberate, documented divergence.
 #include "../../include/crick_cuda.h"
 #include "api_common.h"
+#include "stats_dev.cuh"
 
 #include <cmath>
+#include <type_traits>
 
 namespace crick {
 
@@ -140,103 +142,61 @@ __global__ void k_stats_seq(StatsState* st, const XT* __restrict__ x,
 
 // ---------------------------------------------------------------------------
 // parallel path
-struct StatsPart {          // mergeable summary of a contiguous index range
-    long long count;
-    double sum, vmin, vmax, m2, m3, m4;
-    long first_idx;          // index of first non-NaN element (LONG_MAX if none)
-    long last_nan_idx;       // index of last NaN element (-1 if none)
-    double first_value;      // value at first_idx
-    double last_value;       // value of the last element seen (for the all-NaN case)
-    long last_idx;
-};
-
-__device__ __forceinline__ void part_fresh(StatsPart& p) {
-    p.count = 0; p.sum = 0; p.vmin = INFINITY; p.vmax = -INFINITY; p.m2 = p.m3 = p.m4 = 0;
-    p.first_idx = 0x7fffffffffffffffl; p.last_nan_idx = -1; p.first_value = 0.0;
-    p.last_value = 0.0; p.last_idx = -1;
-}
-
-__device__ __forceinline__ void part_merge(StatsPart& a, const StatsPart& b) {
-    if (b.first_idx < a.first_idx) { a.first_idx = b.first_idx; a.first_value = b.first_value; }
-    if (b.last_nan_idx > a.last_nan_idx) a.last_nan_idx = b.last_nan_idx;
-    if (b.last_idx > a.last_idx) { a.last_idx = b.last_idx; a.last_value = b.last_value; }
-    if (b.count == 0) return;
-    if (a.count == 0) {
-        a.count = b.count; a.sum = b.sum; a.vmin = b.vmin; a.vmax = b.vmax;
-        a.m2 = b.m2; a.m3 = b.m3; a.m4 = b.m4;
-        return;
-    }
-    // Pebay pairwise merge, fp64 products
-    double n1 = (double)a.count, n2 = (double)b.count, n = n1 + n2;
-    double delta = b.sum / n2 - a.sum / n1;
-    double dn = delta / n, dn2 = dn * dn, dn3 = dn2 * dn;
-    double n1n2 = n1 * n2;
-    double m4 = a.m4 + b.m4 + n1n2 * (n1 * n1 - n1n2 + n2 * n2) * delta * dn3 +
-                6.0 * (n1 * n1 * b.m2 + n2 * n2 * a.m2) * dn2 + 4.0 * (n1 * b.m3 - n2 * a.m3) * dn;
-    double m3 = a.m3 + b.m3 + n1n2 * (n1 - n2) * delta * dn2 + 3.0 * (n1 * b.m2 - n2 * a.m2) * dn;
-    double m2 = a.m2 + b.m2 + n1n2 * delta * dn;
-    a.m4 = m4; a.m3 = m3; a.m2 = m2;
-    a.count += b.count; a.sum += b.sum;
-    a.vmin = fmin(a.vmin, b.vmin); a.vmax = fmax(a.vmax, b.vmax);
-}
-
-__device__ __forceinline__ StatsPart part_shfl_xor(const StatsPart& p, int m) {
-    StatsPart o;
-    o.count = __shfl_xor_sync(CRICK_FULL, p.count, m);
-    o.sum = shfl_xor_d(p.sum, m); o.vmin = shfl_xor_d(p.vmin, m); o.vmax = shfl_xor_d(p.vmax, m);
-    o.m2 = shfl_xor_d(p.m2, m); o.m3 = shfl_xor_d(p.m3, m); o.m4 = shfl_xor_d(p.m4, m);
-    o.first_idx = __shfl_xor_sync(CRICK_FULL, p.first_idx, m);
-    o.last_nan_idx = __shfl_xor_sync(CRICK_FULL, p.last_nan_idx, m);
-    o.first_value = shfl_xor_d(p.first_value, m);
-    o.last_value = shfl_xor_d(p.last_value, m);
-    o.last_idx = __shfl_xor_sync(CRICK_FULL, p.last_idx, m);
-    return o;
-}
-
-template <typename XT>
-__global__ void __launch_bounds__(256) k_stats_partial(const XT* __restrict__ x,
+// 128-bit loads (2 elements), 4 in flight per thread; HBM bound (8 B / value)
+template <typename XT, bool UNIT>
+__global__ void __launch_bounds__(512) k_stats_partial(const XT* __restrict__ x,
                                                        const long long* __restrict__ cnt,
                                                        long long cnt_scalar, long n,
                                                        StatsPart* __restrict__ parts) {
-    __shared__ StatsPart s_part[8];
+    __shared__ StatsPart s_part[16];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long stride = (long)gridDim.x * blockDim.x;
-    // per-thread shifted power sums around K = first non-NaN value this thread sees
-    double K = 0.0;
-    bool haveK = false;
-    double cN = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, sx = 0.0;
-    long long cnt_i = 0;
+    StatsAcc a;
+    a.K = 0.0; a.cN = 0.0; a.s1 = a.s2 = a.s3 = a.s4 = a.sx = 0.0;
+    a.vmin = INFINITY; a.vmax = -INFINITY; a.cnt = 0; a.haveK = false;
     StatsPart p;
     part_fresh(p);
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double v = load_x(x, i);
-        p.last_idx = i; p.last_value = v;
-        if (v != v) { p.last_nan_idx = i; continue; }
-        long long c = cnt ? cnt[i] : cnt_scalar;
-        if (i < p.first_idx) { p.first_idx = i; p.first_value = v; }
-        double cd = (double)c;
-        double u = v / cd;  // stats_do_update: u2 = sum2 / n2 (:51)
-        if (!haveK) { K = u; haveK = true; }
-        double d = u - K, d2 = d * d;
-        cN += cd; cnt_i += c; sx += v;
-        s1 += cd * d; s2 += cd * d2; s3 += cd * d2 * d; s4 += cd * d2 * d2;
-        p.vmin = fmin(p.vmin, v); p.vmax = fmax(p.vmax, v);
-    }
-    if (haveK) {
-        double md = s1 / cN;
-        p.count = cnt_i; p.sum = sx;
-        p.m2 = s2 - cN * md * md;
-        p.m3 = s3 - 3.0 * md * s2 + 2.0 * cN * md * md * md;
-        p.m4 = s4 - 4.0 * md * s3 + 6.0 * md * md * s2 - 3.0 * cN * md * md * md * md;
-        if (p.m2 < 0.0) p.m2 = 0.0;
-        if (p.m4 < 0.0) p.m4 = 0.0;
-    }
+    const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (!cnt || (reinterpret_cast<uintptr_t>(cnt) & 15) == 0);
+    long done = 0;
+    if (vec) {
+        const long npair = n >> 1;
+        constexpr int U = 4;
+        for (long j0 = tid; j0 < npair; j0 += U * stride) {
+            double v[2 * U];
+            long long c[2 * U];
 #pragma unroll
-    for (int m = 1; m < 32; m <<= 1) {
-        StatsPart o = part_shfl_xor(p, m);
-        // fixed association (lower lane on the left) => deterministic
-        if ((threadIdx.x & m) == 0) part_merge(p, o);
-        else { StatsPart t = o; part_merge(t, p); p = t; }
+            for (int k = 0; k < U; ++k) {
+                const long j = j0 + k * stride;
+                if (j < npair) {
+                    if (sizeof(XT) == 8 && !std::is_same<XT, double>::value) {
+                        longlong2 t = __ldg(reinterpret_cast<const longlong2*>(x) + j);
+                        v[2 * k] = (double)t.x; v[2 * k + 1] = (double)t.y;
+                    } else {
+                        double2 t = __ldg(reinterpret_cast<const double2*>(x) + j);
+                        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+                    }
+                    if (!UNIT && cnt) {
+                        longlong2 t = __ldg(reinterpret_cast<const longlong2*>(cnt) + j);
+                        c[2 * k] = t.x; c[2 * k + 1] = t.y;
+                    } else { c[2 * k] = c[2 * k + 1] = cnt_scalar; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long j = j0 + k * stride;
+                if (j < npair) {
+                    stats_one<UNIT>(a, p, v[2 * k], c[2 * k], 2 * j);
+                    stats_one<UNIT>(a, p, v[2 * k + 1], c[2 * k + 1], 2 * j + 1);
+                }
+            }
+        }
+        done = npair << 1;
     }
+    for (long i = done + tid; i < n; i += stride)
+        stats_one<UNIT>(a, p, load_x(x, i), cnt ? cnt[i] : cnt_scalar, i);
+    stats_thread_finish(a, p);
+    p = stats_warp_reduce(p);
     const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) s_part[warp] = p;
     __syncthreads();
@@ -247,10 +207,29 @@ __global__ void __launch_bounds__(256) k_stats_partial(const XT* __restrict__ x,
     }
 }
 
-__global__ void k_stats_final(StatsState* st, const StatsPart* __restrict__ parts, int nparts) {
-    if (threadIdx.x || blockIdx.x) return;
-    StatsPart t = parts[0];
-    for (int i = 1; i < nparts; ++i) part_merge(t, parts[i]);
+// one CTA of 1024 threads: shuffle tree per warp (fixed association, left = lower index), then
+// thread 0 folds the <= 32 warp results -- ~40 dependent Pebay merges instead of nparts
+__global__ void __launch_bounds__(1024) k_stats_final(StatsState* st,
+                                                      const StatsPart* __restrict__ parts,
+                                                      int nparts) {
+    __shared__ StatsPart s_w[32];
+    StatsPart p;
+    part_fresh(p);
+    // thread t folds parts t, t + 1024, ... (nparts <= 1024 in practice: one each)
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+        if (i == (int)threadIdx.x) p = parts[i]; else part_merge(p, parts[i]);
+    }
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        StatsPart o = part_shfl_xor(p, m);
+        if ((threadIdx.x & m) == 0) part_merge(p, o);
+        else { StatsPart t2 = o; part_merge(t2, p); p = t2; }
+    }
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x) return;
+    StatsPart t = s_w[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) part_merge(t, s_w[w]);
     StatsState T = *st;
     // homogeneous / first_value bookkeeping of the update loop (:200-205)
     const bool any_nonnan = t.first_idx != 0x7fffffffffffffffl;
@@ -344,14 +323,34 @@ static cudaError_t stats_launch(crick_stats* s, const XT* x, const long long* c,
         k_stats_seq<XT><<<1, 32, 0, st>>>(s->d, x, c, cs, n, 1);
         return cudaGetLastError();
     }
-    long blocks = (n + 256 * 16 - 1) / (256 * 16);
+    long blocks = (n + 512 * 16 - 1) / (512 * 16);
     if (blocks > s->nparts) blocks = s->nparts;
     count_launch();
-    k_stats_partial<XT><<<(unsigned)blocks, 256, 0, st>>>(x, c, cs, n, s->parts);
+    if (!c && cs == 1) k_stats_partial<XT, true><<<(unsigned)blocks, 512, 0, st>>>(x, c, cs, n, s->parts);
+    else k_stats_partial<XT, false><<<(unsigned)blocks, 512, 0, st>>>(x, c, cs, n, s->parts);
     count_launch();
-    k_stats_final<<<1, 32, 0, st>>>(s->d, s->parts, (int)blocks);
+    k_stats_final<<<1, 1024, 0, st>>>(s->d, s->parts, (int)blocks);
     return cudaGetLastError();
 }
+
+// ---- hooks for the fused t-digest + moments pass (tdigest_parallel.cu) -------------------
+// begin: pending scalar adds are applied first; returns the per-CTA parts buffer.
+namespace crick {
+int stats_fused_begin(crick_stats* s, cudaStream_t st, StatsPart** parts, int* nparts) {
+    cudaStream_t own = ss_stream(s, st);
+    if (ss_drain(s, own)) return -1;
+    s->mirror_ok = false;
+    *parts = s->parts;
+    *nparts = s->nparts;
+    return 0;
+}
+// finish: fold `nused` parts (one per CTA of the accumulate kernel) into the state
+cudaError_t stats_fused_finish(crick_stats* s, int nused, cudaStream_t st) {
+    count_launch();
+    k_stats_final<<<1, 1024, 0, st>>>(s->d, s->parts, nused);
+    return cudaGetLastError();
+}
+}  // namespace crick
 
 extern "C" {
 
@@ -359,7 +358,7 @@ crick_stats_t* crick_stats_new(void) {
     if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
     crick_stats* s = new (std::nothrow) crick_stats();
     if (!s) return nullptr;
-    s->nparts = sm_count() * 8;
+    s->nparts = sm_count() * 4;   // 4 CTAs of 512 threads per SM
     cudaError_t e = cudaMalloc(&s->d, sizeof(StatsState));
     if (e == cudaSuccess) e = cudaMalloc(&s->parts, sizeof(StatsPart) * s->nparts);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking);

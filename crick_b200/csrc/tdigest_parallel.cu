@@ -30,6 +30,7 @@
 // is (a) bucket sums vs a CPU restatement of the same partition at 1e-12 and
 // (b) rank error <= the reference's on the same data (tests/test_parallel.py).
 #include "kernels.h"
+#include "stats_dev.cuh"
 #include "tdigest_ref.cuh"
 
 #include <cstdlib>
@@ -775,12 +776,13 @@ __device__ __forceinline__ void stage_read(unsigned stage, int lane, double* xs,
 
 // VEC: 16-byte aligned input.  STAGE: tiles arrive through the per-warp TMA stage; otherwise
 // they are prefetched into L2 and loaded with LDG.128 (VEC) or plain loads (!VEC).
-template <bool HAS_W, bool VEC, bool STAGE, int GRID, bool FAST>
+template <bool HAS_W, bool VEC, bool STAGE, bool STATS, int GRID, bool FAST>
 __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ring, unsigned stage,
                                                   unsigned mbar, const double* __restrict__ X,
                                                   const double* __restrict__ W, double wsc, long n,
                                                   long gw, long tw, int lane, double& vmin,
-                                                  double& vmax, int* badw_flag) {
+                                                  double& vmax, int* badw_flag, StatsAcc& sa,
+                                                  StatsPart& sp, long idx_base) {
     const long nfull = n / kTile;
     const long ntiles = (n + kTile - 1) / kTile;
     const long rounds = (ntiles + tw - 1) / tw;  // the same for every warp: the token needs all
@@ -814,6 +816,15 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
             }
         } else if (have) {
             m = load_partial<HAS_W>(X, W, t * kTile, n, lane, xs, ws);
+        }
+        if (STATS && have) {
+            // SummaryStats moments of x in the same pass (stats_update_ndarray :199-210 with
+            // count 1): NaN skipped, everything else -- infinities included -- counted
+#pragma unroll
+            for (int k = 0; k < 2 * kU; ++k)
+                if ((m >> k) & 1u)
+                    stats_one<true>(sa, sp, xs[k], 1,
+                                    idx_base + t * kTile + (k >> 1) * 64 + 2 * lane + (k & 1));
         }
         if (have) {
             bool e0 = classify_group<HAS_W, GRID, FAST>(L, xs, ws, wsc, m & 0xfu, addr, ww, ss,
@@ -852,15 +863,17 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
     if (HAS_W && __any_sync(CRICK_FULL, badw) && lane == 0) atomicOr(badw_flag, 1);
 }
 
-template <bool HAS_W, bool VEC, bool STAGE>
-__global__ void __launch_bounds__(448, 1) k_bin_accumulate(const double* __restrict__ X,
+template <bool HAS_W, bool VEC, bool STAGE, bool STATS>
+__global__ void __launch_bounds__(STATS ? 384 : 448, 1) k_bin_accumulate(const double* __restrict__ X,
                                                            const double* __restrict__ W, double wsc,
                                                            long n, ParHeader* hdr,
                                                            const double* __restrict__ g_edges,
                                                            const unsigned short* __restrict__ g_tab,
                                                            double2* __restrict__ partial,
                                                            double2* __restrict__ minmax, int bmax,
-                                                           int cols, int ntab, int accumulate_into) {
+                                                           int cols, int ntab, int accumulate_into,
+                                                           StatsPart* __restrict__ stats_parts,
+                                                           long idx_base) {
     // shared: stage[nwarps][4 KB] (STAGE only) | acc[ntab][bmax + 1][cols] double2 |
     //         edges[bmax + kEdgePad] | tab[kTabLen] uint16 | mbar[nwarps]
     const int nwarps = blockDim.x >> 5;   // a multiple of ntab, <= 14 (one named barrier each)
@@ -910,15 +923,19 @@ __global__ void __launch_bounds__(448, 1) k_bin_accumulate(const double* __restr
     ring.passes = 32 / cols;
     ring.pass = lane / cols;
     double vmin = INFINITY, vmax = -INFINITY;
+    StatsAcc sa;
+    StatsPart sp;
+    stats_acc_fresh(sa);
+    part_fresh(sp);
     const long gw = (long)blockIdx.x * nwarps + warp;
     const long tw = (long)gridDim.x * nwarps;
     const bool fast = L.kmax <= kKFast;
     if (hdr->grid == 1) {
-        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 1, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
-        else accumulate_stream<HAS_W, VEC, STAGE, 1, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
+        if (fast) accumulate_stream<HAS_W, VEC, STAGE, STATS, 1, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw, sa, sp, idx_base);
+        else accumulate_stream<HAS_W, VEC, STAGE, STATS, 1, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw, sa, sp, idx_base);
     } else {
-        if (fast) accumulate_stream<HAS_W, VEC, STAGE, 0, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
-        else accumulate_stream<HAS_W, VEC, STAGE, 0, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw);
+        if (fast) accumulate_stream<HAS_W, VEC, STAGE, STATS, 0, true>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw, sa, sp, idx_base);
+        else accumulate_stream<HAS_W, VEC, STAGE, STATS, 0, false>(L, ring, stage, mbar, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw, sa, sp, idx_base);
     }
     // CTA reduction in fixed column order -> deterministic partials
 #pragma unroll
@@ -927,7 +944,19 @@ __global__ void __launch_bounds__(448, 1) k_bin_accumulate(const double* __restr
         vmax = fmax(vmax, shfl_xor_d(vmax, d));
     }
     if (lane == 0) { s_min[warp] = vmin; s_max[warp] = vmax; }
+    __shared__ StatsPart s_sp[STATS ? 12 : 1];
+    if (STATS) {
+        stats_thread_finish(sa, sp);
+        sp = stats_warp_reduce(sp);
+        if (lane == 0) s_sp[warp] = sp;
+    }
     __syncthreads();
+    if (STATS && threadIdx.x == 0) {
+        StatsPart t = s_sp[0];
+        for (int wv = 1; wv < nwarps; ++wv) part_merge(t, s_sp[wv]);
+        if (accumulate_into) { StatsPart o = stats_parts[blockIdx.x]; part_merge(o, t); t = o; }
+        stats_parts[blockIdx.x] = t;
+    }
     // one warp per bucket: lanes read the columns (conflict-free), xor-shuffle tree
     double2* row = partial + (size_t)blockIdx.x * kBPad;
     for (int b = warp; b < B; b += nwarps) {
@@ -1150,7 +1179,7 @@ cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratc
 // not fit: one table (32 columns, or 16 / 8 / 4 for large compressions), one ring of 12
 // warps, tiles staged through shared memory by TMA.
 struct AccCfg { int cols, ntab, nw, stage; size_t smem; };
-static AccCfg acc_cfg(int bmax) {
+static AccCfg acc_cfg(int bmax, bool stats) {
     const size_t budget = 230000;                       // of 232448 B opt-in, 512 B are static
     const size_t fixed = kTabBytes + sizeof(double) * (size_t)(bmax + kEdgePad) + 16 * 8;
     const size_t table32 = (size_t)(bmax + 1) * 32 * 16;
@@ -1158,7 +1187,7 @@ static AccCfg acc_cfg(int bmax) {
     int want_tab = 0;
     if (const char* e = getenv("CRICK_ACC_T")) want_tab = atoi(e);   // tuning hooks (bench sweeps)
     if (want_tab != 1 && fixed + 2 * table32 <= budget) {
-        c.ntab = 2; c.cols = 32; c.nw = 14; c.stage = 0;
+        c.ntab = 2; c.cols = 32; c.nw = stats ? 12 : 14; c.stage = 0;
     } else {
         c.ntab = 1; c.nw = 12; c.stage = 1; c.cols = 32;
         while (c.cols > 1 &&
@@ -1167,7 +1196,7 @@ static AccCfg acc_cfg(int bmax) {
     }
     if (const char* e = getenv("CRICK_ACC_W")) {
         int v = atoi(e);
-        if (v >= c.ntab && v <= 14) c.nw = v - v % c.ntab;
+        if (v >= c.ntab && v <= (stats ? 12 : 14)) c.nw = v - v % c.ntab;
     }
     c.smem = fixed + (c.stage ? (size_t)c.nw * kStageBytes : 0) +
              (size_t)c.ntab * (bmax + 1) * c.cols * 16;
@@ -1204,10 +1233,10 @@ int profile_collect(double* total_ms, long long* launches) {
 
 static cudaError_t accumulate_impl(const BatchView& v, const double* X, const double* W, double wsc,
                                    long n, void* scratch, int sm_count, cudaStream_t st,
-                                   int accumulate_into) {
+                                   int accumulate_into, StatsPart* stats_parts, long idx_base) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     const int bmax = bmax_for(v.comp);
-    const AccCfg cfg = acc_cfg(bmax);
+    const AccCfg cfg = acc_cfg(bmax, stats_parts != nullptr);
     const size_t smem = cfg.smem;
     const bool vec = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
     const unsigned grid = (unsigned)sm_count;
@@ -1219,15 +1248,20 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
         if (g_prof_on && cudaEventCreate(&pe0) == cudaSuccess && cudaEventCreate(&pe1) == cudaSuccess)
             cudaEventRecord(pe0, st);
     }
-#define CRICK_LAUNCH_ACC(HW, VC, SG)                                                              \
+#define CRICK_LAUNCH_ACC_S(HW, VC, SG, SS)                                                        \
     do {                                                                                          \
-        e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC, SG>,                                    \
+        e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC, SG, SS>,                                \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                           \
         count_launch();                                                                           \
-        k_bin_accumulate<HW, VC, SG><<<grid, block, smem, st>>>(                                  \
+        k_bin_accumulate<HW, VC, SG, SS><<<grid, block, smem, st>>>(                              \
             X, W, wsc, n, L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, cfg.cols, cfg.ntab,   \
-            accumulate_into);                                                                     \
+            accumulate_into, stats_parts, idx_base);                                              \
+    } while (0)
+#define CRICK_LAUNCH_ACC(HW, VC, SG)                                                              \
+    do {                                                                                          \
+        if (stats_parts) CRICK_LAUNCH_ACC_S(HW, VC, SG, true);                                    \
+        else CRICK_LAUNCH_ACC_S(HW, VC, SG, false);                                               \
     } while (0)
     const bool stage = vec && cfg.stage;   // unaligned input: plain loads, no staging
     if (W) {
@@ -1240,6 +1274,7 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
         else CRICK_LAUNCH_ACC(false, true, false);
     }
 #undef CRICK_LAUNCH_ACC
+#undef CRICK_LAUNCH_ACC_S
     if (pe0 && pe1) {
         cudaEventRecord(pe1, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -1249,8 +1284,10 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
 }
 
 cudaError_t parallel_accumulate(const BatchView& v, const double* X, const double* W, double wsc,
-                                long n, void* scratch, int sm_count, cudaStream_t st, int first) {
-    return accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, first ? 0 : 1);
+                                long n, void* scratch, int sm_count, cudaStream_t st, int first,
+                                StatsPart* stats_parts, long idx_base) {
+    return accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, first ? 0 : 1, stats_parts,
+                           idx_base);
 }
 
 cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_count,
@@ -1282,7 +1319,7 @@ cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad) {
 
 cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
                                    double wsc, long n, void* scratch, int sm_count,
-                                   cudaStream_t st, int* bad_weights) {
+                                   cudaStream_t st, int* bad_weights, StatsPart* stats_parts) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     long S = sample_len(n);
     count_launch();
@@ -1291,7 +1328,7 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
     if (e != cudaSuccess) return e;
     e = edges_from_sorted_sample(v, L, S, st);
     if (e != cudaSuccess) return e;
-    e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0);
+    e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, stats_parts, 0);
     if (e != cudaSuccess) return e;
     if (bad_weights && W) {
         // validated update: the digest is only touched when every weight passed

@@ -53,26 +53,53 @@ def gather_records(rec, group=None):
     return out
 
 
-def allgather_merge_tdigest(digest, group=None):
-    """Return a new TDigest equal to ``TDigest(c).merge(*[digest of rank 0, 1, ...])``."""
-    import torch
-    import torch.distributed as dist
+class TDigestAllReduce:
+    """Reusable state of the multi-GPU reduction of one digest per rank: the record buffers
+    and the output digest are allocated once, so a step is export -> all-gather -> merge, three
+    enqueues on the caller's stream and no allocation, free or host synchronisation."""
 
-    world = dist.get_world_size(group)
-    nd = digest.record_doubles()
-    stream = torch.cuda.current_stream()
-    rec = torch.empty(nd, dtype=torch.float64, device="cuda")
-    digest.export_record(rec.data_ptr(), stream=stream.cuda_stream or None)
-    if stream.cuda_stream == 0:
-        # the legacy default stream cannot be named through the C ABI (NULL = handle's own)
-        from ._lib import lib
-        lib.crick_device_synchronize()
-    gathered = gather_records(rec, group)
-    out = TDigest(digest.compression)
-    out.merge_records(gathered.data_ptr(), world, stream=stream.cuda_stream or None)
-    if stream.cuda_stream == 0:
-        torch.cuda.synchronize()
-    out._keepalive = gathered  # the merge kernel reads it asynchronously
+    def __init__(self, compression, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.out = TDigest(compression)
+        nd = self.out.record_doubles()
+        self.rec = torch.empty(nd, dtype=torch.float64, device="cuda")
+        self.gathered = torch.empty((self.world, nd), dtype=torch.float64, device="cuda")
+
+    def __call__(self, digest):
+        """``TDigest(c).merge(*[digest of rank 0, 1, ...])`` on every rank.  Enqueued on torch's
+        current stream, which must not be the legacy default stream; the returned digest is
+        reused by the next call."""
+        import torch
+        import torch.distributed as dist
+
+        st = torch.cuda.current_stream().cuda_stream
+        if st == 0:
+            raise RuntimeError("run the reduction under `with torch.cuda.stream(s)`: the legacy "
+                               "default stream cannot be named through the C ABI")
+        digest.export_record(self.rec.data_ptr(), stream=st)
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.rec, group=self.group)
+        self.out.clear(stream=st)
+        self.out.merge_records(self.gathered.data_ptr(), self.world, stream=st)
+        return self.out
+
+
+def allgather_merge_tdigest(digest, group=None):
+    """One-shot form: a new TDigest equal to ``TDigest(c).merge(*[digest of rank 0, 1, ...])``."""
+    import torch
+
+    s = torch.cuda.current_stream()
+    if s.cuda_stream == 0:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+    red = TDigestAllReduce(digest.compression, group)
+    with torch.cuda.stream(s):
+        out = red(digest)
+    s.synchronize()
+    out._keepalive = red  # owns the gathered records the digest was merged from
     return out
 
 

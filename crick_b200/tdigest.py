@@ -264,7 +264,7 @@ class TDigest:
             raise ValueError("w must be > 0 and finite")
         check(lib.crick_tdigest_add(self._h, x, w), "add")
 
-    def update(self, x, w=1, mode=None, stream=None, check_w=True):
+    def update(self, x, w=1, mode=None, stream=None, check_w=True, stats=None):
         """update(self, x, w=1)
 
         Add many samples to this digest.
@@ -278,12 +278,16 @@ class TDigest:
             The weight (or weights) of the values to add. Default is 1.
         mode : optional override of the digest's update mode for this call.
         stream : optional ``cudaStream_t`` (int) to enqueue the work on.
+        stats : optional :class:`SummaryStats`; its moments of ``x`` (``stats.update(x)``) are
+            accumulated in the same pass over the data as the digest (parallel path).
         check_w : CUDA-array weights only.  True (default): raise ValueError like the
             reference when a weight is not finite or not > 0 -- checked on the device, which
             synchronises the stream.  False: fully asynchronous, ``w <= eps`` is dropped by
             the kernel exactly like ``tdigest_add`` does.
         """  # tdigest.pyx:282-308
         m = self._mode if mode is None else _lib.mode_code(mode)
+        if stats is not None:
+            return self._update_with_stats(x, w, stream, check_w, stats)
         xd = device_view(x)
         if xd is not None:
             return self._update_device(xd, w, m, stream, check_w)
@@ -330,6 +334,57 @@ class TDigest:
         else:
             check(lib.crick_tdigest_update(self._h, xf.ctypes.data, None, float(wf), n, 0, 0,
                                            eff, stream), "update")
+
+    def _update_with_stats(self, x, w, stream, check_w, stats):
+        """One pass over x for both sketches (crick_tdigest_update_stats); inputs too small for
+        the parallel path take the two ordinary calls."""
+        from .stats import SummaryStats
+        if not isinstance(stats, SummaryStats):
+            raise TypeError("stats must be a SummaryStats")
+        xd = device_view(x)
+        wd = device_view(w)
+        bad = ctypes.c_int(0)
+        if xd is not None:
+            if xd.dtype != np.float64:
+                raise TypeError("x must be float64 when given as a CUDA array")
+            if xd.size < _lib.PARALLEL_MIN:
+                self._update_device(xd, w, _lib.MODE_REFERENCE, stream, check_w)
+                return stats.update(x)
+            if wd is not None:
+                if wd.dtype != np.float64 or wd.size != xd.size:
+                    raise TypeError("w must be a float64 CUDA array shaped like x")
+                wp, wsc = wd.ptr, 0.0
+            else:
+                wp, wsc = None, _as_double(w, "w")
+                if wsc != 1 and (not math.isfinite(wsc) or wsc <= 0):
+                    raise ValueError("w must be > 0 and finite")
+            check(lib.crick_tdigest_update_stats(self._h, stats._h, xd.ptr, wp, wsc, xd.size, 1,
+                                                 1 if wp else 0, stream,
+                                                 ctypes.addressof(bad) if check_w else None),
+                  "update")
+        else:
+            x = np.asarray(x)
+            w = np.asarray(w)
+            if not np.can_cast(x.dtype, "f8", casting="safe"):
+                raise TypeError("x must be numeric")
+            if not np.can_cast(w.dtype, "f8", casting="safe"):
+                raise TypeError("w must be numeric")
+            if x.size == 0 or w.size == 0:
+                return
+            xf, wf = korder_pair(x, w)
+            if xf.size < _lib.PARALLEL_MIN:
+                self.update(x, w, mode="reference")
+                return stats.update(x)
+            if isinstance(wf, np.ndarray):
+                wp, wsc = wf.ctypes.data, 0.0
+            else:
+                wp, wsc = None, float(wf)
+                if wsc != 1 and (not math.isfinite(wsc) or wsc <= 0):
+                    raise ValueError("w must be > 0 and finite")
+            check(lib.crick_tdigest_update_stats(self._h, stats._h, xf.ctypes.data, wp, wsc, xf.size,
+                                                 0, 0, stream, ctypes.addressof(bad)), "update")
+        if bad.value:
+            raise ValueError("w must be > 0 and finite")
 
     def _update_device(self, xd, w, m, stream, check_w=True):
         if xd.dtype != np.float64:
@@ -401,6 +456,10 @@ class TDigest:
         out.__setstate__(self.__getstate__())
         check(lib.crick_tdigest_scale(out._h, factor), "scale")
         return out
+
+    def clear(self, stream=None):
+        """Empty the digest in place (the state ``TDigest(compression)`` starts with)."""
+        check(lib.crick_tdigest_reset(self._h, stream), "clear")
 
     # ---- multi-GPU wire format (SURVEY.md 8e) ------------------------------------
     def record_doubles(self):

@@ -89,6 +89,12 @@ int crick_tdigest_update(crick_tdigest_t *t, const double *x, const double *w, d
 int crick_tdigest_update_checked(crick_tdigest_t *t, const double *x, const double *w,
                                  double w_scalar, int64_t n, int x_on_device, int w_on_device,
                                  int mode, void *stream, int *bad_weights);
+/* Parallel-mode update with the SummaryStats moments of x (count 1 per element, NaN skipped:
+ * stats_update_ndarray, stats_stubs.c:199-210) accumulated into `stats` IN THE SAME PASS over
+ * the data.  n >= CRICK_PARALLEL_MIN.  bad_weights may be NULL (no weight validation). */
+int crick_tdigest_update_stats(crick_tdigest_t *t, crick_stats_t *stats, const double *x,
+                               const double *w, double w_scalar, int64_t n, int x_on_device,
+                               int w_on_device, void *stream, int *bad_weights);
 /* tdigest_flush, tdigest_stubs.c:219-273 */
 int crick_tdigest_flush(crick_tdigest_t *t);
 /* tdigest_merge, tdigest_stubs.c:592-606, for each of `others` in order (flushes them) */
@@ -118,6 +124,9 @@ const double *crick_tdigest_centroids_device(crick_tdigest_t *t);
 /* __setstate__, tdigest.pyx:253-263 (bounds-checked here: n <= size) */
 int crick_tdigest_set_state(crick_tdigest_t *t, const double *centroids, int n,
                             double total_weight, double min, double max);
+/* back to the state tdigest_new leaves (tdigest_stubs.c:63-92) without releasing anything:
+ * lets a reduction reuse one output digest per step (asynchronous on `stream`) */
+int crick_tdigest_reset(crick_tdigest_t *t, void *stream);
 /* test hook: bucket edges chosen by the last parallel-mode update (returns their count) */
 int crick_tdigest_debug_edges(crick_tdigest_t *t, double *out, int max_out);
 /* test hook: per-bucket (sum w, sum w*x) and (min, max) of the last parallel-mode update,

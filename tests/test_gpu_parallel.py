@@ -235,3 +235,54 @@ def test_weights_validated_on_the_device(cb):
     t3 = cb.TDigest(100, mode="parallel")
     t3.update(cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w), check_w=False)
     assert abs(t3.size() - w.sum()) <= 1e-12 * w.sum()
+
+
+def test_fused_moments_in_the_same_pass(cb):
+    """north_star: SummaryStats moments fused into the t-digest pass.  The digest must be the one
+    the plain update builds (bit for bit) and the moments must match the stand-alone stats pass
+    and NumPy/SciPy at the reference's own tolerance (test_stats.py:20-21)."""
+    import scipy.stats
+    rng = np.random.default_rng(14)
+    n = 1500003
+    x = rng.lognormal(size=n)
+    x[::5000] = np.nan
+    x[7::9000] = np.inf
+    w = rng.uniform(0.5, 1.5, n)
+    for dev in (False, True):
+        t, s = cb.TDigest(100, mode="parallel"), cb.SummaryStats()
+        if dev:
+            t.update(cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w), stats=s)
+        else:
+            t.update(x, w, stats=s)
+        p = cb.TDigest(100, mode="parallel")
+        p.update(x, w)
+        # (the fused kernel runs 12 warps per SM instead of 14, so the bucket sums are added in
+        # another order: same centroids up to rounding, not bit for bit)
+        a, b = t.centroids(), p.centroids()
+        assert len(a) == len(b)
+        np.testing.assert_allclose(a["mean"], b["mean"], rtol=1e-11)
+        np.testing.assert_allclose(a["weight"], b["weight"], rtol=1e-11)
+        assert abs(t.size() - p.size()) <= 1e-12 * p.size()
+        assert t.min() == p.min() and t.max() == p.max()
+        ok = x[~np.isnan(x)]
+        assert s.count() == ok.size and s.min() == ok.min() and s.max() == np.inf
+        fin = np.where(np.isinf(x), 1.0, x)          # moments on a finite copy
+        t2, s2 = cb.TDigest(100, mode="parallel"), cb.SummaryStats()
+        t2.update(fin, w, stats=s2)
+        okf = fin[~np.isnan(fin)]
+        alone = cb.SummaryStats()
+        alone.update(fin)
+        assert s2.count() == alone.count() == okf.size
+        assert s2.min() == okf.min() and s2.max() == okf.max()
+        np.testing.assert_allclose(s2.mean(), okf.mean(), rtol=1e-12)
+        np.testing.assert_allclose(s2.var(), okf.var(), rtol=1e-10)
+        np.testing.assert_allclose(s2.skew(), scipy.stats.skew(okf), rtol=0, atol=1e-8)
+        np.testing.assert_allclose(s2.kurt(), scipy.stats.kurtosis(okf), rtol=0, atol=1e-7)
+        np.testing.assert_allclose(s2.kurt(), alone.kurt(), rtol=0, atol=1e-7)
+    # a second fused update merges into both sketches; homogeneous bookkeeping survives
+    s3, t3 = cb.SummaryStats(), cb.TDigest(100)
+    ones = np.ones(70000)
+    t3.update(ones, stats=s3)
+    assert np.isnan(s3.skew()) and s3.count() == 70000        # homogeneous -> NaN (stats.pyx)
+    t3.update(np.full(70000, 2.0), stats=s3)
+    assert s3.count() == 140000 and s3.skew() == 0.0 and t3.size() == 140000

@@ -163,17 +163,19 @@ def test_spsv_step_by_step_kat(cb):
 
 @pytest.mark.parametrize("dtype", ["i8", "f8"])
 def test_spsv_stream_vs_oracle_and_topk(cb, dtype):
-    rng = np.random.RandomState(42)                     # test_space_saving.py:11-14
-    data = rng.gamma(0.1, 0.1, size=10000)
-    data = (data * 1e4).astype("i8") if dtype == "i8" else np.round(data, 3)
+    data = np.random.RandomState(42).gamma(0.1, 0.1, size=10000).round(2) * 100   # test_space_saving.py:10-11
+    if dtype == "i8":
+        data = data.astype("i8")
     s, o = cb.SpaceSaving(20, dtype), R.SpaceSaving(20)
     s.update(data)
     o.update(data.view("i8") if dtype == "f8" else data)
     assert s.counters().view("i8").tobytes() == o.counters().view("i8").tobytes()
+    assert s.size() == s.capacity
     vals, counts = np.unique(data, return_counts=True)
-    order = np.argsort(-counts, kind="stable")[:10]
+    inds = counts.argsort()[::-1]                       # test_space_saving.py:16-19,34-41
     top = s.topk(10)
-    assert set(top["item"].tolist()) == set(vals[order].tolist())
+    assert (top["item"] == vals[inds[:10]]).all()
+    assert (top["count"] == counts[inds[:10]]).all()
     true = dict(zip(vals.tolist(), counts.tolist()))
     for it, c, e in s.counters().tolist():
         assert c - e <= true.get(it, 0) <= c            # the Space-Saving guarantee

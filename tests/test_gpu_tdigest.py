@@ -364,3 +364,36 @@ def test_large_query_batch_vs_oracle(cb):
     assert back.tobytes() == o.cdf(xs).tobytes()
     assert (np.diff(xs) >= 0).all()
     assert np.abs(back - q).max() < 1e-3
+
+
+def test_allgather_reducer_world1_nccl(cb):
+    """The multi-GPU reduction (export record -> NCCL all-gather -> rank-order merge kernel) on a
+    1-rank group: must equal TDigest(c).merge(digest); the reducer's buffers are reused."""
+    import torch
+    import torch.distributed as dist
+    from crick_b200.distributed import TDigestAllReduce, allgather_merge_tdigest
+    rng = np.random.default_rng(13)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29617", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        red = TDigestAllReduce(100)
+        s = torch.cuda.Stream()
+        for _ in range(3):
+            x = rng.lognormal(size=50000)
+            t, o = cb.TDigest(100, mode="reference"), R.TDigest(100)
+            t.update(x)
+            o.update(x)
+            with torch.cuda.stream(s):
+                m = red(t)
+            mo = R.TDigest(100)
+            mo.merge(o)
+            same(m, mo)
+        m2 = allgather_merge_tdigest(t)
+        same(m2, mo)
+        t.clear()
+        assert t.size() == 0 and len(t.centroids()) == 0 and np.isnan(t.min())
+    finally:
+        if created:
+            dist.destroy_process_group()
