@@ -24,6 +24,9 @@ struct SpsvHdr {
     long size;
     int hcap;   // power of two >= 4*capacity
     int tomb;   // deleted markers currently in the table
+    long seen;  // elements consumed so far = stream position of the next one
+    int mixed;  // 1 after a user-level merge: `last` positions of two streams are mixed
+    int pad;
 };
 
 struct SpsvView {
@@ -31,6 +34,9 @@ struct SpsvView {
     long long* item;   // [capacity] slot arrays, creation order
     long long* count;
     long long* error;
+    long long* last;   // [capacity] stream position of the slot's latest update (parallel path:
+                       //            exact summaries are listed by (count desc, last asc) like
+                       //            the reference's list)
     int* order;        // [capacity] list position -> slot (0 = head)
     int* pos;          // [capacity] slot -> list position
     long long* hkey;   // [hcap]
@@ -38,7 +44,7 @@ struct SpsvView {
 };
 
 static size_t spsv_bytes(long cap, int hcap) {
-    return 64 + (size_t)cap * (24 + 8) + (size_t)hcap * 12 + 64;
+    return (64 + (size_t)cap * (32 + 8) + (size_t)hcap * 12 + 64 + 15) & ~(size_t)15;
 }
 
 __host__ __device__ inline SpsvView spsv_carve(unsigned char* base, long cap, int hcap) {
@@ -48,6 +54,7 @@ __host__ __device__ inline SpsvView spsv_carve(unsigned char* base, long cap, in
     v.item = reinterpret_cast<long long*>(p); p += cap * 8;
     v.count = reinterpret_cast<long long*>(p); p += cap * 8;
     v.error = reinterpret_cast<long long*>(p); p += cap * 8;
+    v.last = reinterpret_cast<long long*>(p); p += cap * 8;
     v.hkey = reinterpret_cast<long long*>(p); p += (size_t)hcap * 8;
     v.order = reinterpret_cast<int*>(p); p += cap * 4;
     v.pos = reinterpret_cast<int*>(p); p += cap * 4;
@@ -64,10 +71,10 @@ __device__ __forceinline__ unsigned hash64(long long k) {
 
 // working copy: header in registers (warp-uniform), arrays via pointers (shared or global)
 struct SpsvW {
-    long long *item, *count, *error, *hkey;
+    long long *item, *count, *error, *last, *hkey;
     int *order, *pos, *hval;
-    long capacity, size;
-    int hcap, tomb;
+    long capacity, size, seen;
+    int hcap, tomb, mixed;
 };
 
 // warp-parallel probe; returns table index of `k` or -1
@@ -159,10 +166,10 @@ __device__ __forceinline__ void sift(SpsvW& w, int p, int lane) {
 
 // counter_new (:141-164)
 __device__ __forceinline__ int ctr_new(SpsvW& w, long long item, long long count, long long error,
-                                       int lane) {
+                                       long long when, int lane) {
     int s = (int)w.size;
     if (lane == 0) {
-        w.item[s] = item; w.count[s] = count; w.error[s] = error;
+        w.item[s] = item; w.count[s] = count; w.error[s] = error; w.last[s] = when;
         w.order[s] = s; w.pos[s] = s;
     }
     w.size++;
@@ -174,9 +181,9 @@ __device__ __forceinline__ int ctr_new(SpsvW& w, long long item, long long count
 
 // swap (:186-210): relabel slot s, rebalance
 __device__ __forceinline__ void ctr_replace(SpsvW& w, int s, long long item, long long count,
-                                            long long error, int lane) {
+                                            long long error, long long when, int lane) {
     map_del(w, w.item[s], lane);
-    if (lane == 0) { w.item[s] = item; w.count[s] = count; w.error[s] = error; }
+    if (lane == 0) { w.item[s] = item; w.count[s] = count; w.error[s] = error; w.last[s] = when; }
     __syncwarp();
     sift(w, w.pos[s], lane);
     map_put(w, item, s, lane);
@@ -184,19 +191,20 @@ __device__ __forceinline__ void ctr_replace(SpsvW& w, int s, long long item, lon
 }
 
 // spsv_add (:213-250)
-__device__ __forceinline__ void spsv_add1(SpsvW& w, long long item, long long cnt, int lane) {
+__device__ __forceinline__ void spsv_add1(SpsvW& w, long long item, long long cnt, long long when,
+                                          int lane) {
     int idx = map_find(w, item, lane);
     if (idx < 0) {
         if (w.size == w.capacity) {
             int s = w.order[w.size - 1];
             long long c = w.count[s];
-            ctr_replace(w, s, item, c + 1, c, lane);  // ignores cnt (quirk P2)
+            ctr_replace(w, s, item, c + 1, c, when, lane);  // ignores cnt (quirk P2)
         } else {
-            ctr_new(w, item, cnt, 0, lane);
+            ctr_new(w, item, cnt, 0, when, lane);
         }
     } else {
         int s = w.hval[idx];
-        if (lane == 0) w.count[s] += cnt;
+        if (lane == 0) { w.count[s] += cnt; w.last[s] = when; }
         __syncwarp();
         sift(w, w.pos[s], lane);
     }
@@ -213,15 +221,17 @@ __device__ __forceinline__ SpsvW open_state(unsigned char* gbase, long cap, int 
         v = spsv_carve(smem_raw, cap, hcap);
         for (long i = lane; i < h.size; i += 32) {
             v.item[i] = g.item[i]; v.count[i] = g.count[i]; v.error[i] = g.error[i];
+            v.last[i] = g.last[i];
             v.order[i] = g.order[i]; v.pos[i] = g.pos[i];
         }
         for (int i = lane; i < hcap; i += 32) { v.hkey[i] = g.hkey[i]; v.hval[i] = g.hval[i]; }
         __syncwarp();
     }
     SpsvW w;
-    w.item = v.item; w.count = v.count; w.error = v.error; w.hkey = v.hkey;
+    w.item = v.item; w.count = v.count; w.error = v.error; w.last = v.last; w.hkey = v.hkey;
     w.order = v.order; w.pos = v.pos; w.hval = v.hval;
     w.capacity = h.capacity; w.size = h.size; w.hcap = h.hcap; w.tomb = h.tomb;
+    w.seen = h.seen; w.mixed = h.mixed;
     return w;
 }
 
@@ -232,6 +242,7 @@ __device__ __forceinline__ void close_state(const SpsvW& w, unsigned char* gbase
     if (use_smem) {
         for (long i = lane; i < w.size; i += 32) {
             g.item[i] = w.item[i]; g.count[i] = w.count[i]; g.error[i] = w.error[i];
+            g.last[i] = w.last[i];
             g.order[i] = w.order[i]; g.pos[i] = w.pos[i];
         }
         for (int i = lane; i < hcap; i += 32) { g.hkey[i] = w.hkey[i]; g.hval[i] = w.hval[i]; }
@@ -239,6 +250,7 @@ __device__ __forceinline__ void close_state(const SpsvW& w, unsigned char* gbase
     if (lane == 0) {
         SpsvHdr h;
         h.capacity = w.capacity; h.size = w.size; h.hcap = w.hcap; h.tomb = w.tomb;
+        h.seen = w.seen; h.mixed = w.mixed; h.pad = 0;
         *g.hdr = h;
     }
 }
@@ -258,10 +270,42 @@ __global__ void __launch_bounds__(32) k_spsv_update(unsigned char* state, long c
         for (int k = 0; k < m; ++k) {
             long long itk = __shfl_sync(CRICK_FULL, it, k);
             long long ck = __shfl_sync(CRICK_FULL, c, k);
-            spsv_add1(w, itk, ck, lane);
+            spsv_add1(w, itk, ck, w.seen + base + k, lane);
         }
     }
+    w.seen += n;
     close_state(w, state, cap, hcap, use_smem, lane);
+}
+
+// Parallel path, step 1 (Cafaro et al.: one summary per contiguous shard, then merges): warp g
+// replays shard g = [g*n/G, (g+1)*n/G) in order into its own summary in HBM/L2.  Positions
+// are global (main summary's `seen` + index), so that `last` survives the merges.
+__global__ void __launch_bounds__(128) k_spsv_shards(unsigned char* shards, size_t stride, long cap,
+                                                     int hcap, int nshards,
+                                                     const unsigned char* main_state,
+                                                     const long long* __restrict__ item,
+                                                     const long long* __restrict__ cnt,
+                                                     long long cnt_scalar, long n) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= nshards) return;
+    const long base_seen = reinterpret_cast<const SpsvHdr*>(main_state)->seen;
+    unsigned char* state = shards + (size_t)g * stride;
+    SpsvW w = open_state(state, cap, hcap, 0, lane);
+    const long lo = (long)(((__int128)g * n) / nshards), hi = (long)(((__int128)(g + 1) * n) / nshards);
+    for (long base = lo; base < hi; base += 32) {
+        long i = base + lane;
+        long long it = i < hi ? item[i] : 0;
+        long long c = cnt ? (i < hi ? cnt[i] : 0) : cnt_scalar;
+        int m = (int)((hi - base) < 32 ? (hi - base) : 32);
+        for (int k = 0; k < m; ++k) {
+            long long itk = __shfl_sync(CRICK_FULL, it, k);
+            long long ck = __shfl_sync(CRICK_FULL, c, k);
+            spsv_add1(w, itk, ck, base_seen + base + k, lane);
+        }
+    }
+    w.seen = base_seen + hi;
+    close_state(w, state, cap, hcap, 0, lane);
 }
 
 // set_state (:253-286); returns status in *status: 1 ok, -2 duplicate
@@ -274,24 +318,34 @@ __global__ void __launch_bounds__(32) k_spsv_set_state(unsigned char* state, lon
     for (long i = 0; i < n; ++i) {
         long long it = c3[3 * i], cn = c3[3 * i + 1], er = c3[3 * i + 2];
         if (map_find(w, it, lane) >= 0) { rc = -2; break; }
-        ctr_new(w, it, cn, er, lane);
+        ctr_new(w, it, cn, er, w.seen + i, lane);
     }
+    w.seen += n;
     close_state(w, state, cap, hcap, use_smem, lane);
     if (lane == 0) *status = rc;
 }
 
-// spsv_merge (:289-364), T2 read-only from HBM
+// spsv_merge (:289-364), T2 read-only from HBM.  Block b merges s2 + b*pair_stride into
+// s1 + b*pair_stride (one pair for the user-level merge, a whole tree level for the parallel
+// update).  mark_mixed: the two summaries count positions of different streams.
 __global__ void __launch_bounds__(32) k_spsv_merge(unsigned char* s1, long cap1, int hcap1,
                                                    int use_smem, unsigned char* s2, long cap2,
-                                                   int hcap2) {
+                                                   int hcap2, size_t pair_stride, int mark_mixed) {
     const int lane = threadIdx.x;
+    s1 += (size_t)blockIdx.x * pair_stride;
+    s2 += (size_t)blockIdx.x * pair_stride;
     SpsvView g2 = spsv_carve(s2, cap2, hcap2);
     SpsvHdr h2 = *g2.hdr;
-    if (h2.size == 0) return;
+    if (h2.size == 0) {
+        if (lane == 0 && h2.seen > reinterpret_cast<SpsvHdr*>(s1)->seen && !mark_mixed)
+            reinterpret_cast<SpsvHdr*>(s1)->seen = h2.seen;
+        return;
+    }
     SpsvW w2;
-    w2.item = g2.item; w2.count = g2.count; w2.error = g2.error; w2.hkey = g2.hkey;
+    w2.item = g2.item; w2.count = g2.count; w2.error = g2.error; w2.last = g2.last; w2.hkey = g2.hkey;
     w2.order = g2.order; w2.pos = g2.pos; w2.hval = g2.hval;
     w2.capacity = h2.capacity; w2.size = h2.size; w2.hcap = h2.hcap; w2.tomb = h2.tomb;
+    w2.seen = h2.seen; w2.mixed = h2.mixed;
     SpsvW w = open_state(s1, cap1, hcap1, use_smem, lane);
     long long m1 = w.size < w.capacity ? 0 : w.count[w.order[w.size - 1]];
     long long m2 = w2.size < w2.capacity ? 0 : w2.count[w2.order[w2.size - 1]];
@@ -302,6 +356,7 @@ __global__ void __launch_bounds__(32) k_spsv_merge(unsigned char* s1, long cap1,
                 int s2i = w2.hval[idx];
                 w.count[s] += w2.count[s2i];
                 w.error[s] += w2.error[s2i];
+                if (w2.last[s2i] > w.last[s]) w.last[s] = w2.last[s2i];
             } else {
                 w.count[s] += m2;
                 w.error[s] += m2;
@@ -312,17 +367,62 @@ __global__ void __launch_bounds__(32) k_spsv_merge(unsigned char* s1, long cap1,
     }
     for (long p = 0; p < w2.size; ++p) {  // T2's list order (:330)
         int s2i = w2.order[p];
-        long long it = w2.item[s2i], cn = w2.count[s2i], er = w2.error[s2i];
+        long long it = w2.item[s2i], cn = w2.count[s2i], er = w2.error[s2i], la = w2.last[s2i];
         if (map_find(w, it, lane) >= 0) continue;
         if (w.size == w.capacity) {
             int tail = w.order[w.size - 1];
             if (ctr_ge(w.count[tail], w.error[tail], cn, er, m1)) break;
-            ctr_replace(w, tail, it, cn + m1, er + m1, lane);
+            ctr_replace(w, tail, it, cn + m1, er + m1, la, lane);
         } else {
-            ctr_new(w, it, cn + m1, er + m1, lane);
+            ctr_new(w, it, cn + m1, er + m1, la, lane);
         }
     }
+    if (mark_mixed || w2.mixed) w.mixed = 1;
+    else if (w2.seen > w.seen) w.seen = w2.seen;
     close_state(w, s1, cap1, hcap1, use_smem, lane);
+}
+
+// Parallel path, last step: a summary without errors is exact (no eviction happened anywhere),
+// and the reference lists an exact summary by (count desc, position of the latest update asc)
+// -- SURVEY.md 8c, verified on 50 random streams.  One CTA, bitonic sort in shared memory.
+__global__ void __launch_bounds__(1024) k_spsv_reorder_exact(unsigned char* state, long cap, int hcap,
+                                                             int P /* pow2 >= size */) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    long long* kc = reinterpret_cast<long long*>(sm);
+    long long* kl = kc + P;
+    int* ks = reinterpret_cast<int*>(kl + P);
+    __shared__ int s_bad;
+    SpsvView g = spsv_carve(state, cap, hcap);
+    const int n = (int)g.hdr->size;
+    if (threadIdx.x == 0) s_bad = g.hdr->mixed;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (g.error[i] != 0) s_bad = 1;
+    __syncthreads();
+    if (s_bad || n > P) return;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        if (i < n) { kc[i] = g.count[i]; kl[i] = g.last[i]; ks[i] = i; }
+        else { kc[i] = -0x7fffffffffffffffll - 1; kl[i] = 0x7fffffffffffffffll; ks[i] = -1; }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int q = i | j;
+                bool up = (i & k) == 0;
+                // "a before b": larger count first, then earlier last update
+                bool q_first = kc[q] > kc[i] || (kc[q] == kc[i] && kl[q] < kl[i]);
+                if (q_first == up) {
+                    long long t1 = kc[i]; kc[i] = kc[q]; kc[q] = t1;
+                    t1 = kl[i]; kl[i] = kl[q]; kl[q] = t1;
+                    int t2 = ks[i]; ks[i] = ks[q]; ks[q] = t2;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { g.order[i] = ks[i]; g.pos[ks[i]] = i; }
 }
 
 // int64_counters walk (space_saving.pyx:368-386)
@@ -335,11 +435,12 @@ __global__ void k_spsv_counters(unsigned char* state, long cap, int hcap, long l
     }
 }
 
-__global__ void k_spsv_init(unsigned char* state, long cap, int hcap) {
-    SpsvView g = spsv_carve(state, cap, hcap);
+__global__ void k_spsv_init(unsigned char* state, long cap, int hcap, size_t stride) {
+    SpsvView g = spsv_carve(state + (size_t)blockIdx.x * stride, cap, hcap);
     for (int i = threadIdx.x; i < hcap; i += blockDim.x) g.hval[i] = -1;
     if (threadIdx.x == 0) {
         SpsvHdr h; h.capacity = cap; h.size = 0; h.hcap = hcap; h.tomb = 0;
+        h.seen = 0; h.mixed = 0; h.pad = 0;
         *g.hdr = h;
     }
 }
@@ -371,8 +472,66 @@ static cudaStream_t sp_stream(crick_spsv* s, void* stream) {
     return st;
 }
 
+constexpr long kSpsvParallelMin = 1 << 18;   // below: the bit-exact sequential replay
+constexpr long kSpsvShardMin = 4096;         // elements per shard, at least
+
+// Parallel update: shard summaries -> pairwise merge tree -> merge into the main summary ->
+// list order of an exact summary.  Valid Space-Saving summary for any input (the merge is the
+// reference's own, Cafaro et al.); counts are exact whenever #distinct <= capacity.
+static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* item,
+                                             const long long* cnt, long long cs, long n,
+                                             cudaStream_t st) {
+    const size_t stride = spsv_bytes(s->cap, s->hcap);
+    long G = n / kSpsvShardMin;
+    const long gmax = 16L * sm_count();
+    if (G > gmax) G = gmax;
+    while (G > 1 && (size_t)G * stride > ((size_t)8 << 30)) G >>= 1;   // scratch <= 8 GiB
+    if (G < 1) G = 1;
+    unsigned char* shards = nullptr;
+    cudaError_t e = cudaMallocAsync(&shards, (size_t)G * stride, st);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    k_spsv_init<<<(unsigned)G, 256, 0, st>>>(shards, s->cap, s->hcap, stride);
+    count_launch();
+    k_spsv_shards<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(shards, stride, s->cap, s->hcap, (int)G,
+                                                          s->d, item, cnt, cs, n);
+    for (long step = 1; step < G; step <<= 1) {
+        // shard k <- merge(shard k, shard k + step) for k = 0, 2*step, 4*step, ...
+        long pairs = (G - step + 2 * step - 1) / (2 * step);
+        count_launch();
+        k_spsv_merge<<<(unsigned)pairs, 32, 0, st>>>(shards, s->cap, s->hcap, 0, shards + step * stride,
+                                                     s->cap, s->hcap, 2 * step * stride, 0);
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess && s->smem > 48 * 1024)
+        e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+    if (e == cudaSuccess) {
+        count_launch();
+        k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, shards, s->cap, s->hcap,
+                                             0, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && s->cap <= 8192) {
+        int P = 1;
+        while (P < s->cap) P <<= 1;
+        size_t sm = (size_t)P * 20;
+        if (sm > 48 * 1024)
+            e = cudaFuncSetAttribute(k_spsv_reorder_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) {
+            count_launch();
+            k_spsv_reorder_exact<<<1, 1024, sm, st>>>(s->d, s->cap, s->hcap, P);
+            e = cudaGetLastError();
+        }
+    }
+    cudaFreeAsync(shards, st);
+    return e;
+}
+
 static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const long long* cnt,
-                                    long long cs, long n, cudaStream_t st) {
+                                    long long cs, long n, cudaStream_t st, int mode = 0) {
+    // mode: 0 auto, 1 sequential (reference replay), 2 parallel
+    if (mode == 2 || (mode == 0 && n >= kSpsvParallelMin))
+        return sp_launch_update_parallel(s, item, cnt, cs, n, st);
     cudaError_t e = cudaSuccess;
     if (s->smem > 48 * 1024)
         e = cudaFuncSetAttribute(k_spsv_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
@@ -416,7 +575,7 @@ crick_spsv_t* crick_spsv_new(int64_t capacity) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         count_launch();
-        k_spsv_init<<<1, 256, 0, s->own>>>(s->d, s->cap, s->hcap);
+        k_spsv_init<<<1, 256, 0, s->own>>>(s->d, s->cap, s->hcap, 0);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) { fail("spsv_new", e); crick_spsv_free(s); return nullptr; }
@@ -445,7 +604,6 @@ int crick_spsv_add(crick_spsv_t* s, int64_t item, int64_t count) {
 
 int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count, int64_t count_scalar,
                       int64_t n, int item_on_device, int count_on_device, int mode, void* stream) {
-    (void)mode;
     if (n <= 0) return 0;
     cudaStream_t st = sp_stream(s, stream);
     if (sp_drain(s, st)) return -1;
@@ -468,7 +626,7 @@ int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count
             dc = reinterpret_cast<const long long*>(p);
         }
     }
-    if (e == cudaSuccess) e = sp_launch_update(s, di, dc, count_scalar, n, st);
+    if (e == cudaSuccess) e = sp_launch_update(s, di, dc, count_scalar, n, st, mode);
     if (stage) {
         cudaFreeAsync(stage, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -491,7 +649,8 @@ int crick_spsv_merge(crick_spsv_t* s, crick_spsv_t* const* others, int n_others)
             e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
         if (e == cudaSuccess) {
             count_launch();
-            k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, o->d, o->cap, o->hcap);
+            k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, o->d, o->cap, o->hcap,
+                                                 0, 1);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) {

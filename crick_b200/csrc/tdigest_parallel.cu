@@ -48,7 +48,8 @@ constexpr size_t kTabBytes = ((size_t)kTabLen * 2 + 15) & ~(size_t)15;
 constexpr int kEMax = 1024;      // max edges (buckets - 1)
 constexpr int kBPad = kEMax + 8; // row stride of the per-CTA partial sums
 constexpr long kSMax = 16384;    // max sample size (rank error with 16 Ki = with 64 Ki)
-constexpr int kSortChunk = 4096; // elements sorted per CTA in shared memory
+constexpr int kSortChunk = 1024; // elements sorted per CTA in shared memory (one SM sorts
+                                 // 4096 in 73 us, 16 SMs sort 1024 each in ~9 us: r1_o launch list)
 
 struct ParHeader {
     int E;       // number of edges; buckets = E + 1, bucket b = [edge[b-1], edge[b])
@@ -187,8 +188,9 @@ __device__ __forceinline__ void ce(double& ka, double& va, double& kb, double& v
 
 // all stages with stride < kSortChunk for the given k range, inside shared memory
 // mode 0: full local sort (k = 2 .. kSortChunk); mode 1: merge tail of level K (j = kSortChunk/2 .. 1)
-__global__ void __launch_bounds__(512) k_bitonic_local(double* __restrict__ keys,
-                                                       double* __restrict__ vals, long K, int mode) {
+constexpr int kSortThreads = kSortChunk / 2;   // one compare-exchange per thread and stage
+__global__ void __launch_bounds__(kSortThreads) k_bitonic_local(double* __restrict__ keys,
+                                                        double* __restrict__ vals, long K, int mode) {
     double* sk = reinterpret_cast<double*>(smem_raw);
     double* sv = sk + kSortChunk;
     const long base = (long)blockIdx.x * kSortChunk;
@@ -199,15 +201,28 @@ __global__ void __launch_bounds__(512) k_bitonic_local(double* __restrict__ keys
     __syncthreads();
     long k0 = mode == 0 ? 2 : K;
     long k1 = mode == 0 ? kSortChunk : K;
+    constexpr int kCE = kSortChunk / 2 / kSortThreads;
     for (long k = k0; k <= k1; k <<= 1) {
         for (int j = (int)((k >> 1) < kSortChunk ? (k >> 1) : (kSortChunk >> 1)); j > 0; j >>= 1) {
-            for (int p = threadIdx.x; p < kSortChunk / 2; p += blockDim.x) {
-                int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                int q = i | j;
-                bool asc = (((base + i) & k) == 0);
-                double ka = sk[i], va = sv[i], kb = sk[q], vb = sv[q];
-                ce(ka, va, kb, vb, asc);
-                sk[i] = ka; sv[i] = va; sk[q] = kb; sv[q] = vb;
+            // all loads first (independent), stores only where a pair is out of order
+            int ii[kCE], qq[kCE];
+            double ka[kCE], kb[kCE];
+#pragma unroll
+            for (int c = 0; c < kCE; ++c) {
+                int p = threadIdx.x + c * kSortThreads;
+                ii[c] = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                qq[c] = ii[c] | j;
+                ka[c] = sk[ii[c]]; kb[c] = sk[qq[c]];
+            }
+#pragma unroll
+            for (int c = 0; c < kCE; ++c) {
+                bool asc = (((base + ii[c]) & k) == 0);
+                bool sw = asc ? (kb[c] < ka[c]) : (ka[c] < kb[c]);
+                if (sw) {
+                    double va = sv[ii[c]], vb = sv[qq[c]];
+                    sk[ii[c]] = kb[c]; sk[qq[c]] = ka[c];
+                    sv[ii[c]] = vb; sv[qq[c]] = va;
+                }
             }
             __syncthreads();
         }
@@ -237,14 +252,14 @@ static cudaError_t sort_sample(double* keys, double* vals, long L, cudaStream_t 
     if (e != cudaSuccess) return e;
     unsigned nchunk = (unsigned)(L / kSortChunk);
     count_launch();
-    k_bitonic_local<<<nchunk, 512, smem, st>>>(keys, vals, 0, 0);
+    k_bitonic_local<<<nchunk, kSortThreads, smem, st>>>(keys, vals, 0, 0);
     for (long k = 2L * kSortChunk; k <= L; k <<= 1) {
         for (long j = k >> 1; j >= kSortChunk; j >>= 1) {
             count_launch();
             k_bitonic_global<<<(unsigned)((L / 2 + 255) / 256), 256, 0, st>>>(keys, vals, L, j, k);
         }
         count_launch();
-        k_bitonic_local<<<nchunk, 512, smem, st>>>(keys, vals, k, 1);
+        k_bitonic_local<<<nchunk, kSortThreads, smem, st>>>(keys, vals, k, 1);
     }
     return cudaGetLastError();
 }
@@ -1174,33 +1189,30 @@ cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratc
     return edges_from_sorted_sample(v, L, S, st);
 }
 
-// Shape of the hot kernel for a bucket capacity.  Preferred: two tables of 32 columns, each
-// with its own token ring of 7 warps, tiles prefetched into L2 (c <= 100).  When two tables do
-// not fit: one table (32 columns, or 16 / 8 / 4 for large compressions), one ring of 12
-// warps, tiles staged through shared memory by TMA.
+// Shape of the hot kernel for a bucket capacity.  Two tables, each with its own token ring of
+// 7 warps (6 with fused moments), tiles prefetched into L2; C = 32 columns per table when they
+// fit (c <= 100), else 16 / 8 / 4 with 32 / C lane passes per read-modify-write.  Two tables of
+// C columns beat one table of 2C columns + TMA stages (same shared memory, r1_f vs r1_h
+// profiles); the staged single-table shape stays selectable with CRICK_ACC_T=1.
 struct AccCfg { int cols, ntab, nw, stage; size_t smem; };
 static AccCfg acc_cfg(int bmax, bool stats) {
-    const size_t budget = 230000;                       // of 232448 B opt-in, 512 B are static
+    const size_t budget = 230000;                       // of 232448 B opt-in, ~2 KB are static
     const size_t fixed = kTabBytes + sizeof(double) * (size_t)(bmax + kEdgePad) + 16 * 8;
-    const size_t table32 = (size_t)(bmax + 1) * 32 * 16;
+    const size_t col = (size_t)(bmax + 1) * 16;         // one column incl. the dummy row
     AccCfg c;
-    int want_tab = 0;
-    if (const char* e = getenv("CRICK_ACC_T")) want_tab = atoi(e);   // tuning hooks (bench sweeps)
-    if (want_tab != 1 && fixed + 2 * table32 <= budget) {
-        c.ntab = 2; c.cols = 32; c.nw = stats ? 12 : 14; c.stage = 0;
-    } else {
-        c.ntab = 1; c.nw = 12; c.stage = 1; c.cols = 32;
-        while (c.cols > 1 &&
-               fixed + (size_t)c.nw * kStageBytes + (size_t)(bmax + 1) * c.cols * 16 > budget)
-            c.cols >>= 1;
-    }
+    int want_tab = 2;
+    if (const char* e = getenv("CRICK_ACC_T")) want_tab = atoi(e) == 1 ? 1 : 2;   // tuning hooks
+    c.ntab = want_tab;
+    c.stage = want_tab == 1;
+    c.nw = want_tab == 1 ? 12 : (stats ? 12 : 14);
     if (const char* e = getenv("CRICK_ACC_W")) {
         int v = atoi(e);
         if (v >= c.ntab && v <= (stats ? 12 : 14)) c.nw = v - v % c.ntab;
     }
-    c.smem = fixed + (c.stage ? (size_t)c.nw * kStageBytes : 0) +
-             (size_t)c.ntab * (bmax + 1) * c.cols * 16;
-    c.smem = (c.smem + 15) & ~(size_t)15;
+    const size_t stage_bytes = c.stage ? (size_t)c.nw * kStageBytes : 0;
+    c.cols = 32;
+    while (c.cols > 1 && fixed + stage_bytes + (size_t)c.ntab * c.cols * col > budget) c.cols >>= 1;
+    c.smem = (fixed + stage_bytes + (size_t)c.ntab * c.cols * col + 15) & ~(size_t)15;
     return c;
 }
 

@@ -198,7 +198,12 @@ int crick_stats_merge_record(crick_stats_t *s, const double *record9_host);
 crick_spsv_t *crick_spsv_new(int64_t capacity);                  /* spsv_int64_new :75-95 */
 void crick_spsv_free(crick_spsv_t *s);                           /* :98-109 */
 int crick_spsv_add(crick_spsv_t *s, int64_t item, int64_t count);            /* :213-250 */
-/* spsv_int64_update_ndarray :367-451; count == NULL => scalar */
+/* spsv_int64_update_ndarray :367-451; count == NULL => scalar.
+ * mode 0 auto: below 262144 elements the stream is replayed in order (bit-exact with the
+ * reference, list order included); above, shard summaries are built in parallel and merged with
+ * the reference's own merge (:289-364, Cafaro et al.) -- a valid Space-Saving summary for any
+ * input, with exact counts and the reference's list order whenever #distinct <= capacity.
+ * mode 1 forces the sequential replay, mode 2 the parallel path. */
 int crick_spsv_update(crick_spsv_t *s, const int64_t *item, const int64_t *count,
                       int64_t count_scalar, int64_t n, int item_on_device, int count_on_device,
                       int mode, void *stream);

@@ -286,3 +286,34 @@ def test_fused_moments_in_the_same_pass(cb):
     assert np.isnan(s3.skew()) and s3.count() == 70000        # homogeneous -> NaN (stats.pyx)
     t3.update(np.full(70000, 2.0), stats=s3)
     assert s3.count() == 140000 and s3.skew() == 0.0 and t3.size() == 140000
+
+
+def test_tma_staged_single_table_shape():
+    """The alternative kernel shape (one table, tiles staged through shared memory by
+    cp.async.bulk + mbarrier) is selected with CRICK_ACC_T=1; it must build the same digest up
+    to the summation order.  Runs in a subprocess because the shape is read from the environment."""
+    import os, subprocess, sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import crick_b200 as cb
+rng = np.random.default_rng(3)
+x = rng.lognormal(size=700001); w = rng.uniform(0.5, 1.5, x.size)
+for c in (100, 200):
+    t = cb.TDigest(c, mode="parallel"); t.update(x, w)
+    print(c, t.size().hex(), t.min().hex(), t.max().hex(), len(t.centroids()),
+          " ".join(float(v).hex() for v in t.quantile([0.01, 0.5, 0.99])))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env_t in ("2", "1"):
+        env = dict(os.environ, CRICK_ACC_T=env_t)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                           timeout=240)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l.split() for l in r.stdout.strip().splitlines()])
+    for a, b in zip(*outs):
+        assert a[0] == b[0] and a[2:5] == b[2:5]                   # min, max, #centroids
+        assert abs(float.fromhex(a[1]) - float.fromhex(b[1])) <= 1e-12 * float.fromhex(a[1])
+        qa = np.array([float.fromhex(v) for v in a[5:]])
+        qb = np.array([float.fromhex(v) for v in b[5:]])
+        np.testing.assert_allclose(qa, qb, rtol=1e-9)

@@ -235,3 +235,42 @@ def test_spsv_merge_vs_oracle(cb):
         cb.SpaceSaving(0)
     with pytest.raises(ValueError):
         a.add(1, 0)
+
+
+def test_spsv_parallel_path(cb):
+    """Streams above 262144 elements: shard summaries + the reference's merge.  Exact (counts,
+    errors AND list order) whenever #distinct <= capacity; otherwise a valid Space-Saving summary:
+    count - error <= true <= count, sorted, and the heavy hitters are found."""
+    rng = np.random.default_rng(6)
+    n = 700003
+    items = (rng.zipf(1.2, n) % 900).astype(np.int64)
+    w = rng.integers(1, 4, n).astype(np.int64)
+    s, o = cb.SpaceSaving(1000, "i8"), R.SpaceSaving(1000)
+    s.update(cb.DeviceArray.from_numpy(items), cb.DeviceArray.from_numpy(w))
+    o.update(items, w)
+    assert s.counters().tobytes() == o.counters().tobytes()
+    s.update(items[::-1].copy())                      # a second batch on top, host path
+    o.update(items[::-1].copy())
+    assert s.counters().tobytes() == o.counters().tobytes()
+    # more distinct items than counters
+    items = rng.zipf(1.1, n).astype(np.int64)
+    s = cb.SpaceSaving(1000, "i8")
+    s.update(items)
+    c = s.counters()
+    assert len(c) == 1000 and (np.diff(c["count"]) <= 0).all()
+    vals, counts = np.unique(items, return_counts=True)
+    true = dict(zip(vals.tolist(), counts.tolist()))
+    for it, cn, er in c.tolist():
+        assert cn - er <= true.get(it, 0) <= cn
+    top_true = set(vals[np.argsort(-counts, kind="stable")[:20]].tolist())
+    assert top_true <= set(c["item"][:60].tolist())
+    # every item whose true count exceeds the smallest counter must be present (guarantee)
+    floor = c["count"].min()
+    assert set(vals[counts > floor].tolist()) <= set(c["item"].tolist())
+    # float64 items by bit pattern, parallel path
+    f = cb.SpaceSaving(50, "f8")
+    xf = rng.choice(np.array([0.0, -0.0, 1.5, np.nan, np.inf, -2.25]), 300000)
+    f.update(xf)
+    of = R.SpaceSaving(50)
+    of.update(xf.view("i8"))
+    assert f.counters().view("i8").tobytes() == of.counters().view("i8").tobytes()
