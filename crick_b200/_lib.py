@@ -68,6 +68,7 @@ _SIG = {
     "crick_tdigest_record_doubles": (c_int, [_P]),
     "crick_tdigest_export_record": (c_int, [_P, _P, _P]),
     "crick_tdigest_merge_records": (c_int, [_P, _P, c_int, c_int, _P]),
+    "crick_tdigest_merge_records_bulk": (c_int, [_P, _P, c_int, _P]),
     # grouped
     "crick_tdigest_group_new": (_P, [c_double, c_int64]),
     "crick_tdigest_group_free": (None, [_P]),

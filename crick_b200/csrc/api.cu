@@ -552,6 +552,22 @@ int crick_tdigest_merge_records(crick_tdigest_t* t, const double* records_dev, i
     return e == cudaSuccess ? 0 : fail("merge_records", e);
 }
 
+int crick_tdigest_merge_records_bulk(crick_tdigest_t* t, const double* records_dev, int n_records,
+                                     void* stream) {
+    cudaStream_t st = td_stream(t, stream);
+    if (td_drain(t, st)) return -1;
+    t->mirror_ok = false;
+    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    if (e == cudaSuccess) {
+        e = launch_merge_records_bulk(t->s.v, 0, records_dev, n_records, st);
+        if (e == cudaErrorInvalidValue) {   // union too large for one CTA: sequential merge
+            cudaGetLastError();
+            e = launch_merge_records(t->s.v, 0, records_dev, n_records, -1, st);
+        }
+    }
+    return e == cudaSuccess ? 0 : fail("merge_records_bulk", e);
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------

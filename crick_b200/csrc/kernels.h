@@ -25,6 +25,10 @@ cudaError_t launch_init_hdr(DevHdr* hdr, long n, cudaStream_t st);
 cudaError_t launch_pack_record(const BatchView& v, long d, double* rec, cudaStream_t st);
 cudaError_t launch_merge_records(const BatchView& v, long d, const double* recs, int nrec, int skip,
                                  cudaStream_t st);
+// all records in one greedy pass over the sorted union (tdigest_parallel.cu);
+// cudaErrorInvalidValue = does not fit, use launch_merge_records
+cudaError_t launch_merge_records_bulk(const BatchView& v, long d, const double* recs, int nrec,
+                                      cudaStream_t st);
 cudaError_t launch_copy_digest(const BatchView& dv, long dd, const BatchView& sv, long sd,
                                cudaStream_t st);
 cudaError_t launch_group_meta(const BatchView& v, long ng, double* out, cudaStream_t st);

@@ -1144,6 +1144,124 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
     }
 }
 
+// 6. bulk merge of gathered records (multi-GPU tail) -----------------------------------------
+// All centroids of the records are sorted by mean (ties: record order) and go through ONE
+// greedy k-scale pass -- the digest the reference would build had it been handed the union in a
+// single flush.  tdigest_merge's own semantics (through the 42-slot buffer, 23 flushes for 8
+// records) are k_merge_records in tdigest_kernels.cu; this one is 5x shorter on the critical
+// path of every multi-GPU step.  One CTA; P = power of two >= total centroid count.
+__global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d,
+                                                             const double* __restrict__ recs,
+                                                             int nrec, int rec_doubles, int P) {
+    __shared__ int s_off[64 + 1];
+    __shared__ double s_tot, s_mn, s_mx;
+    const int tid = threadIdx.x;
+    const int cap = v.cap;
+    // carve: key[P] | wgt[P] | ord[P] (sort arrays) then cen[cap] | sb[P] | items[cap+P] | kend | start
+    double* key = reinterpret_cast<double*>(smem_raw);
+    double* wgt = key + P;
+    int* ord = reinterpret_cast<int*>(wgt + P);
+    unsigned char* wsbase = reinterpret_cast<unsigned char*>(ord + P);
+    wsbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wsbase) + 15) & ~(uintptr_t)15);
+    WarpWS ws;
+    {
+        size_t t = (size_t)cap + P;
+        ws.cen = reinterpret_cast<double2*>(wsbase);
+        ws.sb = ws.cen + cap;
+        ws.buf = ws.sb;
+        ws.items = ws.sb + P;
+        ws.kend = reinterpret_cast<double*>(ws.items + t);
+        ws.start = reinterpret_cast<int*>(ws.kend + t);
+    }
+    if (tid == 0) {
+        int run = 0;
+        double tot = 0.0, mn = INFINITY, mx = -INFINITY;
+        for (int r = 0; r < nrec; ++r) {
+            const double* rec = recs + (size_t)r * rec_doubles;
+            s_off[r] = run;
+            if (rec[1] != 0.0) {                 // empty digests are skipped (:596)
+                run += (int)rec[0];
+                tot = __dadd_rn(tot, rec[1]);
+                mn = fmin(mn, rec[2]); mx = fmax(mx, rec[3]);
+            }
+        }
+        s_off[nrec] = run;
+        s_tot = tot; s_mn = mn; s_mx = mx;
+    }
+    __syncthreads();
+    const int m = s_off[nrec];
+    for (int i = tid; i < P; i += blockDim.x) { key[i] = INFINITY; wgt[i] = 0.0; ord[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int r = 0; r < nrec; ++r) {
+        const double* rec = recs + (size_t)r * rec_doubles;
+        const int n = s_off[r + 1] - s_off[r];
+        for (int i = tid; i < n; i += blockDim.x) {
+            key[s_off[r] + i] = rec[4 + 2 * i];
+            wgt[s_off[r] + i] = rec[5 + 2 * i];
+            ord[s_off[r] + i] = s_off[r] + i;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P / 2; t += blockDim.x) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int q = i | j;
+                bool up = (i & k) == 0;
+                bool q_first = key[q] < key[i] || (key[q] == key[i] && ord[q] < ord[i]);
+                if (q_first == up) {
+                    double t1 = key[i]; key[i] = key[q]; key[q] = t1;
+                    t1 = wgt[i]; wgt[i] = wgt[q]; wgt[q] = t1;
+                    int t2 = ord[i]; ord[i] = ord[q]; ord[q] = t2;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < m; i += blockDim.x) ws.sb[i] = make_double2(key[i], wgt[i]);
+    __syncthreads();
+    if (tid < 32 && m > 0) {
+        const int lane = tid;
+        Hdr h;
+        const DevHdr dh = v.hdr[d];
+        h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
+        const double2* cg = v.cen + d * (long)cap;
+        for (int i = lane; i < h.n; i += 32) ws.cen[i] = cg[i];
+        __syncwarp();
+        if (h.vmin > s_mn) h.vmin = s_mn;
+        if (h.vmax < s_mx) h.vmax = s_mx;
+        h.total = __dadd_rn(h.total, s_tot);
+        warp_merge_sorted(ws, v.comp, h, m, cap, lane);
+        double2* cgo = v.cen + d * (long)cap;
+        for (int i = lane; i < h.n; i += 32) cgo[i] = ws.cen[i];
+        if (lane == 0) {
+            DevHdr o = dh;
+            o.vmin = h.vmin; o.vmax = h.vmax; o.total = h.total; o.btotal = 0.0;
+            o.n = h.n; o.bn = 0;
+            v.hdr[d] = o;
+        }
+    }
+}
+
+// returns cudaErrorInvalidValue when the union does not fit one CTA's shared memory (the
+// caller then uses the sequential k_merge_records)
+cudaError_t launch_merge_records_bulk(const BatchView& v, long d, const double* recs, int nrec,
+                                      cudaStream_t st) {
+    if (nrec <= 0) return cudaSuccess;
+    if (nrec > 64) return cudaErrorInvalidValue;
+    int P = 1;
+    while (P < nrec * v.cap) P <<= 1;
+    size_t t = (size_t)v.cap + P;
+    size_t smem = (size_t)P * 20 + 16 + (size_t)v.cap * 16 + (size_t)P * 16 + t * 16 + t * 8 + (t + 1) * 4 + 16;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_merge_records_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    k_merge_records_bulk<<<1, 1024, smem, st>>>(v, d, recs, nrec, 4 + 2 * v.cap, P);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 long parallel_sample_pos(long i, long n, long S) {
     long seg = n / S;

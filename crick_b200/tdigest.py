@@ -469,10 +469,16 @@ class TDigest:
         """Flush and write the fixed-size record (4 + 2*size doubles) at `device_ptr`."""
         check(lib.crick_tdigest_export_record(self._h, device_ptr, stream), "export_record")
 
-    def merge_records(self, device_ptr, n_records, skip=-1, stream=None):
-        """``self.merge(*records)`` in record order for records gathered on the device."""
-        check(lib.crick_tdigest_merge_records(self._h, device_ptr, n_records, skip, stream),
-              "merge_records")
+    def merge_records(self, device_ptr, n_records, skip=-1, stream=None, bulk=False):
+        """``self.merge(*records)`` in record order for records gathered on the device.
+        ``bulk=True``: one greedy pass over the sorted union of all centroids instead of the
+        reference's incremental merge (faster, not bit-identical with ``merge``)."""
+        if bulk:
+            check(lib.crick_tdigest_merge_records_bulk(self._h, device_ptr, n_records, stream),
+                  "merge_records")
+        else:
+            check(lib.crick_tdigest_merge_records(self._h, device_ptr, n_records, skip, stream),
+                  "merge_records")
 
     def _debug_edges(self):
         buf = np.empty(2048, dtype=np.float64)

@@ -144,6 +144,13 @@ int crick_tdigest_export_record(crick_tdigest_t *t, double *record_dev, void *st
 int crick_tdigest_merge_records(crick_tdigest_t *t, const double *records_dev, int n_records,
                                 int skip, void *stream);
 
+/* The same records merged in ONE greedy k-scale pass over the sorted union of their centroids
+ * (what a single tdigest_flush of the union would build) instead of tdigest_merge's incremental
+ * walk through the buffer: not bit-identical with merge(*others), same accuracy class, ~5x
+ * shorter on the critical path of a multi-GPU step. */
+int crick_tdigest_merge_records_bulk(crick_tdigest_t *t, const double *records_dev, int n_records,
+                                     void *stream);
+
 /* ---- grouped digests: many independent digests, one warp each ------------
  * (the added entry point; semantics per group are exactly
  *  `t = TDigest(c); t.update(values_g, weights_g)` in reference-compatible mode) */

@@ -317,3 +317,51 @@ for c in (100, 200):
         qa = np.array([float.fromhex(v) for v in a[5:]])
         qb = np.array([float.fromhex(v) for v in b[5:]])
         np.testing.assert_allclose(qa, qb, rtol=1e-9)
+
+
+def test_bulk_merge_of_gathered_records(cb):
+    """The multi-GPU tail on one GPU: 8 shard digests -> 8 records -> merged (a) with the
+    reference's incremental tdigest_merge and (b) in one greedy pass over the sorted union.
+    Both must keep size/min/max exactly and sit in the same rank-error class as 8 reference
+    digests merged in rank order."""
+    rng = np.random.default_rng(1234)
+    n = 4 * 10**6
+    x = rng.lognormal(0, 1, n)
+    w = rng.uniform(0.5, 1.5, n)
+    rank = weighted_rank_fn(x, w)
+    parts, refs = [], []
+    nd = cb.TDigest(100).record_doubles()
+    recs = cb.DeviceArray((8, nd))
+    for k in range(8):
+        sl = slice(k * n // 8, (k + 1) * n // 8)
+        p = cb.TDigest(100, mode="parallel")
+        p.update(x[sl], w[sl])
+        p.export_record(recs.ptr + 8 * nd * k)
+        parts.append(p)
+        r = R.TDigest(100)
+        r.update(x[sl], w[sl])
+        refs.append(r)
+    from crick_b200._lib import lib
+    lib.crick_device_synchronize()
+    exact, bulk = cb.TDigest(100), cb.TDigest(100)
+    exact.merge_records(recs.ptr, 8)
+    bulk.merge_records(recs.ptr, 8, bulk=True)
+    via_merge = cb.TDigest(100)
+    via_merge.merge(*parts)
+    assert exact.centroids().tobytes() == via_merge.centroids().tobytes()
+    mr = R.TDigest(100)
+    mr.merge(*refs)
+    e_ref = np.abs(rank(mr.quantile(QS9)) - QS9).max()
+    for t in (exact, bulk):
+        assert t.min() == x.min() and t.max() == x.max()
+        assert abs(t.size() - w.sum()) <= 1e-12 * w.sum()
+        c = t.centroids()
+        assert (np.diff(c["mean"]) >= 0).all() and abs(c["weight"].sum() - w.sum()) <= 1e-9 * w.sum()
+        err = np.abs(rank(t.quantile(QS9)) - QS9).max()
+        assert err <= max(2 * e_ref, 1e-3), (err, e_ref)
+    e_bulk = np.abs(rank(bulk.quantile(QS9)) - QS9).max()
+    e_exact = np.abs(rank(exact.quantile(QS9)) - QS9).max()
+    assert e_bulk <= max(1.5 * e_exact, 5e-4), (e_bulk, e_exact)
+    # a second bulk merge accumulates on top of the first
+    bulk.merge_records(recs.ptr, 8, bulk=True)
+    assert abs(bulk.size() - 2 * w.sum()) <= 1e-12 * w.sum()
