@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrick_cuda.so")
+# CRICK_CUDA_LIB: another build of the same library (A/B kernel experiments on one box)
+LIB_PATH = os.environ.get("CRICK_CUDA_LIB") or os.path.join(_HERE, "libcrick_cuda.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
