@@ -562,8 +562,8 @@ struct Lookup {
 // (w, w*x) to add, equal buckets folded.  Returns true if some value may be the min / max.
 template <bool HAS_W, int GRID, bool FAST>
 __device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs, const double* ws,
-                                               double wsc, unsigned valid_mask, unsigned* addr,
-                                               double* ww, double* ss, bool& badw) {
+                                               double wsc, unsigned* addr, double* ww, double* ss,
+                                               bool& badw) {
     int b[kU];
     unsigned ea[kU];
 #pragma unroll
@@ -606,11 +606,15 @@ __device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs
     for (int u = 0; u < kU; ++u) {
         const double w = HAS_W ? ws[u] : wsc;
         // tdigest_add's filter (:285): finite x, and not (w <= eps)
+        // tdigest_add's filter (:285) is "finite x and not (w <= eps)".  Here a weight passes
+        // when eps < w <= DBL_MAX; anything else is dropped and, unless it is one of the legal
+        // tiny weights 0 < w <= eps, reported (the wrapper's check, tdigest.pyx:304-305) -- the
+        // exact test runs only in the rare warp-steps that saw such a weight.  Padding lanes
+        // of the last tile carry x = NaN, w = 1.
         const bool finite = fabs(xs[u]) <= DBL_MAX;
-        const bool valid = (valid_mask >> u) & 1u;
-        const bool ok = finite && !(w <= DBL_EPSILON) && valid;
-        // the wrapper's check of w (tdigest.pyx:304-305), done here instead of on the host
-        if (HAS_W) badw |= valid && !(w > 0.0 && w <= DBL_MAX);
+        const bool wok = !HAS_W || (w > DBL_EPSILON && w <= DBL_MAX);
+        const bool ok = finite && wok;
+        if (HAS_W) badw |= !wok;
         ext |= ok && ((unsigned)b[u] - L.ext_lo >= L.ext_span);
         // rejected values go to the dummy row (never read back), whatever their w / w*x --
         // but w*x must stay finite: fold_if_equal multiplies it by 0 (a NaN or infinite x
@@ -636,17 +640,24 @@ __device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs
 // nextafter of one), so this runs for ~1 warp-step in 100
 template <bool HAS_W>
 __device__ __forceinline__ void minmax_group(const Lookup& L, const double* xs, const double* ws,
-                                          double wsc, unsigned valid_mask, double& vmin,
-                                          double& vmax) {
+                                             double wsc, double& vmin, double& vmax) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
         const double w = HAS_W ? ws[u] : wsc;
-        const bool ok = (fabs(xs[u]) <= DBL_MAX) && !(w <= DBL_EPSILON) && ((valid_mask >> u) & 1u);
+        const bool ok = (fabs(xs[u]) <= DBL_MAX) && (!HAS_W || (w > DBL_EPSILON && w <= DBL_MAX));
         if (ok) {
             vmin = xs[u] < vmin ? xs[u] : vmin;
             vmax = xs[u] > vmax ? xs[u] : vmax;
         }
     }
+}
+
+// rare path: some weight of the tile is not in (eps, DBL_MAX]; is any of them illegal?
+__device__ __forceinline__ bool any_illegal_weight(const double* ws) {
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 2 * kU; ++k) bad |= !(ws[k] > 0.0 && ws[k] <= DBL_MAX);
+    return bad;
 }
 
 // read-modify-write of N accumulators with pairwise distinct addresses (or the dummy row):
@@ -710,8 +721,8 @@ __device__ __forceinline__ unsigned load_partial(const double* __restrict__ X,
     for (int k = 0; k < 2 * kU; ++k) {
         long i = base + (k >> 1) * 64 + 2 * lane + (k & 1);
         bool in = i < n;
-        xs[k] = in ? X[i] : 0.0;
-        if (HAS_W) ws[k] = in ? W[i] : 0.0;
+        xs[k] = in ? X[i] : __longlong_as_double(0x7ff8000000000000ll);   // NaN: dropped
+        if (HAS_W) ws[k] = in ? W[i] : 1.0;
         m |= in ? (1u << k) : 0u;
     }
     return m;
@@ -842,14 +853,15 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
                                     idx_base + t * kTile + (k >> 1) * 64 + 2 * lane + (k & 1));
         }
         if (have) {
-            bool e0 = classify_group<HAS_W, GRID, FAST>(L, xs, ws, wsc, m & 0xfu, addr, ww, ss,
-                                                        badw);
-            bool e1 = classify_group<HAS_W, GRID, FAST>(L, xs + kU, ws + kU, wsc, m >> kU,
-                                                        addr + kU, ww + kU, ss + kU, badw);
+            bool susp = false;
+            bool e0 = classify_group<HAS_W, GRID, FAST>(L, xs, ws, wsc, addr, ww, ss, susp);
+            bool e1 = classify_group<HAS_W, GRID, FAST>(L, xs + kU, ws + kU, wsc, addr + kU,
+                                                        ww + kU, ss + kU, susp);
             if (__any_sync(CRICK_FULL, e0 || e1)) {
-                minmax_group<HAS_W>(L, xs, ws, wsc, m & 0xfu, vmin, vmax);
-                minmax_group<HAS_W>(L, xs + kU, ws + kU, wsc, m >> kU, vmin, vmax);
+                minmax_group<HAS_W>(L, xs, ws, wsc, vmin, vmax);
+                minmax_group<HAS_W>(L, xs + kU, ws + kU, wsc, vmin, vmax);
             }
+            if (HAS_W && __any_sync(CRICK_FULL, susp)) badw |= susp && any_illegal_weight(ws);
         }
         if (!STAGE && tn < nfull) {
             load_tile<HAS_W, VEC>(X, W, tn * kTile, lane, xs, ws);
