@@ -365,3 +365,54 @@ def test_bulk_merge_of_gathered_records(cb):
     # a second bulk merge accumulates on top of the first
     bulk.merge_records(recs.ptr, 8, bulk=True)
     assert abs(bulk.size() - 2 * w.sum()) <= 1e-12 * w.sum()
+
+
+@pytest.mark.parametrize("case", ["all_nan", "constant", "two_values", "outlier", "tiny_weights_only",
+                                  "int_input", "strided_2d", "sorted", "denormals"])
+def test_degenerate_and_awkward_inputs(cb, case):
+    rng = np.random.default_rng(99)
+    n = 150000
+    w = 1.0
+    if case == "all_nan":
+        x = np.full(n, np.nan)
+    elif case == "constant":
+        x = np.full(n, 3.25)
+    elif case == "two_values":
+        x = rng.choice([1.0, 2.0], n, p=[0.999, 0.001])
+    elif case == "outlier":
+        x = rng.normal(0, 1e-9, n)
+        x[n // 2] = 1e300
+        x[n // 3] = -1e300
+    elif case == "tiny_weights_only":
+        x, w = rng.normal(size=n), np.full(n, 1e-300)
+    elif case == "int_input":
+        x = rng.integers(-1000, 1000, n)
+    elif case == "strided_2d":
+        x = rng.normal(size=(300, 1000))[:, ::2].T          # non-contiguous: K-order flattening
+    elif case == "sorted":
+        x = np.sort(rng.lognormal(size=n))
+    else:
+        x = rng.uniform(0, 1, n) * 1e-310
+    t = cb.TDigest(100, mode="parallel")
+    t.update(x, w)
+    xa, wa = accepted(np.asarray(x, dtype=np.float64).ravel(), w)
+    if xa.size == 0:
+        assert t.size() == 0 and len(t.centroids()) == 0 and np.isnan(t.min())
+        t.update(rng.normal(size=n))                         # still usable afterwards
+        assert t.size() == n
+        return
+    assert t.size() == pytest.approx(wa.sum(), rel=1e-12)
+    assert t.min() == xa.min() and t.max() == xa.max()
+    c = t.centroids()
+    assert (np.diff(c["mean"]) >= 0).all() and (c["weight"] > 0).all()
+    rank = weighted_rank_fn(xa, wa)
+    qs = np.array([0.01, 0.25, 0.5, 0.75, 0.99])
+    est = t.quantile(qs)
+    assert (np.diff(est) >= 0).all()
+    # rank error at the caps of the reference's own tests (test_tdigest.py:102), ties aside
+    if case not in ("constant", "two_values", "int_input"):
+        assert np.abs(rank(est) - qs).max() <= 0.012
+    else:
+        lo = np.searchsorted(np.sort(xa), est, side="left") / xa.size
+        hi = np.searchsorted(np.sort(xa), est, side="right") / xa.size
+        assert ((lo - 0.012 <= qs) & (qs <= hi + 0.012)).all()
