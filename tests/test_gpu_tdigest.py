@@ -397,3 +397,35 @@ def test_allgather_reducer_world1_nccl(cb):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_pickles_of_the_reference_load_and_round_trip(cb, golden):
+    """sketches move between stock crick and this build.  The golden pickles
+    were written by the reference itself (tests/golden/make_golden.py); they name
+    crick.tdigest.TDigest / crick.stats.SummaryStats / crick.space_saving.SpaceSaving, which the
+    `crick/` shim resolves to our classes.  Loading must give the reference's state, and
+    re-pickling at the same protocol must give the reference's bytes."""
+    import crick  # the shim package at the repository root
+    g, _ = golden
+    i = np.arange(10000)
+    x = ((i * 7919) % 10007) / 10007.0
+    t = pickle.loads(bytes.fromhex(g["pickle_tdigest"]))
+    assert type(t) is cb.TDigest and type(t) is crick.TDigest
+    o = R.TDigest(100)
+    o.update(x)
+    same(t, o)
+    assert pickle.dumps(t, protocol=2) == bytes.fromhex(g["pickle_tdigest"])
+    t.update(x[:100])                                   # a restored digest keeps working
+    o.update(x[:100])
+    same(t, o)
+    s = pickle.loads(bytes.fromhex(g["pickle_stats"]))
+    so = R.SummaryStats()
+    so.update(x)
+    assert type(s) is cb.SummaryStats and s.__getstate__() == so.__getstate__()
+    assert pickle.dumps(s, protocol=2) == bytes.fromhex(g["pickle_stats"])
+    for key, items in (("pickle_spsv_i8", [1, 1, 2, 3, 3, 3]), ("pickle_spsv_f8", [1.5, 1.5, 2.0])):
+        sp = pickle.loads(bytes.fromhex(g[key]))
+        ref = cb.SpaceSaving(5, key[-2:])
+        ref.update(items)
+        assert type(sp) is cb.SpaceSaving and sp.counters().tobytes() == ref.counters().tobytes()
+        assert pickle.dumps(sp, protocol=2) == bytes.fromhex(g[key])
