@@ -100,14 +100,23 @@ class TDigest:
         return (lib.crick_tdigest_total_weight(self._h)
                 + lib.crick_tdigest_buffer_total_weight(self._h))
 
-    def _query(self, x, fn, name):
+    def _query(self, x, fn, name, out=None):
         dv = device_view(x)
         if dv is not None:
             if dv.dtype != np.float64:
                 raise TypeError("%s must be float64 when given as a CUDA array" % name)
-            out = DeviceArray(dv.shape, "f8")
-            check(fn(self._h, dv.ptr, out.ptr, dv.size, 1, None), name)
+            if out is None:
+                out = DeviceArray(dv.shape, "f8")
+                optr = out.ptr
+            else:  # caller-provided CUDA output (no allocation on the query path)
+                ov = device_view(out)
+                if ov is None or ov.dtype != np.float64 or ov.size != dv.size:
+                    raise TypeError("out must be a float64 CUDA array with as many elements as %s" % name)
+                optr = ov.ptr
+            check(fn(self._h, dv.ptr, optr, dv.size, 1, None), name)
             return out
+        if out is not None:
+            raise TypeError("out= is only supported with CUDA array inputs")
         x = np.asarray(x)
         if not np.can_cast(x.dtype, "f8", casting="safe"):  # tdigest.pyx:135,156
             raise TypeError("%s must be numeric" % name)
@@ -122,7 +131,7 @@ class TDigest:
             return np.float64(out)
         return out
 
-    def cdf(self, x):
+    def cdf(self, x, out=None):
         """cdf(self, x)
 
         Compute an estimate of the fraction of all points added to this digest
@@ -132,9 +141,9 @@ class TDigest:
         ----------
         x : array_like or float (NumPy-compatible or CUDA array)
         """  # tdigest.pyx:124-142
-        return self._query(x, lib.crick_tdigest_cdf, "x")
+        return self._query(x, lib.crick_tdigest_cdf, "x", out)
 
-    def quantile(self, q):
+    def quantile(self, q, out=None):
         """quantile(self, q)
 
         Compute an estimate of the qth percentile of the data added to
@@ -145,7 +154,7 @@ class TDigest:
         q : array_like or float
             A number between 0 and 1 inclusive.
         """  # tdigest.pyx:144-163
-        return self._query(q, lib.crick_tdigest_quantile, "q")
+        return self._query(q, lib.crick_tdigest_quantile, "q", out)
 
     def histogram(self, bins=10, range=None):
         """histogram(self, bins=10, range=None)

@@ -67,7 +67,8 @@ def config4(nd=65536, per=2000, nq=10**7):
     m = out["m"]
     rng = np.random.default_rng(3)
     q = cb.DeviceArray.from_numpy(rng.uniform(0, 1, nq)); x = cb.DeviceArray.from_numpy(rng.normal(size=nq))
-    tq = timed(lambda: m.quantile(q)); tc = timed(lambda: m.cdf(x))
+    oq = cb.DeviceArray((nq,))
+    tq = timed(lambda: m.quantile(q, out=oq)); tc = timed(lambda: m.cdf(x, out=oq))
     # reference: 2048 digests merged by the same pairwise tree, queries on 1e6
     sub = d.to_numpy()[:2048]
     ds = []
