@@ -7,28 +7,31 @@
 // dependent flushes.  A centroid, however, is only (sum w, sum w*x) over a
 // contiguous quantile range, and both sums are order independent.  So:
 //
-//   1. k_sample        strided+hashed sample of S (x, w) pairs            (reads S*16 B)
-//   2. k_bitonic_*     sort the sample by x (S = 16 Ki or 64 Ki)
+//   1. k_sample        strided+hashed sample of S = 16 Ki (x, w) pairs      (reads S*16 B)
+//   2. k_bitonic_*     sort the sample by x (1024-element chunks on 16 SMs + global steps)
 //   3. k_make_edges    weighted sample quantiles at the k-scale grid
-//                      q_j = sin^2(pi*j/(2*ov*c)), j = 1..ov*c-1  (ov sub-buckets
+//                      q_j = sin^2(pi*j/(2*ov*c)), j = 1..ov*c-1  (ov = 2 sub-buckets
 //                      per unit of k, so NO asin per element), heavy duplicates get a
-//                      bucket of their own [v, nextafter(v)); plus a 4096-cell lookup
-//                      table over the order-preserving bit pattern of x
+//                      bucket of their own [v, nextafter(v)); plus an 8192-cell uint16 lookup
+//                      table over x (linear) or over the order-preserving bit pattern of x
 //   4. k_bin_accumulate  THE HOT KERNEL: every value is read exactly once from HBM
-//                      (128-bit streaming loads), filtered like tdigest_add (:285),
-//                      mapped to its bucket (one table probe + 0-2 edge compares) and
-//                      accumulated into warp-private (sum w, sum w*x) arrays in shared
-//                      memory -- no atomics: lanes of a warp that hit the same bucket
-//                      are serialised with __match_any_sync.
+//                      (128-bit streaming loads, next tile prefetched into L2 or staged by
+//                      TMA), filtered like tdigest_add (:285), mapped to its bucket (one
+//                      table probe + 1-2 predicated edge compares) and accumulated into
+//                      column-private (sum w, sum w*x) tables in shared memory -- no atomics,
+//                      no MATCH: lane = column, and the warps sharing a table take turns
+//                      through a token ring over named barriers.  Optionally the
+//                      SummaryStats moments of x and the check of w ride in the same pass.
 //   5. k_finalize      bucket sums -> <= ov*c weighted points in sorted order, which are
 //                      merged into the digest with the reference's own greedy k-scale
 //                      merge (warp_merge_sorted == tdigest_flush phases 2-5).
+//   6. k_merge_records_bulk  multi-GPU tail: gathered records merged in one greedy pass.
 //
 // Result: the digest the reference would produce had it been handed the
 // pre-aggregated bucket points in one flush.  Bit parity with the sequential
 // reference is impossible by construction (different clustering); parity here
 // is (a) bucket sums vs a CPU restatement of the same partition at 1e-12 and
-// (b) rank error <= the reference's on the same data (tests/test_parallel.py).
+// (b) rank error <= the reference's on the same data (tests/test_gpu_parallel.py).
 #include "kernels.h"
 #include "stats_dev.cuh"
 #include "tdigest_ref.cuh"
