@@ -237,7 +237,8 @@ class TDigest:
         owner = self
 
         class _View:
-            __cuda_array_interface__ = {"shape": (n, 2), "typestr": "<f8", "data": (ptr, True),
+            # (exported writable: PyTorch rejects read-only CUDA arrays; treat it as read-only)
+            __cuda_array_interface__ = {"shape": (n, 2), "typestr": "<f8", "data": (ptr, False),
                                         "version": 3, "strides": None}
             _keep = owner
         return _View()

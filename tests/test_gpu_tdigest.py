@@ -429,3 +429,43 @@ def test_pickles_of_the_reference_load_and_round_trip(cb, golden):
         ref.update(items)
         assert type(sp) is cb.SpaceSaving and sp.counters().tobytes() == ref.counters().tobytes()
         assert pickle.dumps(sp, protocol=2) == bytes.fromhex(g[key])
+
+
+def test_dlpack_only_inputs_and_zero_copy_centroids(cb):
+    """CUDA arrays may arrive as DLPack producers without __cuda_array_interface__, and
+    centroids_device() exposes the live centroid table without a copy."""
+    import torch
+    rng = np.random.default_rng(31)
+    x = rng.normal(size=100000)
+
+    class DLPackOnly:
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    tx = torch.from_numpy(x).cuda()
+    a, b = cb.TDigest(mode="reference"), R.TDigest()
+    a.update(DLPackOnly(tx))
+    b.update(x)
+    same(a, b)
+    q = torch.tensor([0.1, 0.5, 0.9], dtype=torch.float64, device="cuda")
+    got = a.quantile(DLPackOnly(q)).to_numpy()
+    assert got.tobytes() == b.quantile([0.1, 0.5, 0.9]).tobytes()
+    with pytest.raises(TypeError):
+        a.update(DLPackOnly(tx.float()))                  # float32 CUDA arrays are not accepted
+    with pytest.raises(ValueError):
+        a.update(DLPackOnly(torch.from_numpy(x.reshape(100, 1000)).cuda()[:, ::2]))   # strided
+    view = a.centroids_device()
+    cen = torch.as_tensor(view, device="cuda").cpu().numpy()
+    c = a.centroids()
+    assert cen.shape == (len(c), 2)
+    assert np.array_equal(cen[:, 0], c["mean"]) and np.array_equal(cen[:, 1], c["weight"])
+    # CPU-side DLPack producers are not device arrays: they take the NumPy path
+    a2 = cb.TDigest(mode="reference")
+    a2.update(torch.from_numpy(x))
+    same(a2, b)
