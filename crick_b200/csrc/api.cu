@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 namespace crick {
 
@@ -205,8 +207,24 @@ int crick_synth_fill(double* x, double* w, int64_t n, uint64_t seed, int64_t off
 }
 
 // ---- TDigest ---------------------------------------------------------------
+// keep up to 2 GiB of freed staging memory in the device's default pool instead of returning
+// it to the driver at every synchronisation (cudaMallocAsync is then a pointer bump)
+static void tune_mempool_once() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = 2ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    });
+}
+
 crick_tdigest_t* crick_tdigest_new(double compression) {
     if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
+    tune_mempool_once();
     crick_tdigest* t = new (std::nothrow) crick_tdigest();
     if (!t) return nullptr;
     if (store_alloc(t->s, compression, 1)) { delete t; return nullptr; }
@@ -237,6 +255,60 @@ int crick_tdigest_add(crick_tdigest_t* t, double x, double w) {
 
 // host-resident input, parallel mode: same sample positions as the device sampler, then
 // double-buffered chunks (copy of chunk k+1 overlaps the accumulate of chunk k)
+// ---- pageable host input ------------------------------------------------------------------
+// cudaMemcpyAsync from ordinary (pageable) memory is staged by the driver on one thread at
+// ~11 GB/s (scripts/pageable_probe.py) -- a fifth of what the link moves from pinned memory.
+// NumPy arrays are pageable, so the library stages them itself: a few host threads copy each
+// chunk into one of three cached pinned slots while the previous slots are in flight to the GPU.
+constexpr int64_t kStageChunk = 1 << 22;   // values per slot and array (32 MiB)
+constexpr int kStageSlots = 3;
+struct StagePool {
+    std::mutex mu;
+    double* slot[kStageSlots] = {nullptr, nullptr, nullptr};   // each: x chunk | w chunk
+    bool busy = false;
+};
+static StagePool g_stage;
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static void parallel_memcpy(double* dst, const double* src, int64_t n, int nthreads) {
+    if (nthreads <= 1 || n < (1 << 16)) { memcpy(dst, src, (size_t)n * sizeof(double)); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + nthreads - 1) / nthreads;
+    for (int k = 0; k < nthreads; ++k) {
+        const int64_t lo = k * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        th.emplace_back([=] { memcpy(dst + lo, src + lo, (size_t)(hi - lo) * sizeof(double)); });
+    }
+    for (auto& t : th) t.join();
+}
+
+// takes the process-wide staging slots (allocated on first use); false = in use by another
+// thread or out of pinned memory: the caller falls back to the driver's pageable copy
+static bool stage_acquire() {
+    std::lock_guard<std::mutex> lk(g_stage.mu);
+    if (g_stage.busy) return false;
+    for (int i = 0; i < kStageSlots; ++i) {
+        if (!g_stage.slot[i] &&
+            cudaHostAlloc(reinterpret_cast<void**>(&g_stage.slot[i]),
+                          (size_t)kStageChunk * 2 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            g_stage.slot[i] = nullptr;
+            return false;
+        }
+    }
+    g_stage.busy = true;
+    return true;
+}
+static void stage_release() {
+    std::lock_guard<std::mutex> lk(g_stage.mu);
+    g_stage.busy = false;
+}
+
 static int td_update_host_parallel(crick_tdigest* t, const double* x, const double* w, double wsc,
                                    int64_t n, cudaStream_t st, int* bad_weights,
                                    crick_stats* stats) {
@@ -261,32 +333,50 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     StatsPart* sparts = nullptr;
     int snparts = 0;
     if (stats && stats_fused_begin(stats, st, &sparts, &snparts)) return -1;
-    const int64_t chunk = 1 << 24;  // 16 Mi values: 128 MiB per array per buffer
-    const int nbuf = 2;
-    double* dbuf[2] = {nullptr, nullptr};
+    // pinned (or registered) input goes to the GPU straight from the caller's memory in 16 Mi
+    // chunks; pageable input through the staging slots in 4 Mi chunks
+    const bool staged = (is_pageable(x) || (w && is_pageable(w))) && stage_acquire();
+    const int64_t chunk = staged ? kStageChunk : (int64_t)1 << 24;
+    const int nbuf = staged ? kStageSlots : 2;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+    double* dbuf[kStageSlots] = {nullptr, nullptr, nullptr};
     cudaStream_t cst = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    cudaEvent_t copied[kStageSlots] = {nullptr, nullptr, nullptr}, done[kStageSlots] = {nullptr, nullptr, nullptr};
     const int64_t cw = ((n < chunk ? n : chunk) + 1) & ~(int64_t)1;  // even: w half stays 16-byte aligned
     const size_t per = (size_t)cw * sizeof(double) * (w ? 2 : 1);
     int rc = 0;
     e = cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking);
     for (int b = 0; b < nbuf && e == cudaSuccess; ++b) {
-        e = cudaMalloc(&dbuf[b], per);
+        e = cudaMallocAsync(reinterpret_cast<void**>(&dbuf[b]), per, st);   // stream-ordered pool: no device sync
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) {
-        // the copy stream must see the edges/flush work only through buffer reuse events;
-        // it only touches dbuf, so no extra dependency is needed at the start
+        // the staging buffers come from st's memory pool: the copy stream may touch them only
+        // after the allocation point
+        cudaEvent_t alloc_ev = copied[0];
+        e = cudaEventRecord(alloc_ev, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cst, alloc_ev, 0);
         int k = 0;
         for (int64_t off = 0; off < n && e == cudaSuccess; off += chunk, ++k) {
             const int b = k % nbuf;
             const int64_t m = (n - off) < chunk ? (n - off) : chunk;
             if (k >= nbuf) e = cudaStreamWaitEvent(cst, done[b], 0);
+            const double* hx = x + off;
+            const double* hw_ = w ? w + off : nullptr;
+            if (staged) {
+                // the slot's previous H2D copy must have left the pinned buffer
+                if (k >= nbuf && e == cudaSuccess) e = cudaEventSynchronize(copied[b]);
+                parallel_memcpy(g_stage.slot[b], x + off, m, nthreads);
+                if (w) parallel_memcpy(g_stage.slot[b] + kStageChunk, w + off, m, nthreads);
+                hx = g_stage.slot[b];
+                hw_ = w ? g_stage.slot[b] + kStageChunk : nullptr;
+            }
             if (e == cudaSuccess)
-                e = cudaMemcpyAsync(dbuf[b], x + off, m * sizeof(double), cudaMemcpyHostToDevice, cst);
+                e = cudaMemcpyAsync(dbuf[b], hx, m * sizeof(double), cudaMemcpyHostToDevice, cst);
             if (e == cudaSuccess && w)
-                e = cudaMemcpyAsync(dbuf[b] + cw, w + off, m * sizeof(double), cudaMemcpyHostToDevice, cst);
+                e = cudaMemcpyAsync(dbuf[b] + cw, hw_, m * sizeof(double), cudaMemcpyHostToDevice, cst);
             if (e == cudaSuccess) e = cudaEventRecord(copied[b], cst);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
             if (e == cudaSuccess)
@@ -306,10 +396,11 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     cudaStreamSynchronize(st);
     if (cst) { cudaStreamSynchronize(cst); cudaStreamDestroy(cst); }
     for (int b = 0; b < nbuf; ++b) {
-        if (dbuf[b]) cudaFree(dbuf[b]);
+        if (dbuf[b]) cudaFreeAsync(dbuf[b], st);
         if (copied[b]) cudaEventDestroy(copied[b]);
         if (done[b]) cudaEventDestroy(done[b]);
     }
+    if (staged) stage_release();
     return rc;
 }
 

@@ -416,3 +416,31 @@ def test_degenerate_and_awkward_inputs(cb, case):
         lo = np.searchsorted(np.sort(xa), est, side="left") / xa.size
         hi = np.searchsorted(np.sort(xa), est, side="right") / xa.size
         assert ((lo - 0.012 <= qs) & (qs <= hi + 0.012)).all()
+
+
+def test_pinned_and_pageable_host_inputs_agree(cb):
+    """Host arrays reach the GPU either straight from pinned memory (16 Mi-value chunks) or,
+    when pageable, through the library's threaded staging slots (4 Mi-value chunks).  Same
+    digest up to the summation order of the chunks; several chunks in both paths."""
+    rng = np.random.default_rng(77)
+    n = 18 * 10**6 + 12345
+    x = rng.lognormal(size=n)
+    w = rng.uniform(0.5, 1.5, n)
+    px, pw = cb.PinnedArray(n), cb.PinnedArray(n)
+    px.array[:] = x
+    pw.array[:] = w
+    a, b = cb.TDigest(100, mode="parallel"), cb.TDigest(100, mode="parallel")
+    a.update(x, w)
+    b.update(px.array, pw.array)
+    assert a.min() == b.min() == x.min() and a.max() == b.max() == x.max()
+    assert abs(a.size() - b.size()) <= 1e-12 * b.size()
+    ca, cb_ = a.centroids(), b.centroids()
+    assert len(ca) == len(cb_)
+    np.testing.assert_allclose(ca["mean"], cb_["mean"], rtol=1e-10)
+    np.testing.assert_allclose(ca["weight"], cb_["weight"], rtol=1e-10)
+    s = cb.SummaryStats()
+    c = cb.TDigest(100, mode="parallel")
+    c.update(x, w, stats=s)                       # fused moments across staged chunks
+    assert s.count() == n and s.min() == x.min() and s.max() == x.max()
+    np.testing.assert_allclose(s.mean(), x.mean(), rtol=1e-12)
+    np.testing.assert_allclose(s.var(), x.var(), rtol=1e-9)
