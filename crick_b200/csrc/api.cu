@@ -440,7 +440,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     if (td_drain(t, st)) return -1;
     t->mirror_ok = false;
     bool parallel = mode == CRICK_MODE_PARALLEL ||
-                    (mode == CRICK_MODE_AUTO && n >= 4 * (int64_t)CRICK_PARALLEL_MIN);
+                    (mode == CRICK_MODE_AUTO && n >= (int64_t)CRICK_PARALLEL_MIN);
     if (mode == CRICK_MODE_PARALLEL && n < CRICK_PARALLEL_MIN)
         return fail_msg("parallel mode needs n >= CRICK_PARALLEL_MIN");
     const bool w_arr = w != nullptr;

@@ -42,7 +42,8 @@ class TDigest:
         ``reference``: the reference's sequential buffer/flush algorithm, bit-exact
         with crick's C path.  ``parallel``: k-bucket pre-aggregation for huge arrays
         (needs >= 65536 values per call).  ``auto`` (default): reference below
-        262144 values per ``update`` call, parallel at or above.
+        65536 values per ``update`` call (where one warp replaying the reference's
+        sequential algorithm is still affordable), parallel at or above.
     """
 
     __slots__ = ("_h", "_mode", "_keepalive", "__weakref__")
@@ -322,7 +323,7 @@ class TDigest:
         if m == _lib.MODE_PARALLEL and n_b < _lib.PARALLEL_MIN:
             eff = _lib.MODE_REFERENCE  # too small to sample: same answer, exact algorithm
         goes_parallel = eff == _lib.MODE_PARALLEL or (eff == _lib.MODE_AUTO
-                                                      and n_b >= 4 * _lib.PARALLEL_MIN)
+                                                      and n_b >= _lib.PARALLEL_MIN)
         device_check = check_w and w.ndim > 0 and goes_parallel
         if check_w and not device_check and (not np.isfinite(w).all() or (w <= 0).any()):
             raise ValueError("w must be > 0 and finite")
@@ -412,7 +413,7 @@ class TDigest:
             if wd.size != n:
                 raise ValueError("x and w CUDA arrays must have the same number of elements")
             parallel = eff == _lib.MODE_PARALLEL or (eff == _lib.MODE_AUTO
-                                                     and n >= 4 * _lib.PARALLEL_MIN)
+                                                     and n >= _lib.PARALLEL_MIN)
             if check_w and parallel:
                 bad = ctypes.c_int(0)
                 check(lib.crick_tdigest_update_checked(self._h, xd.ptr, wd.ptr, 0.0, n, 1, 1, eff,

@@ -166,7 +166,7 @@ def test_incremental_updates_accumulate(cb):
     assert t.size() == 600000 and t.min() == x.min() and t.max() == x.max()
     rank = weighted_rank_fn(x, 1.0)
     assert np.abs(rank(t.quantile(QS9)) - QS9).max() < 1e-3
-    a = cb.TDigest(100, mode="auto")     # auto: reference below 262144 values, parallel above
+    a = cb.TDigest(100, mode="auto")     # auto: reference below 65536 values, parallel above
     a.update(x[:1000])
     a.update(x)
     assert a.size() == 601000
