@@ -29,6 +29,8 @@ class DeviceArray:
     def to_numpy(self):
         out = np.empty(self.shape, dtype=self.dtype)
         if self.nbytes:
+            # whichever stream wrote this array (handles own non-blocking streams) has finished
+            check(lib.crick_device_synchronize(), "synchronize")
             check(lib.crick_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, None), "memcpy d2h")
         return out
 

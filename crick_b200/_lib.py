@@ -115,7 +115,7 @@ for _name, (_res, _args) in _SIG.items():
     _fn.argtypes = _args
 
 MODE_AUTO, MODE_REFERENCE, MODE_PARALLEL = 0, 1, 2
-PARALLEL_MIN = 65536
+PARALLEL_MIN = 8192
 _MODES = {"auto": MODE_AUTO, "reference": MODE_REFERENCE, "parallel": MODE_PARALLEL}
 
 

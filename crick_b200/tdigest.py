@@ -41,8 +41,8 @@ class TDigest:
     mode : {"auto", "reference", "parallel"}, optional
         ``reference``: the reference's sequential buffer/flush algorithm, bit-exact
         with crick's C path.  ``parallel``: k-bucket pre-aggregation for huge arrays
-        (needs >= 65536 values per call).  ``auto`` (default): reference below
-        65536 values per ``update`` call (where one warp replaying the reference's
+        (needs >= 8192 values per call).  ``auto`` (default): reference below
+        8192 values per ``update`` call (where one warp replaying the reference's
         sequential algorithm is still affordable), parallel at or above.
     """
 
@@ -115,6 +115,9 @@ class TDigest:
                     raise TypeError("out must be a float64 CUDA array with as many elements as %s" % name)
                 optr = ov.ptr
             check(fn(self._h, dv.ptr, optr, dv.size, 1, None), name)
+            # the kernel ran on this digest's own (non-blocking) stream: make the result
+            # visible to whatever stream the caller reads it from
+            check(lib.crick_device_synchronize(), name)
             return out
         if out is not None:
             raise TypeError("out= is only supported with CUDA array inputs")
@@ -288,7 +291,9 @@ class TDigest:
         w : array_like, optional
             The weight (or weights) of the values to add. Default is 1.
         mode : optional override of the digest's update mode for this call.
-        stream : optional ``cudaStream_t`` (int) to enqueue the work on.
+        stream : optional ``cudaStream_t`` (int) to enqueue the work on.  Without it the work
+            runs on the digest's own non-blocking stream: CUDA array inputs must then be
+            complete (synchronise their producer, or pass the producing stream here).
         stats : optional :class:`SummaryStats`; its moments of ``x`` (``stats.update(x)``) are
             accumulated in the same pass over the data as the digest (parallel path).
         check_w : CUDA-array weights only.  True (default): raise ValueError like the
@@ -619,6 +624,7 @@ class TDigestGroup:
                 raise TypeError("%s must be float64 when given as a CUDA array" % name)
             out = DeviceArray((ng, dv.size), "f8")
             check(fn(self._h, dv.ptr, dv.size, out.ptr, 1, None), name)
+            check(lib.crick_device_synchronize(), name)   # see TDigest._query
             return out
         q = np.asarray(q)
         if not np.can_cast(q.dtype, "f8", casting="safe"):

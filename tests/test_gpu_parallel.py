@@ -91,7 +91,7 @@ def test_partition_restated_on_cpu(cb, dist):
     check_partition(cb, x, w)
 
 
-@pytest.mark.parametrize("n", [65536, 65537, 100003, 262144 + 255, 1 << 20])
+@pytest.mark.parametrize("n", [8192, 8193, 10007, 65536, 65537, 100003, 262144 + 255, 1 << 20])
 def test_ragged_sizes_and_unaligned_views(cb, n):
     rng = np.random.default_rng(n)
     x = rng.lognormal(size=n + 1)
@@ -166,7 +166,7 @@ def test_incremental_updates_accumulate(cb):
     assert t.size() == 600000 and t.min() == x.min() and t.max() == x.max()
     rank = weighted_rank_fn(x, 1.0)
     assert np.abs(rank(t.quantile(QS9)) - QS9).max() < 1e-3
-    a = cb.TDigest(100, mode="auto")     # auto: reference below 65536 values, parallel above
+    a = cb.TDigest(100, mode="auto")     # auto: reference below 8192 values, parallel above
     a.update(x[:1000])
     a.update(x)
     assert a.size() == 601000
