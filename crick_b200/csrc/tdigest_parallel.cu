@@ -7,8 +7,9 @@
 // dependent flushes.  A centroid, however, is only (sum w, sum w*x) over a
 // contiguous quantile range, and both sums are order independent.  So:
 //
-//   1. k_sample        strided+hashed sample of S = 16 Ki (x, w) pairs      (reads S*16 B)
-//   2. k_bitonic_*     sort the sample by x (1024-element chunks on 16 SMs + global steps)
+//   1. k_sort_runs     strided+hashed sample of S = 16 Ki (x, w) pairs (reads S*16 B), sorted
+//                      by x in 1024-element runs on 16 SMs (bitonic in shared memory)
+//   2. k_merge_runs    the runs merged by ranking every element against the other runs
 //   3. k_make_edges    weighted sample quantiles at the k-scale grid
 //                      q_j = sin^2(pi*j/(2*ov*c)), j = 1..ov*c-1  (ov = 2 sub-buckets
 //                      per unit of k, so NO asin per element), heavy duplicates get a
@@ -77,6 +78,8 @@ struct ParLayout {
     double* sx;          // [kSMax]
     double* sw;          // [kSMax]
     double* cw;          // [kSMax]
+    double* sx2;         // [kSMax] merged (sorted) sample when it spans several runs
+    double* sw2;         // [kSMax]
     double2* partial;    // [ncta_max * kBPad]
     double2* minmax;     // [ncta_max]
     unsigned char* fin;  // finalize workspace (global fallback)
@@ -107,7 +110,7 @@ size_t parallel_scratch_bytes(double comp, int sm_count) {
     int cap = 2 * (int)ceil(comp);
     size_t b = 256;
     b += sizeof(double) * kEMax + 2 * kTabBytes;
-    b += 3 * sizeof(double) * kSMax;
+    b += 5 * sizeof(double) * kSMax;
     b += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     b += sizeof(double2) * (size_t)(2 * sm_count);
     b += fin_ws_bytes(cap, mmax_for(comp)) + 64;
@@ -124,6 +127,8 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
     L.sx = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.sw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.cw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.sx2 = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.sw2 = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.partial = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     L.minmax = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count);
     L.fin = p;
@@ -161,71 +166,60 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
 // 1. sample: element i comes from segment i of n/S, at a hashed offset (so a
 // periodic input cannot alias with the stride).  Rejected values (tdigest_add's
 // filter, :285) become (+inf, 0) and sort to the end.
-__global__ void k_sample(const double* __restrict__ X, const double* __restrict__ W, double wsc,
-                         long n, long S, double* __restrict__ sx, double* __restrict__ sw,
-                         ParHeader* hdr) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) hdr->S = S;
-    if (i >= S) return;
-    long seg = n / S;
-    double x = INFINITY, w = 0.0;
-    if (seg > 0) {
-        long pos = i * seg + (long)(mix64((unsigned long long)i) % (unsigned long long)seg);
+__device__ __forceinline__ void sample_one(const double* __restrict__ X, const double* __restrict__ W,
+                                           double wsc, long n, long S, long i, double& x, double& w) {
+    const long seg = n / S;
+    x = INFINITY; w = 0.0;
+    long pos = -1;
+    if (seg > 0) pos = i * seg + (long)(mix64((unsigned long long)i) % (unsigned long long)seg);
+    else if (i < n) pos = i;
+    if (pos >= 0) {
         double xv = X[pos];
         double wv = W ? W[pos] : wsc;
         if (is_finite_d(xv) && !(wv <= DBL_EPSILON)) { x = xv + 0.0; w = wv; }
-    } else if (i < n) {
-        double xv = X[i];
-        double wv = W ? W[i] : wsc;
-        if (is_finite_d(xv) && !(wv <= DBL_EPSILON)) { x = xv + 0.0; w = wv; }
     }
-    sx[i] = x;
-    sw[i] = w;
 }
 
-// 2. bitonic sort of (key, value) pairs, ascending by key.
-__device__ __forceinline__ void ce(double& ka, double& va, double& kb, double& vb, bool asc) {
-    bool sw = asc ? (kb < ka) : (ka < kb);
-    if (sw) { double t = ka; ka = kb; kb = t; t = va; va = vb; vb = t; }
-}
-
-// all stages with stride < kSortChunk for the given k range, inside shared memory
-// mode 0: full local sort (k = 2 .. kSortChunk); mode 1: merge tail of level K (j = kSortChunk/2 .. 1)
+// 2. sort of the (key, value) sample, ascending by key, in two launches:
+//   k_sort_runs   S / 1024 CTAs: each draws (SAMPLE) or loads its 1024 pairs and sorts them in
+//                 shared memory (bitonic, one compare-exchange per thread and stage);
+//   k_merge_runs  S / 1024 CTAs: every CTA stages all S keys (<= 128 KB) in shared memory and
+//                 each thread ranks its own element against the other runs with branch-free
+//                 binary searches (ties: lower run first, so the order is total and fixed), then
+//                 scatters the pair to its final place.
+// (r1_q launch list: the previous 15-launch global bitonic network took 73 us of a 195 us setup.)
 constexpr int kSortThreads = kSortChunk / 2;   // one compare-exchange per thread and stage
-__global__ void __launch_bounds__(kSortThreads) k_bitonic_local(double* __restrict__ keys,
-                                                        double* __restrict__ vals, long K, int mode) {
+template <bool SAMPLE>
+__global__ void __launch_bounds__(kSortThreads) k_sort_runs(double* __restrict__ keys,
+                                                            double* __restrict__ vals,
+                                                            const double* __restrict__ X,
+                                                            const double* __restrict__ W, double wsc,
+                                                            long n, long S, ParHeader* hdr) {
     double* sk = reinterpret_cast<double*>(smem_raw);
     double* sv = sk + kSortChunk;
     const long base = (long)blockIdx.x * kSortChunk;
+    if (SAMPLE && blockIdx.x == 0 && threadIdx.x == 0) hdr->S = S;
     for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) {
-        sk[i] = keys[base + i];
-        sv[i] = vals[base + i];
+        if (SAMPLE) {
+            sample_one(X, W, wsc, n, S, base + i, sk[i], sv[i]);
+        } else {
+            sk[i] = keys[base + i];
+            sv[i] = vals[base + i];
+        }
     }
     __syncthreads();
-    long k0 = mode == 0 ? 2 : K;
-    long k1 = mode == 0 ? kSortChunk : K;
-    constexpr int kCE = kSortChunk / 2 / kSortThreads;
-    for (long k = k0; k <= k1; k <<= 1) {
-        for (int j = (int)((k >> 1) < kSortChunk ? (k >> 1) : (kSortChunk >> 1)); j > 0; j >>= 1) {
-            // all loads first (independent), stores only where a pair is out of order
-            int ii[kCE], qq[kCE];
-            double ka[kCE], kb[kCE];
-#pragma unroll
-            for (int c = 0; c < kCE; ++c) {
-                int p = threadIdx.x + c * kSortThreads;
-                ii[c] = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                qq[c] = ii[c] | j;
-                ka[c] = sk[ii[c]]; kb[c] = sk[qq[c]];
-            }
-#pragma unroll
-            for (int c = 0; c < kCE; ++c) {
-                bool asc = (((base + ii[c]) & k) == 0);
-                bool sw = asc ? (kb[c] < ka[c]) : (ka[c] < kb[c]);
-                if (sw) {
-                    double va = sv[ii[c]], vb = sv[qq[c]];
-                    sk[ii[c]] = kb[c]; sk[qq[c]] = ka[c];
-                    sv[ii[c]] = vb; sv[qq[c]] = va;
-                }
+    for (int k = 2; k <= kSortChunk; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int p = threadIdx.x;
+            const int ii = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+            const int qq = ii | j;
+            const double ka = sk[ii], kb = sk[qq];
+            const bool asc = (ii & k) == 0;   // local index: the last level sorts ascending
+            const bool sw = asc ? (kb < ka) : (ka < kb);
+            if (sw) {
+                double va = sv[ii], vb = sv[qq];
+                sk[ii] = kb; sk[qq] = ka;
+                sv[ii] = vb; sv[qq] = va;
             }
             __syncthreads();
         }
@@ -236,33 +230,72 @@ __global__ void __launch_bounds__(kSortThreads) k_bitonic_local(double* __restri
     }
 }
 
-__global__ void k_bitonic_global(double* __restrict__ keys, double* __restrict__ vals, long L,
-                                 long j, long k) {
-    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= L / 2) return;
-    long i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-    long q = i | j;
-    bool asc = ((i & k) == 0);
-    double ka = keys[i], va = vals[i], kb = keys[q], vb = vals[q];
-    bool sw = asc ? (kb < ka) : (ka < kb);
-    if (sw) { keys[i] = kb; vals[i] = vb; keys[q] = ka; vals[q] = va; }
+__global__ void __launch_bounds__(kSortChunk) k_merge_runs(const double* __restrict__ keys,
+                                                           const double* __restrict__ vals, long S,
+                                                           double* __restrict__ okeys,
+                                                           double* __restrict__ ovals) {
+    double* sk = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x;
+    {
+        const double2* src = reinterpret_cast<const double2*>(keys);
+        double2* dst = reinterpret_cast<double2*>(sk);
+        for (long i = tid; i < S / 2; i += kSortChunk) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int R = (int)(S / kSortChunk);
+    const int r = blockIdx.x;
+    const double key = sk[r * kSortChunk + tid];
+    int rank = tid;
+#pragma unroll 4
+    for (int q = 0; q < R; ++q) {
+        const double* run = sk + q * kSortChunk;
+        // q < r: #elements <= key, q > r: #elements < key  (0 .. 1024)
+        const bool le = q < r;
+        int pos = 0;
+#pragma unroll
+        for (int step = kSortChunk / 2; step > 0; step >>= 1) {
+            const double v = run[pos + step - 1];
+            pos += (le ? (v <= key) : (v < key)) ? step : 0;
+        }
+        {
+            const double v = run[pos];
+            pos += (le ? (v <= key) : (v < key)) ? 1 : 0;
+        }
+        rank += q == r ? 0 : pos;
+    }
+    okeys[rank] = key;
+    ovals[rank] = vals[(long)r * kSortChunk + tid];
 }
 
-static cudaError_t sort_sample(double* keys, double* vals, long L, cudaStream_t st) {
-    size_t smem = (size_t)kSortChunk * 16;
-    cudaError_t e = cudaFuncSetAttribute(k_bitonic_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    unsigned nchunk = (unsigned)(L / kSortChunk);
+// Sorts S pairs (S a power of two >= kSortChunk).  The sorted pairs end up in (*skeys, *svals):
+// the input arrays when S is one run, else (keys2, vals2).
+struct SampleSrc { const double* X; const double* W; double wsc; long n; ParHeader* hdr; };
+static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double* vals2, long S,
+                               const SampleSrc* src, cudaStream_t st, const double** skeys,
+                               const double** svals) {
+    const size_t smem = (size_t)kSortChunk * 16;
+    const unsigned nrun = (unsigned)(S / kSortChunk);
+    cudaError_t e;
     count_launch();
-    k_bitonic_local<<<nchunk, kSortThreads, smem, st>>>(keys, vals, 0, 0);
-    for (long k = 2L * kSortChunk; k <= L; k <<= 1) {
-        for (long j = k >> 1; j >= kSortChunk; j >>= 1) {
-            count_launch();
-            k_bitonic_global<<<(unsigned)((L / 2 + 255) / 256), 256, 0, st>>>(keys, vals, L, j, k);
-        }
+    if (src) {
+        e = cudaFuncSetAttribute(k_sort_runs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_sort_runs<true><<<nrun, kSortThreads, smem, st>>>(keys, vals, src->X, src->W, src->wsc,
+                                                            src->n, S, src->hdr);
+    } else {
+        e = cudaFuncSetAttribute(k_sort_runs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_sort_runs<false><<<nrun, kSortThreads, smem, st>>>(keys, vals, nullptr, nullptr, 0.0, 0, S,
+                                                             nullptr);
+    }
+    *skeys = keys; *svals = vals;
+    if (nrun > 1) {
+        const size_t msm = (size_t)S * 8;
+        e = cudaFuncSetAttribute(k_merge_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+        if (e != cudaSuccess) return e;
         count_launch();
-        k_bitonic_local<<<nchunk, kSortThreads, smem, st>>>(keys, vals, k, 1);
+        k_merge_runs<<<nrun, kSortChunk, msm, st>>>(keys, vals, S, keys2, vals2);
+        *skeys = keys2; *svals = vals2;
     }
     return cudaGetLastError();
 }
@@ -293,7 +326,7 @@ __device__ __forceinline__ int cell_lin(double x, double x0, double inv) {
 
 __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const double* __restrict__ sx,
                                                      const double* __restrict__ sw,
-                                                     double* __restrict__ cw, double* __restrict__ edges,
+                                                     double* __restrict__ edges,
                                                      unsigned short* __restrict__ tab,
                                                      unsigned short* __restrict__ tab2, double comp,
                                                      int ov) {
@@ -304,6 +337,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     int* s_cnt = reinterpret_cast<int*>(s_buf + kEMax * 8);
     int* s_scan = s_cnt + kEMax;
     __shared__ int s_E;
+    double* cw = reinterpret_cast<double*>(smem_raw);   // [S] cumulative sample weights
     const int tid = threadIdx.x;
     const long S = hdr->S;
     // a. inclusive scan of sample weights (fixed order => deterministic): 4 consecutive
@@ -1043,34 +1077,61 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         ws.kend = reinterpret_cast<double*>(ws.items + t);
         ws.start = reinterpret_cast<int*>(ws.kend + t);
     }
-    // a. reduce partials over CTAs (fixed order) and the batch total weight
-    double bw = 0.0, bs = 0.0;
+    // a. reduce partials over CTAs and the batch total weight.  Bucket b is summed by NS
+    // threads, thread (s, b) taking rows s, s + NS, ... (loads independent, 8 in flight), then
+    // the NS slice sums are added in slice order: a fixed order, so the result is deterministic.
+    __shared__ double2 s_part[1024];
+    __shared__ double s_bw[1024];
+    __shared__ double s_before[1024];
+    __shared__ double s_wmn[32], s_wmx[32];
     const int b = tid;  // B <= 1024 (ov*c <= kEMax): one thread per bucket
-    auto reduce_bucket = [&](int bb, double& w_, double& s_) {
-        w_ = 0.0; s_ = 0.0;
-        for (int cta = 0; cta < ncta; ++cta) {
-            double2 a = partial[(size_t)cta * kBPad + bb];
-            w_ += a.x; s_ += a.y;
+    const int NS = 1024 / B > 0 ? 1024 / B : 1;
+    {
+        const int sl = tid / B, bb = tid - sl * B;
+        double w_ = 0.0, s_ = 0.0;
+        if (sl < NS) {
+            int cta = sl;
+            for (; cta + 7 * NS < ncta; cta += 8 * NS) {
+                double2 a[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = partial[(size_t)(cta + k * NS) * kBPad + bb];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { w_ += a[k].x; s_ += a[k].y; }
+            }
+            for (; cta < ncta; cta += NS) {
+                double2 a = partial[(size_t)cta * kBPad + bb];
+                w_ += a.x; s_ += a.y;
+            }
         }
-    };
-    if (b < B) reduce_bucket(b, bw, bs);
-    if (tid == 0) {
-        double mn = INFINITY, mx = -INFINITY;
-        for (int cta = 0; cta < ncta; ++cta) {
-            mn = fmin(mn, minmax[cta].x); mx = fmax(mx, minmax[cta].y);
+        s_part[tid] = make_double2(w_, s_);
+        double mn_ = INFINITY, mx_ = -INFINITY;
+        for (int cta = tid; cta < ncta; cta += 1024) {
+            mn_ = fmin(mn_, minmax[cta].x); mx_ = fmax(mx_, minmax[cta].y);
         }
-        s_mm[0] = mn; s_mm[1] = mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn_ = fmin(mn_, shfl_xor_d(mn_, o)); mx_ = fmax(mx_, shfl_xor_d(mx_, o));
+        }
+        if ((tid & 31) == 0) { s_wmn[tid >> 5] = mn_; s_wmx[tid >> 5] = mx_; }
     }
-    // batch weight: sum of bucket weights in bucket order (deterministic)
     s_scan[tid] = 0;
     __syncthreads();
-    __shared__ double s_bw[1024];
-    if (b < B) s_bw[b] = bw;
+    double bw = 0.0, bs = 0.0;
+    if (b < B) {
+        for (int sl = 0; sl < NS; ++sl) { bw += s_part[sl * B + b].x; bs += s_part[sl * B + b].y; }
+        s_bw[b] = bw;
+    }
+    if (tid == 32) {
+        double mn_ = INFINITY, mx_ = -INFINITY;
+        for (int k = 0; k < 32; ++k) { mn_ = fmin(mn_, s_wmn[k]); mx_ = fmax(mx_, s_wmx[k]); }
+        s_mm[0] = mn_; s_mm[1] = mx_;
+    }
     __syncthreads();
+    // batch weight and the cumulative weight before each bucket: bucket order (deterministic)
     if (tid == 0) {
-        double t = 0.0;
-        for (int i = 0; i < B; ++i) t += s_bw[i];
-        s_W = t;
+        double run = 0.0;
+        for (int i = 0; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
+        s_W = run;
     }
     __syncthreads();
     const double Wb = s_W;          // weight of this batch
@@ -1087,13 +1148,6 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         int p = (int)ceil(span * 2.0);
         return p < 1 ? 1 : p;
     };
-    // cumulative weight before each bucket (exclusive, bucket order)
-    __shared__ double s_before[1024];
-    if (tid == 0) {
-        double run = 0.0;
-        for (int i = 0; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
-    }
-    __syncthreads();
     int np = (b < B) ? pieces_of(b, bw, s_before[b]) : 0;
     // exclusive scan over 1024 buckets
     s_scan[tid] = np;
@@ -1291,13 +1345,17 @@ long parallel_sample_len(long n) {
     return S;
 }
 
-static cudaError_t edges_from_sorted_sample(const BatchView& v, ParLayout& L, long S,
-                                            cudaStream_t st) {
-    cudaError_t e = sort_sample(L.sx, L.sw, S, st);
+static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, const SampleSrc* src,
+                                     cudaStream_t st) {
+    const double *skeys, *svals;
+    cudaError_t e = sort_sample(L.sx, L.sw, L.sx2, L.sw2, S, src, st, &skeys, &svals);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)S * 8;   // cumulative sample weights
+    e = cudaFuncSetAttribute(k_make_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    k_make_edges<<<1, 1024, 0, st>>>(L.hdr, L.sx, L.sw, L.cw, L.edges, L.tab, L.tab2, v.comp,
-                                     ov_for(v.comp));
+    k_make_edges<<<1, 1024, smem, st>>>(L.hdr, skeys, svals, L.edges, L.tab, L.tab2, v.comp,
+                                        ov_for(v.comp));
     return cudaGetLastError();
 }
 
@@ -1319,7 +1377,7 @@ cudaError_t parallel_begin_from_sample(const BatchView& v, long ns, void* scratc
     while (S < ns && S < kSMax) S <<= 1;
     count_launch();
     k_pad_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(L.sx, L.sw, ns, S, L.hdr);
-    return edges_from_sorted_sample(v, L, S, st);
+    return edges_from_sample(v, L, S, nullptr, st);
 }
 
 // Shape of the hot kernel for a bucket capacity.  Two tables, each with its own token ring of
@@ -1467,11 +1525,8 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
                                    cudaStream_t st, int* bad_weights, StatsPart* stats_parts) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     long S = sample_len(n);
-    count_launch();
-    k_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(X, W, wsc, n, S, L.sx, L.sw, L.hdr);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    e = edges_from_sorted_sample(v, L, S, st);
+    SampleSrc src{X, W, wsc, n, L.hdr};
+    cudaError_t e = edges_from_sample(v, L, S, &src, st);
     if (e != cudaSuccess) return e;
     e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, stats_parts, 0);
     if (e != cudaSuccess) return e;
@@ -1497,9 +1552,16 @@ int parallel_debug_buckets(void* scratch, double comp, int sm_count, double* out
     if (cudaMemcpyAsync(rows.data(), L.partial, rows.size() * sizeof(double2), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaMemcpyAsync(mm.data(), L.minmax, mm.size() * sizeof(double2), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    const int NS = 1024 / B > 0 ? 1024 / B : 1;   // k_finalize's order: NS strided slices, then slice order
     for (int b = 0; b < B; ++b) {
         double w = 0.0, s = 0.0;
-        for (int c = 0; c < h.ncta; ++c) { w += rows[(size_t)c * kBPad + b].x; s += rows[(size_t)c * kBPad + b].y; }
+        for (int sl = 0; sl < NS; ++sl) {
+            double pw = 0.0, ps = 0.0;
+            for (int c = sl; c < h.ncta; c += NS) {
+                pw += rows[(size_t)c * kBPad + b].x; ps += rows[(size_t)c * kBPad + b].y;
+            }
+            w += pw; s += ps;
+        }
         out_w[b] = w; out_s[b] = s;
     }
     double mn = INFINITY, mx = -INFINITY;
