@@ -74,7 +74,6 @@ struct ParLayout {
     ParHeader* hdr;
     double* edges;       // [kEMax]
     unsigned short* tab;   // [kTabLen] tab[c] = #edges in cells < c (the grid k_make_edges chose)
-    unsigned short* tab2;  // [kTabLen] scratch: candidate table of the other grid
     double* sx;          // [kSMax]
     double* sw;          // [kSMax]
     double* cw;          // [kSMax]
@@ -109,7 +108,7 @@ static size_t fin_ws_bytes(int cap, int mmax) {
 size_t parallel_scratch_bytes(double comp, int sm_count) {
     int cap = 2 * (int)ceil(comp);
     size_t b = 256;
-    b += sizeof(double) * kEMax + 2 * kTabBytes;
+    b += sizeof(double) * kEMax + kTabBytes;
     b += 5 * sizeof(double) * kSMax;
     b += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     b += sizeof(double2) * (size_t)(2 * sm_count);
@@ -123,7 +122,6 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
     L.hdr = reinterpret_cast<ParHeader*>(p); p += 256;
     L.edges = reinterpret_cast<double*>(p); p += sizeof(double) * kEMax;
     L.tab = reinterpret_cast<unsigned short*>(p); p += kTabBytes;
-    L.tab2 = reinterpret_cast<unsigned short*>(p); p += kTabBytes;
     L.sx = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.sw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.cw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
@@ -138,7 +136,7 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
 
 double* parallel_sample_x(void* scratch) {
     return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256 +
-                                     sizeof(double) * kEMax + 2 * kTabBytes);
+                                     sizeof(double) * kEMax + kTabBytes);
 }
 double* parallel_sample_w(void* scratch) { return parallel_sample_x(scratch) + kSMax; }
 long parallel_sample_capacity(void*) { return kSMax; }
@@ -324,53 +322,85 @@ __device__ __forceinline__ int cell_lin(double x, double x0, double inv) {
     return clamp_cell(__double2int_rd(__dmul_rn(__dadd_rn(x, -x0), inv)));
 }
 
+// inclusive scan over the 1024 threads of the CTA (warp shuffles + one pass of warp 0 over the
+// 32 warp totals); s_w32 is a 32-entry scratch.  Two barriers.
+template <typename T>
+__device__ __forceinline__ T block_scan_incl(T v, T* s_w32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(CRICK_FULL, v, d);
+        if (lane >= d) v += o;
+    }
+    __syncthreads();                      // s_w32 may still be read from the previous call
+    if (lane == 31) s_w32[wid] = v;
+    __syncthreads();
+    T t = s_w32[lane];                    // every warp scans the 32 totals itself
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(CRICK_FULL, t, d);
+        if (lane >= d) t += o;
+    }
+    T before = __shfl_sync(CRICK_FULL, t, wid > 0 ? wid - 1 : 0);
+    return wid > 0 ? v + before : v;
+}
+
 __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const double* __restrict__ sx,
                                                      const double* __restrict__ sw,
                                                      double* __restrict__ edges,
-                                                     unsigned short* __restrict__ tab,
-                                                     unsigned short* __restrict__ tab2, double comp,
+                                                     unsigned short* __restrict__ tab, double comp,
                                                      int ov) {
-    // phases b-c use s_raw / s_cnt / s_scan, phase d reuses the same bytes as s_cnt2
+    // dynamic shared memory: cw[S] cumulative sample weights | the candidate table of each grid
+    // static: s_buf = raw edges + dedupe counts (phases b-c), then the per-cell counts (phase d)
     __shared__ __align__(16) unsigned char s_buf[(kTabLen + 6) * 4];
-    static_assert(sizeof(s_buf) >= kEMax * 8 + kEMax * 4 + 1024 * 4, "phase b-c arrays must fit");
+    static_assert(sizeof(s_buf) >= kEMax * 8 + kEMax * 4, "phase b-c arrays must fit");
+    __shared__ double s_edge[kEMax];
+    __shared__ double s_wd[32];
+    __shared__ int s_wi[32];
+    __shared__ int s_cost[2], s_kmax[2];
     double* s_raw = reinterpret_cast<double*>(s_buf);
     int* s_cnt = reinterpret_cast<int*>(s_buf + kEMax * 8);
-    int* s_scan = s_cnt + kEMax;
-    __shared__ int s_E;
-    double* cw = reinterpret_cast<double*>(smem_raw);   // [S] cumulative sample weights
     const int tid = threadIdx.x;
     const long S = hdr->S;
-    // a. inclusive scan of sample weights (fixed order => deterministic): 4 consecutive
-    // elements per thread and chunk, warp shuffles + one pass over the 32 warp totals
+    double* cw = reinterpret_cast<double*>(smem_raw);
+    unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + S * 8);   // [2][kTabLen]
+    // a. inclusive scan of the sample weights (fixed order => deterministic).  Warp w owns the
+    // S / 32 consecutive elements [w * S/32, ...): 16-deep coalesced loads, one shuffle scan per
+    // 32 elements with a running carry, then the offsets of the 32 warp totals.
     {
-        __shared__ double s_wtot[32];
-        __shared__ double s_run;
-        if (tid == 0) s_run = 0.0;
-        __syncthreads();
         const int lane = tid & 31, wid = tid >> 5;
-        for (long base = 0; base < S; base += 4096) {
-            const long i0 = base + 4L * tid;
-            double v[4];
+        const int seg = (int)(S >> 5);                 // 32 .. 512 (S is a power of two >= 1024)
+        const double* src = sw + (long)wid * seg;
+        double r[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = (i0 + k < S) ? sw[i0 + k] : 0.0;
-            v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
-            double inc = v[3];
+        for (int k = 0; k < 16; ++k) r[k] = k * 32 < seg ? src[k * 32 + lane] : 0.0;
+        double carry = 0.0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                double o = shfl_up_d(inc, d);
-                if (lane >= d) inc += o;
+        for (int k = 0; k < 16; ++k) {
+            if (k * 32 < seg) {                        // uniform
+                double v = r[k];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    double o = shfl_up_d(v, d);
+                    if (lane >= d) v += o;
+                }
+                v += carry;
+                r[k] = v;
+                carry = shfl_d(v, 31);
             }
-            if (lane == 31) s_wtot[wid] = inc;
-            __syncthreads();
-            double off = s_run;
-            for (int k = 0; k < wid; ++k) off += s_wtot[k];
-            off += inc - v[3];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (i0 + k < S) cw[i0 + k] = off + v[k];
-            __syncthreads();
-            if (tid == 1023) s_run = off + v[3];
-            __syncthreads();
         }
+        if (lane == 0) s_wd[wid] = carry;
+        __syncthreads();
+        double t = s_wd[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double o = shfl_up_d(t, d);
+            if (lane >= d) t += o;
+        }
+        const double before = wid > 0 ? shfl_d(t, wid - 1) : 0.0;
+        double* mine = cw + (long)wid * seg;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (k * 32 < seg) mine[k * 32 + lane] = before + r[k];
     }
     __syncthreads();
     const double Wt = cw[S - 1];
@@ -388,14 +418,14 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
             long mid = (lo + hi) >> 1;
             if (cw[mid] < target) lo = mid + 1; else hi = mid;
         }
-        double e = sx[lo];
-        s_raw[j] = e;
+        s_raw[j] = sx[lo];
     }
     __syncthreads();
     // c. dedupe; a value chosen more than once is "heavy" and gets [v, nextafter(v))
-    for (int j = tid; j < E0; j += blockDim.x) {
+    int cnt = 0;                                                   // E0 <= 1023: thread t owns raw edge t
+    if (tid < E0) {
+        const int j = tid;
         double v = s_raw[j];
-        int cnt = 0;
         bool first = (j == 0) || (s_raw[j - 1] != v);
         if (first && is_finite_d(v) && Wt > 0.0) {
             cnt = 1;
@@ -406,98 +436,71 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
                 if (is_finite_d(nx) && !(jn < E0 && s_raw[jn] == nx)) cnt = 2;
             }
         }
-        s_cnt[j] = cnt;
     }
-    __syncthreads();
-    // exclusive scan of s_cnt (E0 <= 1023): thread t owns element t
-    {
-        int v = (tid < E0) ? s_cnt[tid] : 0;
-        s_scan[tid] = v;
-        __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1) {
-            int o = (tid >= d) ? s_scan[tid - d] : 0;
-            __syncthreads();
-            s_scan[tid] += o;
-            __syncthreads();
-        }
-        int excl = s_scan[tid] - v;
-        if (tid < E0 && v > 0) {
-            double e = s_raw[tid];
-            edges[excl] = e;
-            if (v == 2) edges[excl + 1] = next_up(e);
-        }
-        if (tid == 1023) s_E = s_scan[1023];
+    const int incl = block_scan_incl<int>(cnt, s_wi);
+    if (cnt > 0) {
+        const double e = s_raw[tid];
+        const int at = incl - cnt;
+        s_edge[at] = e; edges[at] = e;
+        if (cnt == 2) { s_edge[at + 1] = next_up(e); edges[at + 1] = next_up(e); }
     }
+    __shared__ int s_E;
+    if (tid == 1023) s_E = incl;
+    if (tid < 2) { s_cost[tid] = 0; s_kmax[tid] = 0; }
     __syncthreads();
-    const int E = s_E;
+    const int En = s_E;
     // d. lookup tables: tab[c] = #edges whose cell is < c (so the edges of cell c are
     // tab[c] .. tab[c+1]-1), for both grids; keep the one whose fullest cell holds fewer edges
     // (ties: fewer expected compares).
-    __shared__ unsigned long long s_cost[2];
-    __shared__ int s_kmax[2];
     int kbase = 0, shift = 0;
     double x0 = 0.0, inv = 0.0;
     bool lin_ok = false;
-    if (E > 0) {
-        kbase = skey_half(edges[0]);
-        long long span = (long long)skey_half(edges[E - 1]) - (long long)kbase;
+    if (En > 0) {
+        kbase = skey_half(s_edge[0]);
+        long long span = (long long)skey_half(s_edge[En - 1]) - (long long)kbase;
         while (shift < 31 && ((span >> shift) + 1ll) > (long long)(kNC - 2)) ++shift;
-        x0 = edges[0];
-        double width = edges[E - 1] - x0;
+        x0 = s_edge[0];
+        double width = s_edge[En - 1] - x0;
         inv = (double)(kNC - 2) / width;
-        lin_ok = E >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv);
+        lin_ok = En >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv);
     }
-    if (tid < 2) { s_cost[tid] = 0ull; s_kmax[tid] = 0; }
-    __syncthreads();
     // per grid: count the edges of every cell (edges are sorted and cell() is monotone), then
     // an inclusive scan over the cells: tab[c] = sum of counts of cells < c
     int* s_cnt2 = reinterpret_cast<int*>(s_buf);
-    __shared__ int s_wsum[32];
     constexpr int kPer = (kTabLen + 1023) / 1024;   // cells per thread
     for (int g = 0; g < 2; ++g) {
-        unsigned short* out = g == 0 ? tab : tab2;
+        unsigned short* out = s_tab + g * kTabLen;
         if (g == 1 && !lin_ok) break;
-        for (int c = tid; c < kTabLen + 6; c += blockDim.x) s_cnt2[c] = 0;
+        __syncthreads();                             // s_buf is free (phase c / previous grid)
+        for (int cc = tid; cc < kTabLen + 6; cc += blockDim.x) s_cnt2[cc] = 0;
         __syncthreads();
-        for (int j = tid; j < E; j += blockDim.x) {
-            int ce_ = g == 0 ? cell_key(edges[j], kbase, shift) : cell_lin(edges[j], x0, inv);
+        for (int j = tid; j < En; j += blockDim.x) {
+            int ce_ = g == 0 ? cell_key(s_edge[j], kbase, shift) : cell_lin(s_edge[j], x0, inv);
             atomicAdd(&s_cnt2[ce_ + 1], 1);          // counted at index cell + 1
         }
         __syncthreads();
-        unsigned long long local = 0;
-        int lmax = 0, run = 0;
+        int local = 0, lmax = 0, run = 0;
         int vals[kPer];
         const int c0 = tid * kPer;
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
-            int c = c0 + k;
-            int m = c < kTabLen ? s_cnt2[c] : 0;    // = edges in cell c - 1
-            int lg = 0;
-            while ((1 << lg) < m + 1) ++lg;
-            local += (unsigned long long)m * (unsigned long long)lg;
+            int cc = c0 + k;
+            int m = cc < kTabLen ? s_cnt2[cc] : 0;    // = edges in cell cc - 1
+            int lg = m > 0 ? 32 - __clz(m) : 0;       // compares of a binary search over m + 1 outcomes
+            local += m * lg;
             lmax = m > lmax ? m : lmax;
             run += m;
             vals[k] = run;
         }
-        int inc = run;
-        const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int o = __shfl_up_sync(CRICK_FULL, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) s_wsum[wid] = inc;
-        __syncthreads();
-        int off = inc - run;
-        for (int k = 0; k < wid; ++k) off += s_wsum[k];
+        const int off = block_scan_incl<int>(run, s_wi) - run;
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
-            int c = c0 + k;
-            if (c < kTabLen) out[c] = (unsigned short)(off + vals[k]);
+            int cc = c0 + k;
+            if (cc < kTabLen) out[cc] = (unsigned short)(off + vals[k]);
         }
-        atomicAdd(&s_cost[g], local);
-        atomicMax(&s_kmax[g], lmax);
-        __syncthreads();
+        local = __reduce_add_sync(CRICK_FULL, local);
+        lmax = __reduce_max_sync(CRICK_FULL, lmax);
+        if ((tid & 31) == 0) { atomicAdd(&s_cost[g], local); atomicMax(&s_kmax[g], lmax); }
     }
     __syncthreads();
     int grid = 0;
@@ -505,10 +508,13 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         if (s_kmax[0] != s_kmax[1]) grid = s_kmax[1] < s_kmax[0] ? 1 : 0;
         else grid = s_cost[1] <= s_cost[0] ? 1 : 0;
     }
-    if (grid == 1)
-        for (int cell = tid; cell < kTabLen; cell += blockDim.x) tab[cell] = tab2[cell];
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(s_tab + grid * kTabLen);
+        unsigned* dst = reinterpret_cast<unsigned*>(tab);
+        for (int i = tid; i < kTabLen / 2; i += blockDim.x) dst[i] = src[i];
+    }
     if (tid == 0) {
-        hdr->E = E;
+        hdr->E = En;
         hdr->shift = shift;
         hdr->kbase = kbase;
         hdr->sample_total = Wt;
@@ -1050,6 +1056,78 @@ __global__ void __launch_bounds__(STATS ? 384 : 448, 1) k_bin_accumulate(const d
     }
 }
 
+// warp_merge_sorted (tdigest_ref.cuh) for a whole CTA: the same phases and the same arithmetic,
+// with the order-independent ones spread over all threads and the two sequential ones on
+// thread 0.  (Integer weights need no special case here: the warp version's parallel scan is
+// exact for them, i.e. equal to the sequential sum used below.)
+__device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp, Hdr& h, int m,
+                                                   int cap, int* s_nc) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = h.n;
+    const int T = n + m;
+    // ---- phase 2a: prefix max of centroid means -> kend[0..n)
+    if (tid < 32) {
+        double carry = -INFINITY;
+        for (int base = 0; base < n; base += 32) {
+            int j = base + lane;
+            double v = (j < n) ? ws.cen[j].x : -INFINITY;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double o = shfl_up_d(v, d);
+                if (lane >= d) v = fmax(v, o);
+            }
+            v = fmax(v, carry);
+            if (j < n) ws.kend[j] = v;
+            carry = shfl_d(v, 31);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2b: merged positions
+    for (int i = tid; i < m; i += blockDim.x) {
+        double2 it = ws.sb[i];
+        int lo = 0, hi = n;  // first j with PM[j] > b
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (ws.kend[mid] > it.x) hi = mid; else lo = mid + 1;
+        }
+        ws.items[i + lo] = it;
+    }
+    for (int j = tid; j < n; j += blockDim.x) {
+        double p = ws.kend[j];
+        int lo = 0, hi = m;  // number of sorted buffer items strictly below PM[j]
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (ws.sb[mid].x < p) lo = mid + 1; else hi = mid;
+        }
+        ws.items[j + lo] = ws.cen[j];
+    }
+    __syncthreads();
+    // ---- phase 3: cumulative weights (into kend), then k-scale per item
+    if (tid == 0) serial_cumsum(ws.items, ws.kend, T);
+    __syncthreads();
+    for (int i = tid; i < T; i += blockDim.x)
+        ws.kend[i] = kscale(comp, __ddiv_rn(ws.kend[i], h.total));
+    __syncthreads();
+    // ---- phase 4: boundary chain
+    if (tid == 0) *s_nc = serial_chain(ws.kend, ws.start, T, cap);
+    __syncthreads();
+    const int nc = *s_nc;
+    // ---- phase 5: fold runs
+    for (int c = tid; c < nc; c += blockDim.x) {
+        int s = ws.start[c], e = ws.start[c + 1];
+        double2 f = ws.items[s];
+        double mean = f.x, wt = f.y;
+        for (int i = s + 1; i < e; ++i) {
+            double2 it = ws.items[i];
+            wt = __dadd_rn(wt, it.y);
+            mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(__dadd_rn(it.x, -mean), it.y), wt));
+        }
+        ws.cen[c] = make_double2(mean, wt);
+    }
+    __syncthreads();
+    h.n = nc;
+}
+
 // 5. finalize: bucket sums -> sorted weighted points -> greedy k-scale merge.
 __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeader* hdr,
                                                    const double* __restrict__ edges,
@@ -1130,7 +1208,15 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
     // batch weight and the cumulative weight before each bucket: bucket order (deterministic)
     if (tid == 0) {
         double run = 0.0;
-        for (int i = 0; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
+        int i = 0;
+        for (; i + 8 <= B; i += 8) {        // loads batched, only the adds are serial
+            double y[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = s_bw[i + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s_before[i + k] = run; run += y[k]; }
+        }
+        for (; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
         s_W = run;
     }
     __syncthreads();
@@ -1150,15 +1236,11 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
     };
     int np = (b < B) ? pieces_of(b, bw, s_before[b]) : 0;
     // exclusive scan over 1024 buckets
-    s_scan[tid] = np;
+    __shared__ int s_wi[32];
+    const int incl = block_scan_incl<int>(np, s_wi);
+    int pos = incl - np;
+    if (tid == 1023) s_scan[1023] = incl;
     __syncthreads();
-    for (int dd = 1; dd < 1024; dd <<= 1) {
-        int o = (tid >= dd) ? s_scan[tid - dd] : 0;
-        __syncthreads();
-        s_scan[tid] += o;
-        __syncthreads();
-    }
-    int pos = s_scan[tid] - np;
     int total1024 = s_scan[1023];
     auto emit = [&](int bb, double w_, double s_, int p, int at) {
         if (p <= 0) return;
@@ -1181,29 +1263,40 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         s_m = m > mmax ? mmax : m;
     }
     __syncthreads();
-    // c. merge into the digest: warp 0 only (the greedy chain is sequential)
-    if (tid < 32) {
-        const int lane = tid;
+    // c. merge into the digest (tdigest_flush phases 2-5 with the bucket points as the buffer)
+    {
+        __shared__ double s_bt;
+        __shared__ int s_nc;
         const int m = s_m;
         Hdr h;
         const DevHdr dh = v.hdr[d];
         h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
         const double2* cg = v.cen + d * (long)cap;
-        for (int i = lane; i < h.n; i += 32) ws.cen[i] = cg[i];
-        __syncwarp();
+        for (int i = tid; i < h.n; i += blockDim.x) ws.cen[i] = cg[i];
         if (m > 0) {
             // batch weight in item order, sequential (pieces re-sum to the bucket weight
             // only up to rounding, so sum what is actually merged)
-            double bt = 0.0;
-            if (lane == 0) for (int i = 0; i < m; ++i) bt = __dadd_rn(bt, ws.sb[i].y);
-            bt = shfl_d(bt, 0);
+            if (tid == 0) {
+                double bt = 0.0;
+                int i = 0;
+                for (; i + 8 <= m; i += 8) {
+                    double y[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) y[k] = ws.sb[i + k].y;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) bt = __dadd_rn(bt, y[k]);
+                }
+                for (; i < m; ++i) bt = __dadd_rn(bt, ws.sb[i].y);
+                s_bt = bt;
+            }
+            __syncthreads();
             if (h.vmin > mn) h.vmin = mn;
             if (h.vmax < mx) h.vmax = mx;
-            h.total = __dadd_rn(h.total, bt);
-            warp_merge_sorted(ws, v.comp, h, m, cap, lane);
+            h.total = __dadd_rn(h.total, s_bt);
+            block_merge_sorted(ws, v.comp, h, m, cap, &s_nc);
             double2* cgo = v.cen + d * (long)cap;
-            for (int i = lane; i < h.n; i += 32) cgo[i] = ws.cen[i];
-            if (lane == 0) {
+            for (int i = tid; i < h.n; i += blockDim.x) cgo[i] = ws.cen[i];
+            if (tid == 0) {
                 DevHdr o = dh;
                 o.vmin = h.vmin; o.vmax = h.vmax; o.total = h.total; o.btotal = 0.0;
                 o.n = h.n; o.bn = 0;
@@ -1289,21 +1382,20 @@ __global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d
     }
     for (int i = tid; i < m; i += blockDim.x) ws.sb[i] = make_double2(key[i], wgt[i]);
     __syncthreads();
-    if (tid < 32 && m > 0) {
-        const int lane = tid;
+    if (m > 0) {                                  // uniform
+        __shared__ int s_nc;
         Hdr h;
         const DevHdr dh = v.hdr[d];
         h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
         const double2* cg = v.cen + d * (long)cap;
-        for (int i = lane; i < h.n; i += 32) ws.cen[i] = cg[i];
-        __syncwarp();
+        for (int i = tid; i < h.n; i += blockDim.x) ws.cen[i] = cg[i];
         if (h.vmin > s_mn) h.vmin = s_mn;
         if (h.vmax < s_mx) h.vmax = s_mx;
         h.total = __dadd_rn(h.total, s_tot);
-        warp_merge_sorted(ws, v.comp, h, m, cap, lane);
+        block_merge_sorted(ws, v.comp, h, m, cap, &s_nc);   // starts with a barrier
         double2* cgo = v.cen + d * (long)cap;
-        for (int i = lane; i < h.n; i += 32) cgo[i] = ws.cen[i];
-        if (lane == 0) {
+        for (int i = tid; i < h.n; i += blockDim.x) cgo[i] = ws.cen[i];
+        if (tid == 0) {
             DevHdr o = dh;
             o.vmin = h.vmin; o.vmax = h.vmax; o.total = h.total; o.btotal = 0.0;
             o.n = h.n; o.bn = 0;
@@ -1350,11 +1442,11 @@ static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, c
     const double *skeys, *svals;
     cudaError_t e = sort_sample(L.sx, L.sw, L.sx2, L.sw2, S, src, st, &skeys, &svals);
     if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)S * 8;   // cumulative sample weights
+    const size_t smem = (size_t)S * 8 + 2 * kTabBytes;   // cumulative sample weights + 2 candidate tables
     e = cudaFuncSetAttribute(k_make_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    k_make_edges<<<1, 1024, smem, st>>>(L.hdr, skeys, svals, L.edges, L.tab, L.tab2, v.comp,
+    k_make_edges<<<1, 1024, smem, st>>>(L.hdr, skeys, svals, L.edges, L.tab, v.comp,
                                         ov_for(v.comp));
     return cudaGetLastError();
 }
