@@ -179,90 +179,105 @@ __device__ __forceinline__ void sample_one(const double* __restrict__ X, const d
 }
 
 // 2. sort of the (key, value) sample, ascending by key, in two launches:
-//   k_sort_runs   S / 1024 CTAs: each draws (SAMPLE) or loads its 1024 pairs and sorts them in
-//                 shared memory (bitonic, one compare-exchange per thread and stage);
-//   k_merge_runs  S / 1024 CTAs: every CTA stages all S keys (<= 128 KB) in shared memory and
+//   k_sort_runs   S / 1024 CTAs: each draws (SAMPLE) or loads its 1024 pairs and sorts them
+//                 (bitonic network on registers: shuffles below distance 32, shared memory above);
+//   k_merge_runs  S / 256 CTAs: every CTA stages all S keys (<= 128 KB) in shared memory and
 //                 each thread ranks its own element against the other runs with branch-free
 //                 binary searches (ties: lower run first, so the order is total and fixed), then
 //                 scatters the pair to its final place.
 // (r1_q launch list: the previous 15-launch global bitonic network took 73 us of a 195 us setup.)
-constexpr int kSortThreads = kSortChunk / 2;   // one compare-exchange per thread and stage
 template <bool SAMPLE>
-__global__ void __launch_bounds__(kSortThreads) k_sort_runs(double* __restrict__ keys,
-                                                            double* __restrict__ vals,
-                                                            const double* __restrict__ X,
-                                                            const double* __restrict__ W, double wsc,
-                                                            long n, long S, ParHeader* hdr) {
-    double* sk = reinterpret_cast<double*>(smem_raw);
-    double* sv = sk + kSortChunk;
+__global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ keys,
+                                                          double* __restrict__ vals,
+                                                          const double* __restrict__ X,
+                                                          const double* __restrict__ W, double wsc,
+                                                          long n, long S, ParHeader* hdr) {
+    // one (key, source index) pair per thread in registers; compare-exchange partners at
+    // distance < 32 come by shuffle, the others through a double-buffered shared array (one
+    // barrier per stage).  Order: (key, index), so ties are deterministic.
+    __shared__ double s_key[2][kSortChunk];
+    __shared__ short s_idx[2][kSortChunk];
+    __shared__ double s_val[kSortChunk];
+    const int t = threadIdx.x;
     const long base = (long)blockIdx.x * kSortChunk;
-    if (SAMPLE && blockIdx.x == 0 && threadIdx.x == 0) hdr->S = S;
-    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) {
-        if (SAMPLE) {
-            sample_one(X, W, wsc, n, S, base + i, sk[i], sv[i]);
-        } else {
-            sk[i] = keys[base + i];
-            sv[i] = vals[base + i];
-        }
+    if (SAMPLE && blockIdx.x == 0 && t == 0) hdr->S = S;
+    double key, val;
+    if (SAMPLE) {
+        sample_one(X, W, wsc, n, S, base + t, key, val);
+    } else {
+        key = keys[base + t];
+        val = vals[base + t];
     }
-    __syncthreads();
+    s_val[t] = val;
+    int idx = t;
+    int buf = 0;
+#pragma unroll
     for (int k = 2; k <= kSortChunk; k <<= 1) {
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const int p = threadIdx.x;
-            const int ii = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-            const int qq = ii | j;
-            const double ka = sk[ii], kb = sk[qq];
-            const bool asc = (ii & k) == 0;   // local index: the last level sorts ascending
-            const bool sw = asc ? (kb < ka) : (ka < kb);
-            if (sw) {
-                double va = sv[ii], vb = sv[qq];
-                sk[ii] = kb; sk[qq] = ka;
-                sv[ii] = vb; sv[qq] = va;
+            double pk;
+            int pi;
+            if (j < 32) {
+                pk = shfl_xor_d(key, j);
+                pi = __shfl_xor_sync(CRICK_FULL, idx, j);
+            } else {
+                s_key[buf][t] = key;
+                s_idx[buf][t] = (short)idx;
+                __syncthreads();
+                pk = s_key[buf][t ^ j];
+                pi = s_idx[buf][t ^ j];
+                buf ^= 1;
             }
-            __syncthreads();
+            const bool partner_less = pk < key || (pk == key && pi < idx);
+            const bool take_min = ((t & j) == 0) == ((t & k) == 0);
+            if (partner_less == take_min) { key = pk; idx = pi; }
         }
     }
-    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) {
-        keys[base + i] = sk[i];
-        vals[base + i] = sv[i];
-    }
+    __syncthreads();                      // s_val complete (k = 1024 had barriers, but be explicit)
+    keys[base + t] = key;
+    vals[base + t] = s_val[idx];
 }
 
-__global__ void __launch_bounds__(kSortChunk) k_merge_runs(const double* __restrict__ keys,
-                                                           const double* __restrict__ vals, long S,
-                                                           double* __restrict__ okeys,
-                                                           double* __restrict__ ovals) {
+constexpr int kMergeThreads = 256;   // S / 256 CTAs: the searches are a latency chain, so spread them
+__device__ __forceinline__ int count_below(const double* run, double key, bool or_equal) {
+    // #elements < key (or <= key) of a sorted run of kSortChunk, branch-free
+    int pos = 0;
+    if (or_equal) {
+#pragma unroll
+        for (int step = kSortChunk / 2; step > 0; step >>= 1) pos += (run[pos + step - 1] <= key) ? step : 0;
+        pos += (run[pos] <= key) ? 1 : 0;
+    } else {
+#pragma unroll
+        for (int step = kSortChunk / 2; step > 0; step >>= 1) pos += (run[pos + step - 1] < key) ? step : 0;
+        pos += (run[pos] < key) ? 1 : 0;
+    }
+    return pos;
+}
+__global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const double* __restrict__ keys,
+                                                              const double* __restrict__ vals, long S,
+                                                              double* __restrict__ okeys,
+                                                              double* __restrict__ ovals) {
     double* sk = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x;
+    const long e = (long)blockIdx.x * kMergeThreads + tid;      // this thread's element
+    const double val = vals[e];
     {
         const double2* src = reinterpret_cast<const double2*>(keys);
         double2* dst = reinterpret_cast<double2*>(sk);
-        for (long i = tid; i < S / 2; i += kSortChunk) dst[i] = src[i];
+        for (long i = tid; i < S / 2; i += kMergeThreads) dst[i] = src[i];
     }
     __syncthreads();
     const int R = (int)(S / kSortChunk);
-    const int r = blockIdx.x;
-    const double key = sk[r * kSortChunk + tid];
-    int rank = tid;
+    const int r = (int)(e / kSortChunk);
+    const double key = sk[e];
+    int rank = (int)(e - (long)r * kSortChunk);
+    // ties: the lower run first -- runs before r count their elements <= key, runs after r < key
 #pragma unroll 4
-    for (int q = 0; q < R; ++q) {
-        const double* run = sk + q * kSortChunk;
-        // q < r: #elements <= key, q > r: #elements < key  (0 .. 1024)
-        const bool le = q < r;
-        int pos = 0;
-#pragma unroll
-        for (int step = kSortChunk / 2; step > 0; step >>= 1) {
-            const double v = run[pos + step - 1];
-            pos += (le ? (v <= key) : (v < key)) ? step : 0;
-        }
-        {
-            const double v = run[pos];
-            pos += (le ? (v <= key) : (v < key)) ? 1 : 0;
-        }
-        rank += q == r ? 0 : pos;
-    }
+    for (int q = 0; q < r; ++q) rank += count_below(sk + q * kSortChunk, key, true);
+#pragma unroll 4
+    for (int q = r + 1; q < R; ++q) rank += count_below(sk + q * kSortChunk, key, false);
     okeys[rank] = key;
-    ovals[rank] = vals[(long)r * kSortChunk + tid];
+    ovals[rank] = val;
 }
 
 // Sorts S pairs (S a power of two >= kSortChunk).  The sorted pairs end up in (*skeys, *svals):
@@ -271,28 +286,21 @@ struct SampleSrc { const double* X; const double* W; double wsc; long n; ParHead
 static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double* vals2, long S,
                                const SampleSrc* src, cudaStream_t st, const double** skeys,
                                const double** svals) {
-    const size_t smem = (size_t)kSortChunk * 16;
     const unsigned nrun = (unsigned)(S / kSortChunk);
     cudaError_t e;
     count_launch();
-    if (src) {
-        e = cudaFuncSetAttribute(k_sort_runs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_sort_runs<true><<<nrun, kSortThreads, smem, st>>>(keys, vals, src->X, src->W, src->wsc,
-                                                            src->n, S, src->hdr);
-    } else {
-        e = cudaFuncSetAttribute(k_sort_runs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_sort_runs<false><<<nrun, kSortThreads, smem, st>>>(keys, vals, nullptr, nullptr, 0.0, 0, S,
-                                                             nullptr);
-    }
+    if (src)
+        k_sort_runs<true><<<nrun, kSortChunk, 0, st>>>(keys, vals, src->X, src->W, src->wsc, src->n, S,
+                                                       src->hdr);
+    else
+        k_sort_runs<false><<<nrun, kSortChunk, 0, st>>>(keys, vals, nullptr, nullptr, 0.0, 0, S, nullptr);
     *skeys = keys; *svals = vals;
     if (nrun > 1) {
         const size_t msm = (size_t)S * 8;
         e = cudaFuncSetAttribute(k_merge_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
         if (e != cudaSuccess) return e;
         count_launch();
-        k_merge_runs<<<nrun, kSortChunk, msm, st>>>(keys, vals, S, keys2, vals2);
+        k_merge_runs<<<(unsigned)(S / kMergeThreads), kMergeThreads, msm, st>>>(keys, vals, S, keys2, vals2);
         *skeys = keys2; *svals = vals2;
     }
     return cudaGetLastError();
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + S * 8);   // [2][kTabLen]
     // a. inclusive scan of the sample weights (fixed order => deterministic).  Warp w owns the
     // S / 32 consecutive elements [w * S/32, ...): 16-deep coalesced loads, one shuffle scan per
-    // 32 elements with a running carry, then the offsets of the 32 warp totals.
+    // 32 elements, the chunk totals chained, then the offsets of the 32 warp totals.
     {
         const int lane = tid & 31, wid = tid >> 5;
         const int seg = (int)(S >> 5);                 // 32 .. 512 (S is a power of two >= 1024)
@@ -374,19 +382,25 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         double r[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) r[k] = k * 32 < seg ? src[k * 32 + lane] : 0.0;
+        // the 16 chunk scans are independent (the shuffles pipeline); the chunk totals are
+        // then chained
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k * 32 < seg) {                    // uniform
+                    double o = shfl_up_d(r[k], d);
+                    if (lane >= d) r[k] += o;
+                }
+            }
+        }
         double carry = 0.0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            if (k * 32 < seg) {                        // uniform
-                double v = r[k];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    double o = shfl_up_d(v, d);
-                    if (lane >= d) v += o;
-                }
-                v += carry;
-                r[k] = v;
-                carry = shfl_d(v, 31);
+            if (k * 32 < seg) {
+                const double tot = shfl_d(r[k], 31);
+                r[k] += carry;
+                carry += tot;
             }
         }
         if (lane == 0) s_wd[wid] = carry;
@@ -1060,8 +1074,11 @@ __global__ void __launch_bounds__(STATS ? 384 : 448, 1) k_bin_accumulate(const d
 // with the order-independent ones spread over all threads and the two sequential ones on
 // thread 0.  (Integer weights need no special case here: the warp version's parallel scan is
 // exact for them, i.e. equal to the sequential sum used below.)
+//
+// s_bt != nullptr: h.total does not yet include the new items; their weights are summed
+// sequentially in ws.sb order (by another thread, next to the cumulative sum) and added first.
 __device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp, Hdr& h, int m,
-                                                   int cap, int* s_nc) {
+                                                   int cap, int* s_nc, double* s_bt) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int n = h.n;
     const int T = n + m;
@@ -1104,12 +1121,48 @@ __device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp
     __syncthreads();
     // ---- phase 3: cumulative weights (into kend), then k-scale per item
     if (tid == 0) serial_cumsum(ws.items, ws.kend, T);
+    if (s_bt != nullptr && tid == 32) {
+        double bt = 0.0;
+        int i = 0;
+        for (; i + 8 <= m; i += 8) {
+            double y[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = ws.sb[i + k].y;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bt = __dadd_rn(bt, y[k]);
+        }
+        for (; i < m; ++i) bt = __dadd_rn(bt, ws.sb[i].y);
+        *s_bt = bt;
+    }
     __syncthreads();
+    if (s_bt != nullptr) h.total = __dadd_rn(h.total, *s_bt);
     for (int i = tid; i < T; i += blockDim.x)
         ws.kend[i] = kscale(comp, __ddiv_rn(ws.kend[i], h.total));
     __syncthreads();
-    // ---- phase 4: boundary chain
-    if (tid == 0) *s_nc = serial_chain(ws.kend, ws.start, T, cap);
+    // ---- phase 4: boundary chain (serial_chain's recurrence, tdigest_ref.cuh).  While
+    // k1 = kend[p] the next centroid opens at nb(p) = first i >= p + 2 with
+    // !(fl(kend_i - k1) <= 1), and then k1 = kend[nb(p) - 1]: every nb(p) is found in parallel
+    // (a short linear scan, the same test in the same order, so no monotonicity is assumed) and
+    // one thread follows the links.  p = -1 stands for the initial k1 = 0.  nb lives in ws.sb,
+    // which is dead after phase 2b (4 ints per slot >= T + 1).
+    int* nb = reinterpret_cast<int*>(ws.sb);
+    for (int p = tid - 1; p < T - 1; p += blockDim.x) {
+        const double k1 = p < 0 ? 0.0 : ws.kend[p];
+        int i = p + 2;
+        while (i < T && __dadd_rn(ws.kend[i], -k1) <= 1.0) ++i;
+        nb[p + 1] = i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ws.start[0] = 0;
+        int nc_ = 1, i = nb[0];
+        while (i < T && nc_ < cap) {
+            ws.start[nc_++] = i;
+            i = nb[i];                       // p = i - 1
+        }
+        ws.start[nc_] = T;
+        *s_nc = nc_;
+    }
     __syncthreads();
     const int nc = *s_nc;
     // ---- phase 5: fold runs
@@ -1156,7 +1209,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         ws.start = reinterpret_cast<int*>(ws.kend + t);
     }
     // a. reduce partials over CTAs and the batch total weight.  Bucket b is summed by NS
-    // threads, thread (s, b) taking rows s, s + NS, ... (loads independent, 8 in flight), then
+    // threads, thread (s, b) taking rows s, s + NS, ... (loads independent, 16 in flight), then
     // the NS slice sums are added in slice order: a fixed order, so the result is deterministic.
     __shared__ double2 s_part[1024];
     __shared__ double s_bw[1024];
@@ -1169,12 +1222,12 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         double w_ = 0.0, s_ = 0.0;
         if (sl < NS) {
             int cta = sl;
-            for (; cta + 7 * NS < ncta; cta += 8 * NS) {
-                double2 a[8];
+            for (; cta + 15 * NS < ncta; cta += 16 * NS) {
+                double2 a[16];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] = partial[(size_t)(cta + k * NS) * kBPad + bb];
+                for (int k = 0; k < 16; ++k) a[k] = partial[(size_t)(cta + k * NS) * kBPad + bb];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { w_ += a[k].x; s_ += a[k].y; }
+                for (int k = 0; k < 16; ++k) { w_ += a[k].x; s_ += a[k].y; }
             }
             for (; cta < ncta; cta += NS) {
                 double2 a = partial[(size_t)cta * kBPad + bb];
@@ -1205,36 +1258,38 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         s_mm[0] = mn_; s_mm[1] = mx_;
     }
     __syncthreads();
-    // batch weight and the cumulative weight before each bucket: bucket order (deterministic)
-    if (tid == 0) {
-        double run = 0.0;
-        int i = 0;
-        for (; i + 8 <= B; i += 8) {        // loads batched, only the adds are serial
-            double y[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) y[k] = s_bw[i + k];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { s_before[i + k] = run; run += y[k]; }
-        }
-        for (; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
-        s_W = run;
-    }
-    __syncthreads();
-    const double Wb = s_W;          // weight of this batch
     const double mn = s_mm[0], mx = s_mm[1];
     // b. pieces per bucket.  A single-valued bucket [v, nextafter(v)) heavier than
     // half a k-unit is split into equal pieces with the same mean, so that the
     // digest keeps several centroids on a heavy duplicate like the reference does.
-    auto pieces_of = [&](int bb, double w_, double before) -> int {
-        if (!(w_ > 0.0)) return 0;
-        bool single = bb >= 1 && bb <= E - 1 && edges[bb] == next_up(edges[bb - 1]);
-        if (!single) return 1;
-        double q0 = before / Wb, q1 = (before + w_) / Wb;
-        double span = kscale(v.comp, q1) - kscale(v.comp, q0);
-        int p = (int)ceil(span * 2.0);
-        return p < 1 ? 1 : p;
-    };
-    int np = (b < B) ? pieces_of(b, bw, s_before[b]) : 0;
+    const bool single = b < B && bw > 0.0 && b >= 1 && b <= E - 1 && edges[b] == next_up(edges[b - 1]);
+    int np = (b < B && bw > 0.0) ? 1 : 0;
+    if (__syncthreads_or(single)) {
+        // batch weight and the cumulative weight before each bucket, in bucket order
+        // (sequential: deterministic); only needed when there is such a bucket
+        if (tid == 0) {
+            double run = 0.0;
+            int i = 0;
+            for (; i + 8 <= B; i += 8) {        // loads batched, only the adds are serial
+                double y[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[k] = s_bw[i + k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s_before[i + k] = run; run += y[k]; }
+            }
+            for (; i < B; ++i) { s_before[i] = run; run += s_bw[i]; }
+            s_W = run;
+        }
+        __syncthreads();
+        if (single) {
+            const double Wb = s_W;          // weight of this batch
+            const double before = s_before[b];
+            double q0 = before / Wb, q1 = (before + bw) / Wb;
+            double span = kscale(v.comp, q1) - kscale(v.comp, q0);
+            int p = (int)ceil(span * 2.0);
+            np = p < 1 ? 1 : p;
+        }
+    }
     // exclusive scan over 1024 buckets
     __shared__ int s_wi[32];
     const int incl = block_scan_incl<int>(np, s_wi);
@@ -1274,26 +1329,11 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         const double2* cg = v.cen + d * (long)cap;
         for (int i = tid; i < h.n; i += blockDim.x) ws.cen[i] = cg[i];
         if (m > 0) {
-            // batch weight in item order, sequential (pieces re-sum to the bucket weight
-            // only up to rounding, so sum what is actually merged)
-            if (tid == 0) {
-                double bt = 0.0;
-                int i = 0;
-                for (; i + 8 <= m; i += 8) {
-                    double y[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) y[k] = ws.sb[i + k].y;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) bt = __dadd_rn(bt, y[k]);
-                }
-                for (; i < m; ++i) bt = __dadd_rn(bt, ws.sb[i].y);
-                s_bt = bt;
-            }
-            __syncthreads();
             if (h.vmin > mn) h.vmin = mn;
             if (h.vmax < mx) h.vmax = mx;
-            h.total = __dadd_rn(h.total, s_bt);
-            block_merge_sorted(ws, v.comp, h, m, cap, &s_nc);
+            // the batch weight (sum of the pieces actually merged, in item order) is summed
+            // inside the merge, next to the cumulative weights; it is added to h.total there
+            block_merge_sorted(ws, v.comp, h, m, cap, &s_nc, &s_bt);
             double2* cgo = v.cen + d * (long)cap;
             for (int i = tid; i < h.n; i += blockDim.x) cgo[i] = ws.cen[i];
             if (tid == 0) {
@@ -1392,7 +1432,7 @@ __global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d
         if (h.vmin > s_mn) h.vmin = s_mn;
         if (h.vmax < s_mx) h.vmax = s_mx;
         h.total = __dadd_rn(h.total, s_tot);
-        block_merge_sorted(ws, v.comp, h, m, cap, &s_nc);   // starts with a barrier
+        block_merge_sorted(ws, v.comp, h, m, cap, &s_nc, nullptr);   // starts with a barrier
         double2* cgo = v.cen + d * (long)cap;
         for (int i = tid; i < h.n; i += blockDim.x) cgo[i] = ws.cen[i];
         if (tid == 0) {
