@@ -264,7 +264,16 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const double* __re
     {
         const double2* src = reinterpret_cast<const double2*>(keys);
         double2* dst = reinterpret_cast<double2*>(sk);
-        for (long i = tid; i < S / 2; i += kMergeThreads) dst[i] = src[i];
+        // S / 2 is a multiple of 16 * kMergeThreads for S >= 8192: 16 loads in flight
+        long i = tid;
+        for (; i + 15 * kMergeThreads < S / 2; i += 16 * kMergeThreads) {
+            double2 a[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = src[i + k * kMergeThreads];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[i + k * kMergeThreads] = a[k];
+        }
+        for (; i < S / 2; i += kMergeThreads) dst[i] = src[i];
     }
     __syncthreads();
     const int R = (int)(S / kSortChunk);
@@ -357,7 +366,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
                                                      const double* __restrict__ sw,
                                                      double* __restrict__ edges,
                                                      unsigned short* __restrict__ tab, double comp,
-                                                     int ov) {
+                                                     int ov, long S) {
     // dynamic shared memory: cw[S] cumulative sample weights | the candidate table of each grid
     // static: s_buf = raw edges + dedupe counts (phases b-c), then the per-cell counts (phase d)
     __shared__ __align__(16) unsigned char s_buf[(kTabLen + 6) * 4];
@@ -369,7 +378,6 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     double* s_raw = reinterpret_cast<double*>(s_buf);
     int* s_cnt = reinterpret_cast<int*>(s_buf + kEMax * 8);
     const int tid = threadIdx.x;
-    const long S = hdr->S;
     double* cw = reinterpret_cast<double*>(smem_raw);
     unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + S * 8);   // [2][kTabLen]
     // a. inclusive scan of the sample weights (fixed order => deterministic).  Warp w owns the
@@ -1041,24 +1049,32 @@ __global__ void __launch_bounds__(STATS ? 384 : 448, 1) k_bin_accumulate(const d
         if (accumulate_into) { StatsPart o = stats_parts[blockIdx.x]; part_merge(o, t); t = o; }
         stats_parts[blockIdx.x] = t;
     }
-    // one warp per bucket: lanes read the columns (conflict-free), xor-shuffle tree
+    // column sums in place: the tables are added into table 0, then a halving tree over the
+    // columns (c += c + d, d = cols/2 .. 1): the same order as a xor-shuffle tree, without the
+    // 20 shuffles per bucket
     double2* row = partial + (size_t)blockIdx.x * kBPad;
-    for (int b = warp; b < B; b += nwarps) {
-        double sw_ = 0.0, sx_ = 0.0;
-        if (lane < cols) {
-            for (int tb = 0; tb < ntab; ++tb) {
-                double2 a = s_acc[((size_t)tb * rows + b) * cols + lane];
-                sw_ += a.x; sx_ += a.y;
+    {
+        const int nrc = B * cols;                      // rows 0 .. B-1 of table 0
+        for (int tb = 1; tb < ntab; ++tb) {
+            for (int i = threadIdx.x; i < nrc; i += blockDim.x) {
+                double2 a = s_acc[i], o = s_acc[(size_t)tb * rows * cols + i];
+                s_acc[i] = make_double2(a.x + o.x, a.y + o.y);
             }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            sw_ += shfl_xor_d(sw_, d);
-            sx_ += shfl_xor_d(sx_, d);
+        __syncthreads();
+        for (int dcol = cols >> 1; dcol > 0; dcol >>= 1) {
+            const int sh = __ffs(dcol) - 1;
+            for (int i = threadIdx.x; i < B * dcol; i += blockDim.x) {
+                const int bb = i >> sh, c = i & (dcol - 1);
+                double2 a = s_acc[bb * cols + c], o = s_acc[bb * cols + c + dcol];
+                s_acc[bb * cols + c] = make_double2(a.x + o.x, a.y + o.y);
+            }
+            __syncthreads();
         }
-        if (lane == 0) {
-            if (accumulate_into) { double2 o = row[b]; sw_ += o.x; sx_ += o.y; }
-            row[b] = make_double2(sw_, sx_);
+        for (int bb = threadIdx.x; bb < B; bb += blockDim.x) {
+            double2 a = s_acc[bb * cols];
+            if (accumulate_into) { double2 o = row[bb]; a.x += o.x; a.y += o.y; }
+            row[bb] = a;
         }
     }
     if (threadIdx.x == 0) {
@@ -1487,7 +1503,7 @@ static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, c
     if (e != cudaSuccess) return e;
     count_launch();
     k_make_edges<<<1, 1024, smem, st>>>(L.hdr, skeys, svals, L.edges, L.tab, v.comp,
-                                        ov_for(v.comp));
+                                        ov_for(v.comp), S);
     return cudaGetLastError();
 }
 
