@@ -194,6 +194,7 @@ int crick_device_synchronize(void) {
     return e == cudaSuccess ? 0 : fail("cudaDeviceSynchronize", e);
 }
 int crick_profile_enable(int on) { profile_enable(on); return 0; }
+int crick_group_kernel(int mode) { return ingest_lanes_mode(mode); }
 int crick_profile_collect(double* total_ms, int64_t* launches) {
     long long n = 0;
     int rc = profile_collect(total_ms, &n);
@@ -668,6 +669,9 @@ struct crick_tdigest_group {
     cudaStream_t own = nullptr;
     cudaStream_t last = nullptr;
     cudaEvent_t ev = nullptr;
+    // what may be waiting in the buffers: 0 nothing, 1 items that all weigh pend_w, 2 anything
+    int pend = 0;
+    double pend_w = 0.0;
 };
 
 static cudaStream_t grp_stream(crick_tdigest_group* g, void* stream) {
@@ -713,10 +717,13 @@ int crick_tdigest_group_update(crick_tdigest_group_t* g, const double* values, c
     cudaStream_t st = grp_stream(g, stream);
     const long ng = g->s.nd;
     static_assert(sizeof(long) == sizeof(int64_t), "LP64 expected");
+    const bool uniform = weights == nullptr && (g->pend == 0 || (g->pend == 1 && g->pend_w == w_scalar));
+    g->pend = uniform ? 1 : 2;
+    g->pend_w = w_scalar;
     if (on_device) {
         cudaError_t e = launch_ingest(g->s.v, ng, values, weights, w_scalar, 1, 1,
                                       reinterpret_cast<const long*>(offsets), row_len, row_stride,
-                                      nullptr, 0, st);
+                                      nullptr, 0, st, uniform);
         return e == cudaSuccess ? 0 : fail("group_update", e);
     }
     // host input: stage values (+weights, +offsets) once
@@ -739,7 +746,7 @@ int crick_tdigest_group_update(crick_tdigest_group_t* g, const double* values, c
     }
     if (e == cudaSuccess)
         e = launch_ingest(g->s.v, ng, d, weights ? d + total : nullptr, w_scalar, 1, 1, doff, row_len,
-                          row_stride, nullptr, 0, st);
+                          row_stride, nullptr, 0, st, uniform);
     cudaFreeAsync(d, st);
     if (doff) cudaFreeAsync(doff, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -749,12 +756,14 @@ int crick_tdigest_group_update(crick_tdigest_group_t* g, const double* values, c
 int crick_tdigest_group_flush(crick_tdigest_group_t* g) {
     cudaStream_t st = grp_stream(g, nullptr);
     cudaError_t e = launch_flush(g->s.v, 0, 1, g->s.nd, st);
+    if (e == cudaSuccess) g->pend = 0;
     return e == cudaSuccess ? 0 : fail("group_flush", e);
 }
 
 int crick_tdigest_group_merge_tree(crick_tdigest_group_t* g, crick_tdigest_t* out) {
     if (out->s.v.cap != g->s.v.cap || out->s.v.bufcap != g->s.v.bufcap)
         return fail_msg("merge_tree: output digest has a different compression");
+    g->pend = 2;   // merges feed centroids through the buffers (tdigest_merge :592-606)
     cudaStream_t st = grp_stream(g, nullptr);
     const long n = g->s.nd;
     cudaError_t e = cudaSuccess;

@@ -10,7 +10,17 @@ struct StatsPart;   // stats_dev.cuh
 // ---- reference-compatible path (tdigest_kernels.cu)
 cudaError_t launch_ingest(const BatchView& v, long ngroups, const double* X, const double* W,
                           double wsc, long sx, long sw, const long* offsets, long fixed_len,
-                          long row_stride, const long* dmap, int flags, cudaStream_t st);
+                          long row_stride, const long* dmap, int flags, cudaStream_t st,
+                          bool pending_uniform = false);
+// pending_uniform: the caller knows that W == nullptr and every item still waiting in a buffer
+// of these digests has weight wsc (or the buffers are empty), so no per-item weights are kept
+// thread-per-digest variant for many groups (tdigest_lanes.cu); same arguments and results
+bool ingest_lanes_wanted(long ngroups);
+int ingest_lanes_mode(int mode);   // -1 auto, 0 warp per digest, 1 thread per digest; returns previous
+cudaError_t launch_ingest_lanes(const BatchView& v, long ngroups, const double* X, const double* W,
+                                double wsc, long sx, long sw, const long* offsets, long fixed_len,
+                                long row_stride, const long* dmap, int flags, cudaStream_t st,
+                                bool pending_uniform);
 cudaError_t launch_flush(const BatchView& v, long first, long step, long count, cudaStream_t st);
 cudaError_t launch_merge_pairs(const BatchView& dv, const BatchView& sv, long dfirst, long dstep,
                                long sfirst, long sstep, long count, cudaStream_t st);

@@ -398,8 +398,12 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 
 cudaError_t launch_ingest(const BatchView& v, long ngroups, const double* X, const double* W,
                           double wsc, long sx, long sw, const long* offsets, long fixed_len,
-                          long row_stride, const long* dmap, int flags, cudaStream_t st) {
+                          long row_stride, const long* dmap, int flags, cudaStream_t st,
+                          bool pending_uniform) {
     if (ngroups <= 0) return cudaSuccess;
+    if (ingest_lanes_wanted(ngroups))
+        return launch_ingest_lanes(v, ngroups, X, W, wsc, sx, sw, offsets, fixed_len, row_stride,
+                                   dmap, flags, st, pending_uniform);
     size_t smem;
     // many groups: 8 warps/CTA keeps >=2 CTAs per SM resident at c=100; a single
     // digest gets a 1-warp CTA

@@ -47,6 +47,11 @@ int64_t crick_launch_count(void);
  * launched on: enable, run, then collect (synchronises) -> summed ms and launch count */
 int crick_profile_enable(int on);
 int crick_profile_collect(double *total_ms, int64_t *launches);
+/* grouped reference-compatible ingest: which kernel runs.  -1 (default) one thread per digest
+ * from 4 warps of digests per SM (18944 groups on a B200), one warp per digest below; 0 always
+ * one warp per digest; 1 always one thread per digest.  Results are bit-identical either way.
+ * Returns the previous setting. */
+int crick_group_kernel(int mode);
 /* pinned host memory for callers that want true async H2D (bench e2e leg) */
 void *crick_host_alloc(int64_t bytes);
 void crick_host_free(void *p);

@@ -280,7 +280,17 @@ def test_device_array_inputs_match_host_inputs(cb):
 
 
 # ---- grouped digests and the merge tree (BASELINE configs[2], [3]) ---------------------
-def test_grouped_fixed_rows_vs_oracle(cb):
+@pytest.fixture(params=[0, 1], ids=["warp_per_digest", "thread_per_digest"])
+def group_kernel(request):
+    """Both grouped ingest kernels (tdigest_kernels.cu k_ingest, tdigest_lanes.cu) must give the
+    reference's bits; auto would pick by group count."""
+    from crick_b200._lib import lib
+    prev = lib.crick_group_kernel(request.param)
+    yield request.param
+    lib.crick_group_kernel(prev)
+
+
+def test_grouped_fixed_rows_vs_oracle(cb, group_kernel):
     rng = np.random.default_rng(2)
     vals = rng.normal(size=(3000, 1000))
     g = cb.TDigestGroup(3000, 100)
@@ -301,7 +311,7 @@ def test_grouped_fixed_rows_vs_oracle(cb):
     assert (meta[:, 1] + 0 >= 0).all()
 
 
-def test_grouped_ragged_weighted_and_incremental(cb):
+def test_grouped_ragged_weighted_and_incremental(cb, group_kernel):
     rng = np.random.default_rng(4)
     lens = rng.integers(0, 400, 500)
     lens[7] = 0
@@ -320,6 +330,56 @@ def test_grouped_ragged_weighted_and_incremental(cb):
         assert g.centroids(r).tobytes() == b.centroids().tobytes(), r
     d = g.digest(3)
     assert d.centroids().tobytes() == g.centroids(3).tobytes()
+
+
+@pytest.mark.parametrize("comp", [20, 100, 333.5, 1000])
+def test_group_kernels_agree_on_hostile_input(cb, comp):
+    """Thread-per-digest vs warp-per-digest on the same input: NaN / inf (dropped, :285), +-0.0
+    ties, duplicates, tiny weights, ragged lengths incl. empty groups, pending buffers
+    carried over a second update -- every byte of the state must agree, and a sample of groups
+    must equal the reference."""
+    from crick_b200._lib import lib
+    rng = np.random.default_rng(int(comp))
+    ng = 700
+    lens = rng.integers(0, 900, ng)
+    lens[[3, 77]] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(off[-1])
+    v = rng.normal(size=n).round(1)                       # many duplicates
+    v[rng.random(n) < 0.02] = np.nan
+    v[rng.random(n) < 0.01] = np.inf
+    v[rng.random(n) < 0.02] = -0.0
+    v[rng.random(n) < 0.02] = 0.0
+    w = rng.uniform(0.1, 3.0, n)
+    w[rng.random(n) < 0.02] = 1e-17                        # <= eps: dropped
+    states = []
+    for mode in (0, 1):
+        prev = lib.crick_group_kernel(mode)
+        try:
+            g = cb.TDigestGroup(ng, comp)
+            g.update(v, w, offsets=off)
+            g.update(v[::-1].copy(), 2.0, offsets=(n - off[::-1]).astype(np.int64))
+            meta_pending = g.meta().copy()
+            cents = [g.centroids(r) for r in range(ng)]    # flushes
+            states.append((meta_pending, g.meta().copy(), cents))
+        finally:
+            lib.crick_group_kernel(prev)
+    a, b = states
+    assert a[0].tobytes() == b[0].tobytes()
+    assert a[1].tobytes() == b[1].tobytes()
+    for r in range(ng):
+        assert a[2][r].tobytes() == b[2][r].tobytes(), r
+    # reference check of the second-update composition on a few groups
+    offr = (n - off[::-1]).astype(np.int64)
+    vr = v[::-1].copy()
+    for r in range(0, ng, 41):
+        o = R.TDigest(comp)
+        s1 = slice(off[r], off[r + 1]); s2 = slice(offr[r], offr[r + 1])
+        if s1.stop > s1.start:
+            o.update(v[s1], w[s1])
+        if s2.stop > s2.start:
+            o.update(vr[s2], 2.0)
+        assert a[2][r].tobytes() == o.centroids().tobytes(), r
 
 
 @pytest.mark.parametrize("ngroups", [1, 2, 37, 64])
