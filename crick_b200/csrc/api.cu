@@ -85,6 +85,7 @@ struct crick_tdigest {
     std::vector<double> px, pw;      // pending scalar adds (tdigest_add), in order
     DevHdr mirror;                   // host copy of the header
     bool mirror_ok = false;
+    bool buf_clean = false;          // the insertion buffer is known to be empty (no flush needed)
     void* scratch = nullptr;         // parallel-mode scratch (lazy)
     size_t scratch_bytes = 0;
 };
@@ -116,7 +117,7 @@ static int td_drain(crick_tdigest* t, cudaStream_t st) {
     cudaFreeAsync(d, st);
     t->px.clear();
     t->pw.clear();
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     if (e != cudaSuccess) return fail("drain pending adds", e);
     return 0;
 }
@@ -312,9 +313,9 @@ static void stage_release() {
 
 static int td_update_host_parallel(crick_tdigest* t, const double* x, const double* w, double wsc,
                                    int64_t n, cudaStream_t st, int* bad_weights,
-                                   crick_stats* stats) {
+                                   crick_stats* stats, bool clean) {
     if (td_scratch(t)) return -1;
-    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
     if (e != cudaSuccess) return fail("flush", e);
     const long S = parallel_sample_len(n);
     std::vector<double> sx((size_t)S), sw((size_t)S);
@@ -402,6 +403,7 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
         if (done[b]) cudaEventDestroy(done[b]);
     }
     if (staged) stage_release();
+    if (rc == 0) t->buf_clean = true;   // flushed above, and k_finalize leaves no buffer
     return rc;
 }
 
@@ -439,7 +441,8 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     if (n <= 0) return 0;  // tdigest_stubs.c:648-650
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    const bool clean = t->buf_clean;   // after the drain: pending adds go through the buffer
+    t->mirror_ok = false; t->buf_clean = false;
     bool parallel = mode == CRICK_MODE_PARALLEL ||
                     (mode == CRICK_MODE_AUTO && n >= (int64_t)CRICK_PARALLEL_MIN);
     if (mode == CRICK_MODE_PARALLEL && n < CRICK_PARALLEL_MIN)
@@ -448,7 +451,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     if (w_arr && (x_on_device != w_on_device))
         return fail_msg("x and w must both be host or both be device arrays");
     if (!x_on_device) {
-        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st, bad_weights, stats);
+        if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st, bad_weights, stats, clean);
         // reference mode from host memory: stage the whole (small) input
         double* d = nullptr;
         size_t bytes = (size_t)n * sizeof(double) * (w_arr ? 2 : 1);
@@ -469,7 +472,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     cudaError_t e;
     if (parallel) {
         if (td_scratch(t)) return -1;
-        e = launch_flush(t->s.v, 0, 1, 1, st);
+        e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
         StatsPart* sparts = nullptr;
         int snparts = 0;
         if (stats && stats_fused_begin(stats, st, &sparts, &snparts)) return -1;
@@ -478,6 +481,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
                                        bad_weights, sparts);
         if (e == cudaSuccess && stats && !(bad_weights && *bad_weights))
             e = stats_fused_finish(stats, sm_count(), st);
+        if (e == cudaSuccess) t->buf_clean = true;   // flushed above, and k_finalize leaves no buffer
     } else {
         e = launch_ingest(t->s.v, 1, x, w, w_scalar, 1, 1, nullptr, n, 0, nullptr, 0, st);
     }
@@ -487,20 +491,21 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
 int crick_tdigest_flush(crick_tdigest_t* t) {
     cudaStream_t st = td_stream(t, nullptr);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    if (e == cudaSuccess) t->buf_clean = true;
     return e == cudaSuccess ? 0 : fail("flush", e);
 }
 
 int crick_tdigest_merge(crick_tdigest_t* t, crick_tdigest_t* const* others, int n_others) {
     cudaStream_t st = td_stream(t, nullptr);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     for (int i = 0; i < n_others; ++i) {
         crick_tdigest* o = others[i];
         cudaStream_t ost = td_stream(o, nullptr);
         if (td_drain(o, ost)) return -1;
-        o->mirror_ok = false;
+        o->mirror_ok = false; o->buf_clean = false;
         cudaError_t e = launch_flush(o->s.v, 0, 1, 1, ost);  // tdigest_merge flushes `other` (:595)
         if (e == cudaSuccess && o != t) {
             e = cudaEventRecord(o->ev, ost);
@@ -520,7 +525,7 @@ int crick_tdigest_merge(crick_tdigest_t* t, crick_tdigest_t* const* others, int 
 int crick_tdigest_scale(crick_tdigest_t* t, double factor) {
     cudaStream_t st = td_stream(t, nullptr);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
     if (e == cudaSuccess) e = launch_scale(t->s.v, 0, factor, st);
     return e == cudaSuccess ? 0 : fail("scale", e);
@@ -530,7 +535,7 @@ static int td_query(crick_tdigest* t, bool cdf, const double* in, double* out, i
                     int on_device, void* stream) {
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;  // query_prep flushes (tdigest_stubs.c:307)
+    t->mirror_ok = false; t->buf_clean = false;  // query_prep flushes (tdigest_stubs.c:307)
     cudaError_t e = launch_query_prep(t->s.v, 0, 1, st);
     if (e != cudaSuccess) return fail("query prep", e);
     if (n <= 0) return 0;
@@ -607,7 +612,7 @@ int crick_tdigest_reset(crick_tdigest_t* t, void* stream) {
     cudaStream_t st = td_stream(t, stream);
     t->px.clear();
     t->pw.clear();
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = launch_init_hdr(t->s.v.hdr, 1, st);
     return e == cudaSuccess ? 0 : fail("reset", e);
 }
@@ -629,7 +634,7 @@ int crick_tdigest_record_doubles(crick_tdigest_t* t) { return 4 + 2 * t->s.v.cap
 int crick_tdigest_export_record(crick_tdigest_t* t, double* record_dev, void* stream) {
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
     if (e == cudaSuccess) e = launch_pack_record(t->s.v, 0, record_dev, st);
     return e == cudaSuccess ? 0 : fail("export_record", e);
@@ -639,7 +644,7 @@ int crick_tdigest_merge_records(crick_tdigest_t* t, const double* records_dev, i
                                 void* stream) {
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = launch_merge_records(t->s.v, 0, records_dev, n_records, skip, st);
     return e == cudaSuccess ? 0 : fail("merge_records", e);
 }
@@ -648,7 +653,7 @@ int crick_tdigest_merge_records_bulk(crick_tdigest_t* t, const double* records_d
                                      void* stream) {
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false;
+    t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
     if (e == cudaSuccess) {
         e = launch_merge_records_bulk(t->s.v, 0, records_dev, n_records, st);
@@ -775,7 +780,7 @@ int crick_tdigest_group_merge_tree(crick_tdigest_group_t* g, crick_tdigest_t* ou
     if (e != cudaSuccess) return fail("merge_tree", e);
     cudaStream_t ost = td_stream(out, nullptr);
     if (td_drain(out, ost)) return -1;
-    out->mirror_ok = false;
+    out->mirror_ok = false; out->buf_clean = false;
     e = cudaEventRecord(g->ev, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, g->ev, 0);
     if (e == cudaSuccess) e = launch_copy_digest(out->s.v, 0, g->s.v, 0, ost);
@@ -852,7 +857,7 @@ int crick_tdigest_group_extract(crick_tdigest_group_t* g, int64_t i, crick_tdige
     cudaStream_t st = grp_stream(g, nullptr);
     cudaStream_t ost = td_stream(out, nullptr);
     if (td_drain(out, ost)) return -1;
-    out->mirror_ok = false;
+    out->mirror_ok = false; out->buf_clean = false;
     cudaError_t e = cudaEventRecord(g->ev, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, g->ev, 0);
     if (e == cudaSuccess) e = launch_copy_digest(out->s.v, 0, g->s.v, i, ost);

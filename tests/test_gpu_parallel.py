@@ -10,6 +10,7 @@ checked the way SURVEY.md 8c prescribes:
   (c) size-independent properties at full size (1e9 values on the device): exact total weight
       by linearity, exact min/max, monotone quantiles.
 """
+import pickle
 import numpy as np
 import pytest
 
@@ -444,3 +445,42 @@ def test_pinned_and_pageable_host_inputs_agree(cb):
     assert s.count() == n and s.min() == x.min() and s.max() == x.max()
     np.testing.assert_allclose(s.mean(), x.mean(), rtol=1e-12)
     np.testing.assert_allclose(s.var(), x.var(), rtol=1e-9)
+
+
+def test_pending_buffer_is_flushed_before_a_parallel_update(cb):
+    """The library skips the flush launch when it knows the insertion buffer is empty; every
+    way of putting items into the buffer (add, small reference-mode update, merge, pickle
+    round trip) must still be seen by the next parallel update."""
+    rng = np.random.default_rng(77)
+    big = rng.normal(size=50000)
+
+    def total_after(prepare):
+        t = cb.TDigest(100)
+        t.update(big, mode="parallel")          # buffer known empty from here on
+        w = prepare(t)
+        t.update(big, mode="parallel")
+        return t, 2 * big.size + w
+
+    def by_add(t):
+        for v in (1.0, 2.0, 3.0):
+            t.add(v, 2.0)
+        return 6.0
+
+    def by_small_update(t):
+        t.update(np.arange(10.0), mode="reference")
+        return 10.0
+
+    def by_merge(t):
+        o = cb.TDigest(100)
+        o.update(np.arange(30.0), mode="reference")
+        t.merge(o)
+        return 30.0
+
+    for prepare in (by_add, by_small_update, by_merge):
+        t, want = total_after(prepare)
+        assert t.size() == want, prepare.__name__
+        assert t.centroids()["weight"].sum() == want, prepare.__name__
+        t2 = pickle.loads(pickle.dumps(t))
+        t2.add(5.0)
+        t2.update(big, mode="parallel")
+        assert t2.centroids()["weight"].sum() == want + 1 + big.size
