@@ -46,6 +46,38 @@ namespace crick {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// Programmatic dependent launch: the setup kernels of one update are a chain of short
+// dependent grids, so each is launched with cudaLaunchAttributeProgrammaticStreamSerialization --
+// it may be scheduled (and run its own prologue) while its predecessor in the stream is still
+// running, and executes grid_dep_wait() before it touches anything the predecessor wrote.
+// CRICK_PDL=0 falls back to plain launches.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static bool pdl_enabled() {
+    static const bool on = [] {
+        const char* env = getenv("CRICK_PDL");
+        return !(env && env[0] == '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kNC = 8192;        // lookup-table cells (uint16 entries, + 2 sentinels)
 constexpr int kTabLen = kNC + 2;
 constexpr size_t kTabBytes = ((size_t)kTabLen * 2 + 15) & ~(size_t)15;
@@ -260,6 +292,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const double* __re
     double* sk = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x;
     const long e = (long)blockIdx.x * kMergeThreads + tid;      // this thread's element
+    grid_dep_wait();                                            // the sorted runs
     const double val = vals[e];
     {
         const double2* src = reinterpret_cast<const double2*>(keys);
@@ -309,7 +342,9 @@ static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double
         e = cudaFuncSetAttribute(k_merge_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
         if (e != cudaSuccess) return e;
         count_launch();
-        k_merge_runs<<<(unsigned)(S / kMergeThreads), kMergeThreads, msm, st>>>(keys, vals, S, keys2, vals2);
+        e = launch_dep(k_merge_runs, dim3((unsigned)(S / kMergeThreads)), dim3(kMergeThreads), msm, st,
+                       keys, vals, S, keys2, vals2);
+        if (e != cudaSuccess) return e;
         *skeys = keys2; *svals = vals2;
     }
     return cudaGetLastError();
@@ -378,6 +413,8 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     double* s_raw = reinterpret_cast<double*>(s_buf);
     int* s_cnt = reinterpret_cast<int*>(s_buf + kEMax * 8);
     const int tid = threadIdx.x;
+    grid_dep_launch();        // k_bin_accumulate may take the other SMs and clear its tables
+    grid_dep_wait();          // the sorted sample
     double* cw = reinterpret_cast<double*>(smem_raw);
     unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + S * 8);   // [2][kTabLen]
     // a. inclusive scan of the sample weights (fixed order => deterministic).  Warp w owns the
@@ -979,14 +1016,16 @@ __global__ void __launch_bounds__(STATS ? 384 : 448, 1) k_bin_accumulate(const d
     __shared__ double s_min[32], s_max[32];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
+    // clearing the tables needs nothing from k_make_edges: it runs before the dependency wait
+    for (int i = threadIdx.x; i < ntab * rows * cols; i += blockDim.x)
+        s_acc[i] = make_double2(0.0, 0.0);
+    grid_dep_wait();
     const int E = hdr->E;
     const int B = E + 1;
     for (int i = threadIdx.x; i < kTabLen / 2; i += blockDim.x)
         reinterpret_cast<unsigned*>(s_tab)[i] = reinterpret_cast<const unsigned*>(g_tab)[i];
     for (int i = threadIdx.x; i < bmax + kEdgePad; i += blockDim.x)
         s_edges[i] = i < E ? g_edges[i] : INFINITY;
-    for (int i = threadIdx.x; i < ntab * rows * cols; i += blockDim.x)
-        s_acc[i] = make_double2(0.0, 0.0);
     const unsigned stage = (unsigned)__cvta_generic_to_shared(s_stage) + (unsigned)warp * kStageBytes;
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_mbar) + 8u * (unsigned)warp;
     if (STAGE) {
@@ -1208,6 +1247,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
     __shared__ int s_m;
     __shared__ double s_W;
     const int tid = threadIdx.x;
+    grid_dep_wait();          // the partials of k_bin_accumulate
     const int E = hdr->E;
     const int B = E + 1;
     const int ncta = hdr->ncta;
@@ -1502,9 +1542,8 @@ static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, c
     e = cudaFuncSetAttribute(k_make_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    k_make_edges<<<1, 1024, smem, st>>>(L.hdr, skeys, svals, L.edges, L.tab, v.comp,
-                                        ov_for(v.comp), S);
-    return cudaGetLastError();
+    return launch_dep(k_make_edges, dim3(1), dim3(1024), smem, st, L.hdr, skeys, svals, L.edges, L.tab,
+                      v.comp, ov_for(v.comp), S);
 }
 
 // host supplies ns (<= kSMax) sample pairs already copied into parallel_sample_x/w
@@ -1605,9 +1644,10 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return e;                                                           \
         count_launch();                                                                           \
-        k_bin_accumulate<HW, VC, SG, SS><<<grid, block, smem, st>>>(                              \
-            X, W, wsc, n, L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, cfg.cols, cfg.ntab,   \
-            accumulate_into, stats_parts, idx_base);                                              \
+        e = launch_dep(k_bin_accumulate<HW, VC, SG, SS>, dim3(grid), dim3(block), smem, st, X, W, \
+                       wsc, n, L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, cfg.cols,        \
+                       cfg.ntab, accumulate_into, stats_parts, idx_base);                         \
+        if (e != cudaSuccess) return e;                                                           \
     } while (0)
 #define CRICK_LAUNCH_ACC(HW, VC, SG)                                                              \
     do {                                                                                          \
@@ -1652,9 +1692,8 @@ cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_
                                          (int)(use_smem ? wsb : 0));
     if (e != cudaSuccess) return e;
     count_launch();
-    k_finalize<<<1, 1024, smem, st>>>(v, d, L.hdr, L.edges, L.partial, L.minmax, L.fin, mmax,
-                                      use_smem);
-    return cudaGetLastError();
+    return launch_dep(k_finalize, dim3(1), dim3(1024), smem, st, v, d, L.hdr, L.edges, L.partial,
+                      L.minmax, L.fin, mmax, use_smem);
 }
 
 // reads the "some weight is not > 0 and finite" flag of the accumulate calls since the last

@@ -484,3 +484,19 @@ def test_pending_buffer_is_flushed_before_a_parallel_update(cb):
         t2.add(5.0)
         t2.update(big, mode="parallel")
         assert t2.centroids()["weight"].sum() == want + 1 + big.size
+
+
+def test_parallel_update_is_deterministic(cb):
+    """Ordered sums + a setup chain launched with programmatic dependencies (griddepcontrol):
+    repeating the same updates must reproduce the same bytes every time."""
+    rng = np.random.default_rng(123)
+    for n in (20000, 700000):
+        x = cb.DeviceArray.from_numpy(rng.lognormal(size=n))
+        w = cb.DeviceArray.from_numpy(rng.uniform(0.5, 1.5, n))
+        seen = set()
+        for _ in range(40):
+            t = cb.TDigest(100)
+            t.update(x, w, mode="parallel")
+            t.update(x, mode="parallel")
+            seen.add(t.centroids().tobytes())
+        assert len(seen) == 1, n
