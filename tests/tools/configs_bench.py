@@ -1,8 +1,9 @@
 """Timing of BASELINE.json configs 3, 4 and 5 (parity-test cases, not the bench line) on one
-GPU, next to the reference's C code on the host.  Prints one JSON object per config."""
+GPU, next to the reference's C code on the host.  Prints one JSON object per config.
+Test tooling (it imports oracle/ as checker and CPU baseline), hence under tests/."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import crick_b200 as cb
 from crick_b200._lib import lib
 import oracle

@@ -1,3 +1,4 @@
+"""Rank error and time of the parallel path on small inputs, against the oracle (test tooling)."""
 import sys, numpy as np, time
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import crick_b200 as cb, oracle
