@@ -162,7 +162,27 @@ __global__ void __launch_bounds__(512) k_stats_partial(const XT* __restrict__ x,
     if (vec) {
         const long npair = n >> 1;
         constexpr int U = 4;
-        for (long j0 = tid; j0 < npair; j0 += U * stride) {
+        long j0 = tid;
+        if (UNIT) {
+            // full groups of UF 128-bit loads: no predicates, block update
+            constexpr int UF = 8;
+            for (; j0 + (UF - 1) * stride < npair; j0 += UF * stride) {
+                double v[2 * UF];
+#pragma unroll
+                for (int k = 0; k < UF; ++k) {
+                    const long j = j0 + k * stride;
+                    if (sizeof(XT) == 8 && !std::is_same<XT, double>::value) {
+                        longlong2 t = __ldg(reinterpret_cast<const longlong2*>(x) + j);
+                        v[2 * k] = (double)t.x; v[2 * k + 1] = (double)t.y;
+                    } else {
+                        double2 t = __ldg(reinterpret_cast<const double2*>(x) + j);
+                        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+                    }
+                }
+                stats_block_unit<2 * UF>(a, p, v, [&](int k) { return 2 * (j0 + (k >> 1) * stride) + (k & 1); });
+            }
+        }
+        for (; j0 < npair; j0 += U * stride) {
             double v[2 * U];
             long long c[2 * U];
 #pragma unroll

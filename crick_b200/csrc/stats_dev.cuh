@@ -92,6 +92,32 @@ __device__ __forceinline__ void stats_one(StatsAcc& a, StatsPart& p, double v, l
 }
 
 
+// N elements with count 1 at once.  When the thread already has its shift K and none of the N
+// values is a NaN (the common case) nothing but the power sums, the sum and min / max is touched:
+// 13 instructions per value instead of ~40 with the per-value bookkeeping of stats_one.
+// idx(k) gives the global index of v[k] (only evaluated on the slow path).
+template <int N, typename IdxFn>
+__device__ __forceinline__ void stats_block_unit(StatsAcc& a, StatsPart& p, const double* v, IdxFn idx) {
+    bool slow = !a.haveK;
+#pragma unroll
+    for (int k = 0; k < N; ++k) slow |= (v[k] != v[k]);
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) stats_one<true>(a, p, v[k], 1, idx(k));
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double d = v[k] - a.K, d2 = d * d;
+        a.s1 += d; a.s2 += d2; a.s3 = __fma_rn(d2, d, a.s3); a.s4 = __fma_rn(d2, d2, a.s4);
+        a.sx += v[k];
+        a.vmin = v[k] < a.vmin ? v[k] : a.vmin;
+        a.vmax = v[k] > a.vmax ? v[k] : a.vmax;
+    }
+    a.cN += (double)N;
+    a.cnt += N;
+}
+
 // per-thread shifted power sums -> central moments of the thread's elements
 __device__ __forceinline__ void stats_thread_finish(const StatsAcc& a, StatsPart& p) {
     if (a.haveK) {

@@ -948,11 +948,14 @@ __device__ __forceinline__ void accumulate_stream(const Lookup& L, const Ring ri
         if (STATS && have) {
             // SummaryStats moments of x in the same pass (stats_update_ndarray :199-210 with
             // count 1): NaN skipped, everything else -- infinities included -- counted
+            const long i0 = idx_base + t * kTile + 2 * lane;
+            if (m == 0xffu) {
+                stats_block_unit<2 * kU>(sa, sp, xs, [&](int k) { return i0 + (k >> 1) * 64 + (k & 1); });
+            } else {
 #pragma unroll
-            for (int k = 0; k < 2 * kU; ++k)
-                if ((m >> k) & 1u)
-                    stats_one<true>(sa, sp, xs[k], 1,
-                                    idx_base + t * kTile + (k >> 1) * 64 + 2 * lane + (k & 1));
+                for (int k = 0; k < 2 * kU; ++k)
+                    if ((m >> k) & 1u) stats_one<true>(sa, sp, xs[k], 1, i0 + (k >> 1) * 64 + (k & 1));
+            }
         }
         if (have) {
             bool susp = false;
