@@ -259,21 +259,26 @@ __device__ __forceinline__ void close_state(const SpsvW& w, unsigned char* gbase
 __global__ void __launch_bounds__(32) k_spsv_update(unsigned char* state, long cap, int hcap,
                                                     int use_smem, const long long* __restrict__ item,
                                                     const long long* __restrict__ cnt,
-                                                    long long cnt_scalar, long n) {
+                                                    long long cnt_scalar, long n,
+                                                    const long long* __restrict__ when) {
+    // when != nullptr: the elements are a sub-sequence of a stream that has already been
+    // accounted for in `seen`; when[i] is the stream position of element i (heavy-hitter path)
     const int lane = threadIdx.x;
     SpsvW w = open_state(state, cap, hcap, use_smem, lane);
     for (long base = 0; base < n; base += 32) {
         long i = base + lane;
         long long it = i < n ? item[i] : 0;
         long long c = cnt ? (i < n ? cnt[i] : 0) : cnt_scalar;
+        long long wh = when ? (i < n ? when[i] : 0) : w.seen + i;
         int m = (int)((n - base) < 32 ? (n - base) : 32);
         for (int k = 0; k < m; ++k) {
             long long itk = __shfl_sync(CRICK_FULL, it, k);
             long long ck = __shfl_sync(CRICK_FULL, c, k);
-            spsv_add1(w, itk, ck, w.seen + base + k, lane);
+            long long whk = __shfl_sync(CRICK_FULL, wh, k);
+            spsv_add1(w, itk, ck, whk, lane);
         }
     }
-    w.seen += n;
+    if (!when) w.seen += n;
     close_state(w, state, cap, hcap, use_smem, lane);
 }
 
@@ -285,7 +290,8 @@ __global__ void __launch_bounds__(128) k_spsv_shards(unsigned char* shards, size
                                                      const unsigned char* main_state,
                                                      const long long* __restrict__ item,
                                                      const long long* __restrict__ cnt,
-                                                     long long cnt_scalar, long n) {
+                                                     long long cnt_scalar, long n,
+                                                     const long long* __restrict__ when) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= nshards) return;
@@ -297,14 +303,16 @@ __global__ void __launch_bounds__(128) k_spsv_shards(unsigned char* shards, size
         long i = base + lane;
         long long it = i < hi ? item[i] : 0;
         long long c = cnt ? (i < hi ? cnt[i] : 0) : cnt_scalar;
+        long long wh = when ? (i < hi ? when[i] : 0) : base_seen + i;
         int m = (int)((hi - base) < 32 ? (hi - base) : 32);
         for (int k = 0; k < m; ++k) {
             long long itk = __shfl_sync(CRICK_FULL, it, k);
             long long ck = __shfl_sync(CRICK_FULL, c, k);
-            spsv_add1(w, itk, ck, base_seen + base + k, lane);
+            long long whk = __shfl_sync(CRICK_FULL, wh, k);
+            spsv_add1(w, itk, ck, whk, lane);
         }
     }
-    w.seen = base_seen + hi;
+    w.seen = when ? base_seen : base_seen + hi;
     close_state(w, state, cap, hcap, 0, lane);
 }
 
@@ -447,6 +455,8 @@ __global__ void k_spsv_init(unsigned char* state, long cap, int hcap, size_t str
 
 }  // namespace crick
 
+#include "spsv_hh.cuh"
+
 using namespace crick;
 
 struct crick_spsv {
@@ -474,13 +484,15 @@ static cudaStream_t sp_stream(crick_spsv* s, void* stream) {
 
 constexpr long kSpsvParallelMin = 1 << 18;   // below: the bit-exact sequential replay
 constexpr long kSpsvShardMin = 4096;         // elements per shard, at least
+constexpr long kSpsvHHMin = 1 << 22;         // from here: count candidates instead of replaying
+constexpr long kSpsvHHMaxCap = 1024;         // (4 x capacity candidates must fit the lookup image)
 
 // Parallel update: shard summaries -> pairwise merge tree -> merge into the main summary ->
 // list order of an exact summary.  Valid Space-Saving summary for any input (the merge is the
 // reference's own, Cafaro et al.); counts are exact whenever #distinct <= capacity.
 static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* item,
                                              const long long* cnt, long long cs, long n,
-                                             cudaStream_t st) {
+                                             cudaStream_t st, const long long* when = nullptr) {
     const size_t stride = spsv_bytes(s->cap, s->hcap);
     long G = n / kSpsvShardMin;
     const long gmax = 16L * sm_count();
@@ -494,7 +506,7 @@ static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* ite
     k_spsv_init<<<(unsigned)G, 256, 0, st>>>(shards, s->cap, s->hcap, stride);
     count_launch();
     k_spsv_shards<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(shards, stride, s->cap, s->hcap, (int)G,
-                                                          s->d, item, cnt, cs, n);
+                                                          s->d, item, cnt, cs, n, when);
     for (long step = 1; step < G; step <<= 1) {
         // shard k <- merge(shard k, shard k + step) for k = 0, 2*step, 4*step, ...
         long pairs = (G - step + 2 * step - 1) / (2 * step);
@@ -527,18 +539,143 @@ static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* ite
     return e;
 }
 
+static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, long n, cudaStream_t st,
+                                       bool* done);
+
 static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const long long* cnt,
-                                    long long cs, long n, cudaStream_t st, int mode = 0) {
-    // mode: 0 auto, 1 sequential (reference replay), 2 parallel
-    if (mode == 2 || (mode == 0 && n >= kSpsvParallelMin))
-        return sp_launch_update_parallel(s, item, cnt, cs, n, st);
+                                    long long cs, long n, cudaStream_t st, int mode = 0,
+                                    const long long* when = nullptr) {
+    // mode: 0 auto, 1 sequential (reference replay), 2 parallel (shards), 3 counting (heavy hitters)
+    if (!when && !cnt && cs == 1 && s->cap <= kSpsvHHMaxCap &&
+        (mode == 3 || (mode == 0 && n >= kSpsvHHMin)) && n >= 4 * 1024) {
+        bool done = false;
+        cudaError_t e = sp_launch_update_hh(s, item, n, st, &done);
+        if (e != cudaSuccess || done) return e;
+        // not applicable to this batch (see k_hh_finish): replay it
+    }
+    if (mode == 2 || mode == 3 || (mode == 0 && n >= kSpsvParallelMin))
+        return sp_launch_update_parallel(s, item, cnt, cs, n, st, when);
     cudaError_t e = cudaSuccess;
     if (s->smem > 48 * 1024)
         e = cudaFuncSetAttribute(k_spsv_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    k_spsv_update<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, item, cnt, cs, n);
+    k_spsv_update<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, item, cnt, cs, n, when);
     return cudaGetLastError();
+}
+
+// Counting path (spsv_hh.cuh).  *done = false: the batch does not suit it, nothing was changed.
+static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, long n, cudaStream_t st,
+                                       bool* done) {
+    *done = false;
+    int C = 256;
+    while (C < 4 * s->cap) C <<= 1;
+    if (C > kHHCandMax) C = kHHCandMax;
+    const int L = 2 * C;
+    const long S = n / 4 < kHHSampleMax ? n / 4 : kHHSampleMax;
+    const size_t smem_cnt = (size_t)L * 10 + (size_t)C * 8;
+    int G = sm_count() * (2 * smem_cnt + 2048 <= 227 * 1024 ? 2 : 1);
+    const long W = (long)G * kHHWarps;
+    const size_t stride = spsv_bytes(s->cap, s->hcap);
+    // one allocation: sample table | buckets | candidates | lookup image | rows | miss counts | status | tmp
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_tabkey = take((size_t)kHHTabSlots * 8), o_tabcnt = take((size_t)kHHTabSlots * 4);
+    const size_t o_buckets = take((size_t)kHHBuckets * 4);
+    const size_t o_cand = take((size_t)C * 8), o_lutk = take((size_t)L * 8), o_lutv = take((size_t)L * 2);
+    const size_t o_rc = take((size_t)G * C * 4), o_rl = take((size_t)G * C * 4);
+    const size_t o_wm = take((size_t)W * 8), o_wo = take((size_t)W * 8);
+    const size_t o_status = take(sizeof(HHStatus)), o_tmp = take(stride);
+    unsigned char* ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, off, st);
+    if (e != cudaSuccess) return e;
+    long long* tabkey = reinterpret_cast<long long*>(ws + o_tabkey);
+    unsigned* tabcnt = reinterpret_cast<unsigned*>(ws + o_tabcnt);
+    unsigned* buckets = reinterpret_cast<unsigned*>(ws + o_buckets);
+    long long* cand = reinterpret_cast<long long*>(ws + o_cand);
+    long long* lutk = reinterpret_cast<long long*>(ws + o_lutk);
+    unsigned short* lutv = reinterpret_cast<unsigned short*>(ws + o_lutv);
+    unsigned* rc = reinterpret_cast<unsigned*>(ws + o_rc);
+    unsigned* rl = reinterpret_cast<unsigned*>(ws + o_rl);
+    unsigned long long* wm = reinterpret_cast<unsigned long long*>(ws + o_wm);
+    unsigned long long* wo = reinterpret_cast<unsigned long long*>(ws + o_wo);
+    HHStatus* dstatus = reinterpret_cast<HHStatus*>(ws + o_status);
+    unsigned char* tmp = ws + o_tmp;
+    long long* miss_item = nullptr;
+    HHStatus hs = {};
+    long base_seen = 0;
+    do {
+        // the stream position of this batch's first element
+        e = cudaMemcpyAsync(&base_seen, s->d + offsetof(SpsvHdr, seen), sizeof(long), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) break;
+        e = cudaMemsetAsync(tabcnt, 0, (size_t)kHHTabSlots * 4, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(buckets, 0, (size_t)kHHBuckets * 4, st);
+        if (e != cudaSuccess) break;
+        e = cudaMemsetAsync(dstatus, 0, sizeof(HHStatus), st);
+        if (e != cudaSuccess) break;
+        count_launch();
+        k_hh_fill<<<1024, 256, 0, st>>>(tabkey, kHHTabSlots, kHHEmpty);
+        count_launch();
+        k_hh_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(item, n, S, tabkey, tabcnt);
+        count_launch();
+        k_hh_select<<<1, 1024, 0, st>>>(tabkey, tabcnt, C, cand, lutk, lutv, L, dstatus);
+        e = cudaFuncSetAttribute(k_hh_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
+        if (e != cudaSuccess) break;
+        e = cudaStreamSynchronize(st);           // base_seen has arrived
+        if (e != cudaSuccess) break;
+        count_launch();
+        k_hh_count<<<G, kHHWarps * 32, smem_cnt, st>>>(item, n, lutk, lutv, L, C, rc, rl, buckets, wm, 0,
+                                                       nullptr, nullptr, nullptr, base_seen);
+        const size_t smem_fin = (size_t)C * 20;
+        e = cudaFuncSetAttribute(k_hh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
+        if (e != cudaSuccess) break;
+        count_launch();
+        k_hh_finish<<<1, 1024, smem_fin, st>>>(rc, rl, G, C, cand, buckets, wm, n, base_seen, tmp, s->cap,
+                                               s->hcap, dstatus);
+        e = cudaMemcpyAsync(&hs, dstatus, sizeof(HHStatus), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) break;
+        if (hs.fallback) break;                  // *done stays false: nothing was changed
+        // fold the batch's summary into the object (spsv_merge)
+        if (s->smem > 48 * 1024)
+            e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+        if (e != cudaSuccess) break;
+        count_launch();
+        k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, tmp, s->cap, s->hcap, 0, 0);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+        *done = true;
+        if (hs.others > 0 && hs.others <= kHHMissCap) {
+            // few elements outside the candidates: collect them in stream order and replay them
+            e = cudaMallocAsync(&miss_item, (size_t)hs.others * 16, st);
+            if (e != cudaSuccess) break;
+            long long* miss_pos = miss_item + hs.others;
+            count_launch();
+            k_hh_scan<<<1, 1024, 0, st>>>(wm, (int)W, wo);
+            count_launch();
+            k_hh_count<<<G, kHHWarps * 32, smem_cnt, st>>>(item, n, lutk, lutv, L, C, rc, rl, buckets, wm, 1,
+                                                           wo, miss_item, miss_pos, base_seen);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) break;
+            e = sp_launch_update(s, miss_item, nullptr, 1, (long)hs.others, st,
+                                 hs.others >= kSpsvParallelMin ? 2 : 1, miss_pos);
+            if (e != cudaSuccess) break;
+        }
+        if (s->cap <= 8192) {
+            int P = 1;
+            while (P < s->cap) P <<= 1;
+            size_t sm = (size_t)P * 20;
+            if (sm > 48 * 1024)
+                e = cudaFuncSetAttribute(k_spsv_reorder_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) break;
+            count_launch();
+            k_spsv_reorder_exact<<<1, 1024, sm, st>>>(s->d, s->cap, s->hcap, P);
+            e = cudaGetLastError();
+        }
+    } while (0);
+    if (miss_item) cudaFreeAsync(miss_item, st);
+    cudaFreeAsync(ws, st);
+    return e;
 }
 
 static int sp_drain(crick_spsv* s, cudaStream_t st) {

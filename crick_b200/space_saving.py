@@ -147,12 +147,15 @@ class SpaceSaving:
             raise TypeError("item cannot be converted to %s" % self.dtype)
         check(lib.crick_spsv_add(self._h, bits, count), "add")
 
-    def update(self, item, count=1, stream=None):
+    def update(self, item, count=1, stream=None, mode=0):
         """update(self, item, count=1)
 
         Add many elements to the summary.  `item` may be NumPy-compatible or an
-        int64 / float64 CUDA array matching the summary's dtype.
+        int64 / float64 CUDA array matching the summary's dtype.  ``mode`` (an addition) picks
+        the kernel: 0 auto, 1 in-order replay, 2 shard summaries, 3 candidate counting
+        (see ``crick_spsv_update`` in include/crick_cuda.h).
         """  # space_saving.pyx:270-302
+        mode = int(mode)
         idv = device_view(item)
         if idv is not None:
             if idv.dtype != self.dtype:
@@ -163,13 +166,13 @@ class SpaceSaving:
             if cd is not None:
                 if cd.dtype != np.int64 or cd.size != idv.size:
                     raise TypeError("count must be an int64 CUDA array shaped like item")
-                check(lib.crick_spsv_update(self._h, idv.ptr, cd.ptr, 0, idv.size, 1, 1, 0, stream),
+                check(lib.crick_spsv_update(self._h, idv.ptr, cd.ptr, 0, idv.size, 1, 1, mode, stream),
                       "update")
             else:
                 c = _as_int(count, "count")
                 if c <= 0:
                     raise ValueError("count must be > 0")
-                check(lib.crick_spsv_update(self._h, idv.ptr, None, c, idv.size, 1, 0, 0, stream),
+                check(lib.crick_spsv_update(self._h, idv.ptr, None, c, idv.size, 1, 0, mode, stream),
                       "update")
             return
         item = np.asarray(item)
@@ -185,10 +188,10 @@ class SpaceSaving:
             item = item.view("i8")
         xf, cf = korder_pair(item, count, w_dtype="i8", x_dtype="i8")
         if isinstance(cf, np.ndarray):
-            check(lib.crick_spsv_update(self._h, xf.ctypes.data, cf.ctypes.data, 0, xf.size, 0, 0, 0,
+            check(lib.crick_spsv_update(self._h, xf.ctypes.data, cf.ctypes.data, 0, xf.size, 0, 0, mode,
                                         stream), "update")
         else:
-            check(lib.crick_spsv_update(self._h, xf.ctypes.data, None, int(cf), xf.size, 0, 0, 0,
+            check(lib.crick_spsv_update(self._h, xf.ctypes.data, None, int(cf), xf.size, 0, 0, mode,
                                         stream), "update")
 
     def topk(self, k, astuples=False):

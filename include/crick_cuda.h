@@ -215,7 +215,15 @@ int crick_spsv_add(crick_spsv_t *s, int64_t item, int64_t count);            /* 
  * reference, list order included); above, shard summaries are built in parallel and merged with
  * the reference's own merge (:289-364, Cafaro et al.) -- a valid Space-Saving summary for any
  * input, with exact counts and the reference's list order whenever #distinct <= capacity.
- * mode 1 forces the sequential replay, mode 2 the parallel path. */
+ * From 4194304 elements with count 1 (capacity <= 1024) the batch is COUNTED instead of replayed:
+ * the 4 x capacity most frequent items of a 1 Mi sample are counted exactly in one streaming
+ * pass, the top `capacity` form a summary with error 0 (every other item is bounded by the next
+ * candidate / the fullest of 1 Mi miss buckets; counts and errors are raised by the excess if
+ * that bound exceeds the smallest kept count), merged with :289-364; if at most 1 Mi elements
+ * missed the candidates they are replayed with their stream positions, so the result is still
+ * bit-identical to the reference whenever #distinct <= capacity.
+ * mode 1 forces the sequential replay, mode 2 the shard path, mode 3 the counting path (falls
+ * back to 2 when it does not apply). */
 int crick_spsv_update(crick_spsv_t *s, const int64_t *item, const int64_t *count,
                       int64_t count_scalar, int64_t n, int item_on_device, int count_on_device,
                       int mode, void *stream);

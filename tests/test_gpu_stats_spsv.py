@@ -274,3 +274,68 @@ def test_spsv_parallel_path(cb):
     of = R.SpaceSaving(50)
     of.update(xf.view("i8"))
     assert f.counters().view("i8").tobytes() == of.counters().view("i8").tobytes()
+
+
+def _assert_valid_summary(c, items, capacity):
+    """Metwally's guarantees against the true counts."""
+    vals, counts = np.unique(items, return_counts=True)
+    true = dict(zip(vals.tolist(), counts.tolist()))
+    assert (np.diff(c["count"]) <= 0).all()
+    for it, cn, er in c.tolist():
+        assert cn - er <= true.get(it, 0) <= cn, (it, cn, er, true.get(it, 0))
+    present = set(c["item"].tolist())
+    if len(c) < capacity:
+        assert present == set(vals.tolist())
+    else:
+        floor = c["count"].min()
+        assert set(vals[counts > floor].tolist()) <= present
+    return true
+
+
+@pytest.mark.parametrize("n", [50000, 5 * 10**6])
+def test_spsv_counting_path_exact_regime(cb, n):
+    """Candidate counting (mode 3; auto from 4 Mi elements): with #distinct <= capacity the result
+    is the reference's, bit for bit, list order included -- rare items that the sample missed come
+    back through the ordered replay of the misses."""
+    rng = np.random.default_rng(n)
+    items = (rng.zipf(1.3, n) % 700).astype(np.int64) * 7919 - 3
+    items[rng.integers(0, n, 5)] = np.iinfo(np.int64).min        # the lookup's empty marker
+    items[[n // 3, n // 2]] = [123456789, -987654321]            # two singletons
+    s, o = cb.SpaceSaving(1000, "i8"), R.SpaceSaving(1000)
+    s.update(cb.DeviceArray.from_numpy(items), mode=0 if n >= 1 << 22 else 3)
+    o.update(items)
+    assert s.counters().tobytes() == o.counters().tobytes()
+    s.update(items[::-1].copy(), mode=3)                         # on top of an existing summary
+    o.update(items[::-1].copy())
+    assert s.counters().tobytes() == o.counters().tobytes()
+    assert (s.counters()["error"] == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["zipf", "uniform", "two_level"])
+def test_spsv_counting_path_is_a_valid_summary(cb, kind):
+    """More distinct items than counters: exact counts for the kept items, and every guarantee of
+    a Space-Saving summary holds against the true counts (heavy tail, no heavy hitters at all,
+    and a few heavy items over a sea of singletons)."""
+    rng = np.random.default_rng(11)
+    n = 3 * 10**6
+    if kind == "zipf":
+        items = rng.zipf(1.1, n).astype(np.int64)
+    elif kind == "uniform":
+        items = rng.integers(0, 1 << 40, n).astype(np.int64)
+    else:
+        items = np.where(rng.random(n) < 0.7, rng.integers(0, 300, n), rng.integers(1 << 20, 1 << 50, n)).astype(np.int64)
+    for cap in (1000, 20):
+        s = cb.SpaceSaving(cap, "i8")
+        s.update(cb.DeviceArray.from_numpy(items), mode=3)
+        c = s.counters()
+        true = _assert_valid_summary(c, items, cap)
+        if kind != "uniform":
+            vals = np.array(list(true.keys())); counts = np.array(list(true.values()))
+            k = min(cap // 2, 100)
+            top = vals[np.argsort(-counts, kind="stable")[:k]]
+            got = {it: (cn, er) for it, cn, er in c.tolist()}
+            for it in top.tolist():                               # heavy hitters: exact counts
+                assert got[it][0] - got[it][1] == true[it]
+        # a second batch, then a merge with a replayed summary: still valid for the union
+        s.update(items[: n // 2].copy(), mode=3)
+        _assert_valid_summary(s.counters(), np.concatenate([items, items[: n // 2]]), cap)
