@@ -585,6 +585,9 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     const size_t o_cand = take((size_t)C * 8), o_lutk = take((size_t)L * 8), o_lutv = take((size_t)L * 2);
     const size_t o_rc = take((size_t)G * C * 4), o_rl = take((size_t)G * C * 4);
     const size_t o_wm = take((size_t)W * 8), o_wo = take((size_t)W * 8);
+    const size_t o_cc = take((size_t)C * 8), o_cl = take((size_t)C * 8);
+    const size_t o_hist = take(1024 * 4), o_sel = take(sizeof(HHSel));
+    const size_t o_cg = take((size_t)kHHNChunk * 4), o_ce = take((size_t)kHHNChunk * 4);
     const size_t o_status = take(sizeof(HHStatus)), o_tmp = take(stride);
     unsigned char* ws = nullptr;
     cudaError_t e = cudaMallocAsync(&ws, off, st);
@@ -599,6 +602,12 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     unsigned* rl = reinterpret_cast<unsigned*>(ws + o_rl);
     unsigned long long* wm = reinterpret_cast<unsigned long long*>(ws + o_wm);
     unsigned long long* wo = reinterpret_cast<unsigned long long*>(ws + o_wo);
+    long long* ccnt = reinterpret_cast<long long*>(ws + o_cc);
+    long long* clast = reinterpret_cast<long long*>(ws + o_cl);
+    unsigned* hist = reinterpret_cast<unsigned*>(ws + o_hist);
+    HHSel* sel = reinterpret_cast<HHSel*>(ws + o_sel);
+    int* chunk_gt = reinterpret_cast<int*>(ws + o_cg);
+    int* chunk_eq = reinterpret_cast<int*>(ws + o_ce);
     HHStatus* dstatus = reinterpret_cast<HHStatus*>(ws + o_status);
     unsigned char* tmp = ws + o_tmp;
     long long* miss_item = nullptr;
@@ -617,8 +626,18 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         k_hh_fill<<<1024, 256, 0, st>>>(tabkey, kHHTabSlots, kHHEmpty);
         count_launch();
         k_hh_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(item, n, S, tabkey, tabcnt);
+        e = cudaMemsetAsync(hist, 0, 1024 * 4, st);
+        if (e != cudaSuccess) break;
         count_launch();
-        k_hh_select<<<1, 1024, 0, st>>>(tabkey, tabcnt, C, cand, lutk, lutv, L, dstatus);
+        k_hh_hist<<<128, 1024, 0, st>>>(tabcnt, hist);
+        count_launch();
+        k_hh_thresh<<<1, 32, 0, st>>>(hist, C, sel);
+        count_launch();
+        k_hh_chunks<<<kHHNChunk, 1024, 0, st>>>(tabcnt, sel, chunk_gt, chunk_eq);
+        count_launch();
+        k_hh_place<<<kHHNChunk, 1024, 0, st>>>(tabkey, tabcnt, sel, chunk_gt, chunk_eq, cand);
+        count_launch();
+        k_hh_lut<<<1, 1024, 0, st>>>(cand, sel, chunk_eq, lutk, lutv, L, dstatus);
         e = cudaFuncSetAttribute(k_hh_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
         if (e != cudaSuccess) break;
         e = cudaStreamSynchronize(st);           // base_seen has arrived
@@ -630,8 +649,11 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         e = cudaFuncSetAttribute(k_hh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
         if (e != cudaSuccess) break;
         count_launch();
-        k_hh_finish<<<1, 1024, smem_fin, st>>>(rc, rl, G, C, cand, buckets, wm, n, base_seen, tmp, s->cap,
-                                               s->hcap, dstatus);
+        k_hh_reduce<<<64, 256, (size_t)G * sizeof(long), st>>>(rc, rl, G, C, buckets, wm, n, base_seen, ccnt,
+                                                               clast, dstatus);
+        count_launch();
+        k_hh_finish<<<1, 1024, smem_fin, st>>>(ccnt, clast, C, cand, n, base_seen, tmp, s->cap, s->hcap,
+                                               dstatus);
         e = cudaMemcpyAsync(&hs, dstatus, sizeof(HHStatus), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) break;

@@ -8,9 +8,9 @@
 // al.'s merge (spsv_merge, space_saving_stubs.c.in:289-364) combines any two such summaries.
 // So the batch is summarised by EXACT counting of candidates:
 //   1. k_hh_sample    1 Mi elements at strided+hashed positions into a global hash table;
-//   2. k_hh_select    the C = 4 x capacity most frequent sampled items become candidates (one
-//                     CTA: histogram of the sample counts, threshold, compaction in slot order
-//                     => deterministic) + a linear-probing lookup image for them;
+//   2. k_hh_hist ... k_hh_lut  the C = 4 x capacity most frequent sampled items become
+//                     candidates (histogram of the sample counts, threshold, compaction in slot
+//                     order => deterministic) + a linear-probing lookup image for them;
 //   3. k_hh_count     ONE streaming pass over the batch (8 B / element, HBM bound): lookup in
 //                     shared memory, hits -> per-CTA count / latest-position arrays (shared
 //                     atomics), misses -> 1 Mi bucket counters in L2 + a per-warp miss count;
@@ -48,6 +48,14 @@ __device__ __forceinline__ unsigned long long hh_mix(unsigned long long z) {
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
     return z ^ (z >> 31);
 }
+
+// lookup image / miss buckets: one 64-bit multiply (Fibonacci hashing); different bit ranges of
+// the product index the image (top bits) and the buckets
+__device__ __forceinline__ unsigned long long hh_hash(long long k) {
+    return (unsigned long long)k * 0x9e3779b97f4a7c15ull;
+}
+__device__ __forceinline__ unsigned hh_lut_slot(unsigned long long h, int lbits) { return (unsigned)(h >> (64 - lbits)); }
+__device__ __forceinline__ unsigned hh_bucket(unsigned long long h) { return (unsigned)(h >> 21) & (kHHBuckets - 1); }
 
 __global__ void k_hh_fill(long long* p, long n, long long v) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -92,67 +100,118 @@ __device__ __forceinline__ int hh_block_scan(int v, int* s_w32) {
     return wid > 0 ? v + before : v;
 }
 
-// One CTA.  cand_key[0 .. ncand): the C most frequent sampled items (ties by table slot);
-// lut_key / lut_val: linear-probing image (L slots, L = 2 C) mapping a candidate to its index.
-__global__ void __launch_bounds__(1024) k_hh_select(const long long* __restrict__ tabkey,
-                                                    const unsigned* __restrict__ tabcnt, int C,
-                                                    long long* cand_key, long long* lut_key,
-                                                    unsigned short* lut_val, int L, HHStatus* status) {
-    __shared__ int s_hist[1024];
-    __shared__ int s_w32[32];
-    __shared__ int s_tstar, s_above, s_quota, s_run_gt, s_run_eq;
-    const int tid = threadIdx.x;
-    s_hist[tid] = 0;
+// Candidate selection: the C most frequent sampled items, ties by table slot (deterministic).
+//   k_hh_hist    histogram of the sample counts (saturated at 1023)
+//   k_hh_thresh  t* = the count at which the cumulative histogram (from the top) reaches C
+//   k_hh_chunks  per 4096-slot chunk: entries above t* / equal to t*
+//   k_hh_place   candidates written in slot order: all entries above t*, then the first
+//                C - #above entries equal to t*
+//   k_hh_lut     linear-probing lookup image (L = 2 C slots) candidate -> index
+struct HHSel { int tstar, above, quota, pad; };
+constexpr int kHHChunk = 4096;
+constexpr int kHHNChunk = kHHTabSlots / kHHChunk;
+
+__global__ void __launch_bounds__(1024) k_hh_hist(const unsigned* __restrict__ tabcnt, unsigned* hist) {
+    __shared__ unsigned s_hist[1024];
+    s_hist[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = tid; i < kHHTabSlots; i += 1024) {
-        const unsigned c = tabcnt[i];
-        if (c) atomicAdd(&s_hist[c < 1023u ? c : 1023u], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int cum = 0, tstar = 0, above = 0;
-        for (int t = 1023; t >= 1; --t) {
-            if (cum + s_hist[t] >= C) { tstar = t; above = cum; break; }
-            cum += s_hist[t];
-            above = cum;
-        }
-        s_tstar = tstar; s_above = above;
-        s_quota = tstar > 0 ? C - above : 0;   // how many of the entries == tstar are taken
-        s_run_gt = 0; s_run_eq = 0;
-    }
-    __syncthreads();
-    const int tstar = s_tstar, above = s_above, quota = s_quota;
-    // counts above 1023 land in the last histogram bin: they compare as 1023 here as well
-    for (int base = 0; base < kHHTabSlots; base += 4096) {
-        const int i0 = base + tid * 4;
-        const uint4 c4 = *reinterpret_cast<const uint4*>(tabcnt + i0);
+    for (long i = (long)blockIdx.x * 1024 + threadIdx.x; i < kHHTabSlots / 4; i += (long)gridDim.x * 1024) {
+        const uint4 c4 = reinterpret_cast<const uint4*>(tabcnt)[i];
         const unsigned cc[4] = {c4.x, c4.y, c4.z, c4.w};
-        int gt = 0, eq = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = (int)(cc[k] < 1023u ? cc[k] : 1023u);
-            gt += c > tstar ? 1 : 0;
-            eq += (tstar > 0 && c == tstar) ? 1 : 0;
-        }
-        const int pk = hh_block_scan((gt << 16) | eq, s_w32);   // <= 4096 per field
-        int at_gt = s_run_gt + (pk >> 16) - gt, at_eq = s_run_eq + (pk & 0xffff) - eq;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = (int)(cc[k] < 1023u ? cc[k] : 1023u);
-            if (c > tstar) cand_key[at_gt++] = tabkey[i0 + k];
-            else if (tstar > 0 && c == tstar) { if (at_eq < quota) cand_key[above + at_eq] = tabkey[i0 + k]; ++at_eq; }
-        }
-        __syncthreads();
-        if (tid == 1023) { s_run_gt += pk >> 16; s_run_eq += pk & 0xffff; }
-        __syncthreads();
+        for (int k = 0; k < 4; ++k) if (cc[k]) atomicAdd(&s_hist[cc[k] < 1023u ? cc[k] : 1023u], 1u);
     }
-    const int total_eq = s_run_eq;
-    const int ncand = above + (total_eq < quota ? total_eq : quota);
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+__global__ void k_hh_thresh(const unsigned* __restrict__ hist, int C, HHSel* sel) {
+    if (threadIdx.x || blockIdx.x) return;
+    int cum = 0, tstar = 0, above = 0;
+    for (int t = 1023; t >= 1; --t) {
+        if (cum + (int)hist[t] >= C) { tstar = t; above = cum; break; }
+        cum += (int)hist[t];
+        above = cum;
+    }
+    sel->tstar = tstar; sel->above = above;
+    sel->quota = tstar > 0 ? C - above : 0;   // how many of the entries == tstar are taken
+}
+
+// counts above 1023 sit in the last histogram bin: they compare as 1023 here as well
+__device__ __forceinline__ void hh_classify4(const unsigned* tabcnt, int i0, int tstar, unsigned* cc,
+                                             int& gt, int& eq) {
+    const uint4 c4 = *reinterpret_cast<const uint4*>(tabcnt + i0);
+    cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
+    gt = 0; eq = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cc[k] = cc[k] < 1023u ? cc[k] : 1023u;
+        gt += (int)cc[k] > tstar ? 1 : 0;
+        eq += (tstar > 0 && (int)cc[k] == tstar) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_hh_chunks(const unsigned* __restrict__ tabcnt,
+                                                    const HHSel* __restrict__ sel, int* chunk_gt,
+                                                    int* chunk_eq) {
+    __shared__ int s_w32[32];
+    unsigned cc[4];
+    int gt, eq;
+    hh_classify4(tabcnt, blockIdx.x * kHHChunk + threadIdx.x * 4, sel->tstar, cc, gt, eq);
+    const int pk = hh_block_scan((gt << 16) | eq, s_w32);   // <= 4096 per field
+    if (threadIdx.x == 1023) { chunk_gt[blockIdx.x] = pk >> 16; chunk_eq[blockIdx.x] = pk & 0xffff; }
+}
+
+__global__ void __launch_bounds__(1024) k_hh_place(const long long* __restrict__ tabkey,
+                                                   const unsigned* __restrict__ tabcnt,
+                                                   const HHSel* __restrict__ sel,
+                                                   const int* __restrict__ chunk_gt,
+                                                   const int* __restrict__ chunk_eq, long long* cand_key) {
+    __shared__ int s_w32[32];
+    __shared__ int s_pre[2];
+    const int tid = threadIdx.x, ch = blockIdx.x;
+    const int tstar = sel->tstar, above = sel->above, quota = sel->quota;
+    // entries above / equal in the chunks before this one
+    int pg = 0, pe = 0;
+    for (int j = tid; j < ch; j += 1024) { pg += chunk_gt[j]; pe += chunk_eq[j]; }
+    pg = hh_block_scan(pg, s_w32);
+    if (tid == 1023) s_pre[0] = pg;
+    pe = hh_block_scan(pe, s_w32);
+    if (tid == 1023) s_pre[1] = pe;
+    unsigned cc[4];
+    int gt, eq;
+    const int i0 = ch * kHHChunk + tid * 4;
+    hh_classify4(tabcnt, i0, tstar, cc, gt, eq);
+    const int pk = hh_block_scan((gt << 16) | eq, s_w32);   // (ends with the barrier s_pre needs)
+    __syncthreads();
+    int at_gt = s_pre[0] + (pk >> 16) - gt, at_eq = s_pre[1] + (pk & 0xffff) - eq;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if ((int)cc[k] > tstar) cand_key[at_gt++] = tabkey[i0 + k];
+        else if (tstar > 0 && (int)cc[k] == tstar) {
+            if (at_eq < quota) cand_key[above + at_eq] = tabkey[i0 + k];
+            ++at_eq;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_hh_lut(const long long* __restrict__ cand_key,
+                                                 const HHSel* __restrict__ sel,
+                                                 const int* __restrict__ chunk_eq, long long* lut_key,
+                                                 unsigned short* lut_val, int L, HHStatus* status) {
+    __shared__ int s_w32[32];
+    __shared__ int s_ncand;
+    const int tid = threadIdx.x;
+    int te = 0;
+    for (int j = tid; j < kHHNChunk; j += 1024) te += chunk_eq[j];
+    te = hh_block_scan(te, s_w32);
+    if (tid == 1023) s_ncand = sel->above + (te < sel->quota ? te : sel->quota);
     for (int i = tid; i < L; i += 1024) lut_key[i] = kHHEmpty;
     __syncthreads();
+    const int ncand = s_ncand;
     for (int j = tid; j < ncand; j += 1024) {
         const long long key = cand_key[j];
-        unsigned idx = hash64(key) & (unsigned)(L - 1);
+        unsigned idx = hh_lut_slot(hh_hash(key), 31 - __clz(L));
         for (;;) {
             const long long old = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(&lut_key[idx]),
                                                        (unsigned long long)kHHEmpty, (unsigned long long)key);
@@ -188,6 +247,7 @@ __global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __r
     const long cta_lo = (long)(((__int128)((long)blockIdx.x * kHHWarps) * n) / W);
     const long lo = (long)(((__int128)w * n) / W), hi = (long)(((__int128)(w + 1) * n) / W);
     const unsigned lmask = (unsigned)L - 1u;
+    const int lbits = 31 - __clz(L);
     unsigned long long nmiss = 0;
     unsigned long long out = collect ? miss_off[w] : 0ull;
     constexpr int U = 4;
@@ -203,8 +263,9 @@ __global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __r
             const long i = base + u * 32 + lane;
             const bool valid = i < hi;
             int v = -1;
+            const unsigned long long h = hh_hash(key[u]);
             if (valid && key[u] != kHHEmpty) {
-                unsigned idx = hash64(key[u]) & lmask;
+                unsigned idx = hh_lut_slot(h, lbits);
                 for (;;) {
                     const long long k = s_key[idx];
                     if (k == key[u]) { v = s_val[idx]; break; }
@@ -218,7 +279,7 @@ __global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __r
                     atomicAdd(&s_cnt[v], 1u);
                     atomicMax(&s_last[v], (unsigned)(i - cta_lo) + 1u);
                 } else if (miss) {
-                    atomicAdd(&buckets[(unsigned)(hh_mix((unsigned long long)key[u]) >> 40) & (kHHBuckets - 1)], 1u);
+                    atomicAdd(&buckets[hh_bucket(h)], 1u);
                     ++nmiss;
                 }
             } else {
@@ -263,57 +324,68 @@ __global__ void __launch_bounds__(1024) k_hh_scan(const unsigned long long* warp
     for (int k = 0; k < per; ++k) { int i = tid * per + k; if (i < W) { miss_off[i] = run; run += warp_miss[i]; } }
 }
 
-// One CTA: exact candidate counts -> sorted -> the batch's summary written into `tmp` (a full
-// state image: slot i = list position i, hash map included).
-__global__ void __launch_bounds__(1024) k_hh_finish(const unsigned* __restrict__ rows_cnt,
-                                                    const unsigned* __restrict__ rows_last, int G, int C,
+// Exact count and latest stream position of every candidate (sum / max over the CTAs of the
+// counting pass), the number of misses and the fullest miss bucket.  Grid-stride, any grid.
+__global__ void __launch_bounds__(256) k_hh_reduce(const unsigned* __restrict__ rows_cnt,
+                                                   const unsigned* __restrict__ rows_last, int G, int C,
+                                                   const unsigned* __restrict__ buckets,
+                                                   const unsigned long long* __restrict__ warp_miss,
+                                                   long n, long base_seen, long long* cand_cnt,
+                                                   long long* cand_last, HHStatus* status) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    long* s_lo = reinterpret_cast<long*>(sm);   // [G] first element of every counting CTA
+    const long W = (long)G * kHHWarps;
+    for (int g = threadIdx.x; g < G; g += blockDim.x)
+        s_lo[g] = (long)(((__int128)((long)g * kHHWarps) * n) / W);
+    __syncthreads();
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+    for (long c = tid; c < C; c += nthr) {
+        long long cnt = 0, last = -1;
+        for (int g = 0; g < G; ++g) {
+            const unsigned rc = rows_cnt[(size_t)g * C + c], rl = rows_last[(size_t)g * C + c];
+            cnt += rc;
+            const long long p = rc ? base_seen + s_lo[g] + (long long)rl - 1 : -1;
+            last = p > last ? p : last;
+        }
+        cand_cnt[c] = cnt;
+        cand_last[c] = last;
+    }
+    unsigned long long oth = 0;
+    unsigned emax = 0;
+    for (long i = tid; i < W; i += nthr) oth += warp_miss[i];
+    for (long i = tid; i < kHHBuckets; i += nthr) { const unsigned b = buckets[i]; emax = b > emax ? b : emax; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        oth += __shfl_xor_sync(CRICK_FULL, oth, d);
+        const unsigned o = __shfl_xor_sync(CRICK_FULL, emax, d);
+        emax = o > emax ? o : emax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (oth) atomicAdd(reinterpret_cast<unsigned long long*>(&status->others), oth);
+        if (emax) atomicMax(reinterpret_cast<unsigned long long*>(&status->emax), (unsigned long long)emax);
+    }
+}
+
+// One CTA: the candidates sorted by exact count -> the batch's summary written into `tmp` (a
+// full state image: slot i = list position i, hash map included).
+__global__ void __launch_bounds__(1024) k_hh_finish(const long long* __restrict__ cand_cnt,
+                                                    const long long* __restrict__ cand_last, int C,
                                                     const long long* __restrict__ cand_key,
-                                                    const unsigned* __restrict__ buckets,
-                                                    const unsigned long long* __restrict__ warp_miss,
                                                     long n, long base_seen, unsigned char* tmp, long cap,
                                                     int hcap, HHStatus* status) {
     extern __shared__ __align__(16) unsigned char sm[];
     long long* kc = reinterpret_cast<long long*>(sm);   // [C] counts
     long long* kl = kc + C;                             // [C] latest positions
     int* ks = reinterpret_cast<int*>(kl + C);           // [C] candidate index
-    __shared__ unsigned long long s_red[1024];
-    __shared__ long long s_others, s_emax;
     __shared__ int s_kept;
     const int tid = threadIdx.x;
     const int ncand = status->ncand;
-    const long W = (long)G * kHHWarps;
     for (int c = tid; c < C; c += 1024) {
-        long long cnt = 0, last = -1;
-        if (c < ncand) {
-            for (int g = 0; g < G; ++g) {
-                const unsigned rc = rows_cnt[(size_t)g * C + c];
-                if (rc) {
-                    cnt += rc;
-                    const long cta_lo = (long)(((__int128)((long)g * kHHWarps) * n) / W);
-                    const long long p = base_seen + cta_lo + (long long)rows_last[(size_t)g * C + c] - 1;
-                    last = p > last ? p : last;
-                }
-            }
-        }
+        const long long cnt = c < ncand ? cand_cnt[c] : 0;
         kc[c] = cnt > 0 ? cnt : -1;          // unused slots sort to the end
-        kl[c] = cnt > 0 ? last : 0x7fffffffffffffffll;
+        kl[c] = cnt > 0 ? cand_last[c] : 0x7fffffffffffffffll;
         ks[c] = c;
     }
-    unsigned long long oth = 0, emax = 0;
-    for (long i = tid; i < W; i += 1024) oth += warp_miss[i];
-    for (int i = tid; i < kHHBuckets; i += 1024) { unsigned b = buckets[i]; emax = b > emax ? b : emax; }
-    s_red[tid] = oth;
-    __syncthreads();
-    for (int d = 512; d > 0; d >>= 1) { if (tid < d) s_red[tid] += s_red[tid + d]; __syncthreads(); }
-    if (tid == 0) s_others = (long long)s_red[0];
-    __syncthreads();
-    s_red[tid] = emax;
-    __syncthreads();
-    for (int d = 512; d > 0; d >>= 1) {
-        if (tid < d) s_red[tid] = s_red[tid] > s_red[tid + d] ? s_red[tid] : s_red[tid + d];
-        __syncthreads();
-    }
-    if (tid == 0) s_emax = (long long)s_red[0];
     __syncthreads();
     // bitonic sort by (count desc, latest position asc, index asc)
     for (int k = 2; k <= C; k <<= 1) {
@@ -340,7 +412,7 @@ __global__ void __launch_bounds__(1024) k_hh_finish(const unsigned* __restrict__
     }
     __syncthreads();
     const int K = s_kept;
-    const long long others = s_others;
+    const long long others = status->others, s_emax = status->emax;
     // bound for every item that is not kept: the next candidate's exact count, or (for items
     // that were never candidates) the fullest miss bucket -- unless the misses are replayed
     const bool replay = others <= kHHMissCap;
