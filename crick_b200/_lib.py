@@ -105,6 +105,9 @@ _SIG = {
     "crick_spsv_update": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
     "crick_spsv_merge": (c_int, [_P, _P, c_int]),
     "crick_spsv_set_state": (c_int, [_P, _P, c_int64]),
+    "crick_spsv_record_int64s": (c_int64, [_P]),
+    "crick_spsv_export_record": (c_int, [_P, _P, _P]),
+    "crick_spsv_merge_records": (c_int, [_P, _P, c_int, _P]),
     "crick_spsv_size": (c_int64, [_P]),
     "crick_spsv_capacity": (c_int64, [_P]),
     "crick_spsv_counters": (c_int64, [_P, _P, c_int64]),

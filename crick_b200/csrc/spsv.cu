@@ -453,6 +453,51 @@ __global__ void k_spsv_init(unsigned char* state, long cap, int hcap, size_t str
     }
 }
 
+// Multi-GPU tail: a summary travels as the fixed-size record
+// [size, 0, (item, count, error) x capacity] (int64, list order, zero padded) ...
+__global__ void k_spsv_export(unsigned char* state, long cap, int hcap, long long* out) {
+    SpsvView g = spsv_carve(state, cap, hcap);
+    const long n = g.hdr->size;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 + 3 * cap;
+         i += (long)gridDim.x * blockDim.x) {
+        long long v = 0;
+        if (i == 0) v = n;
+        else if (i >= 2) {
+            const long j = (i - 2) / 3;
+            const int f = (int)((i - 2) % 3);
+            if (j < n) { const int sl = g.order[j]; v = f == 0 ? g.item[sl] : f == 1 ? g.count[sl] : g.error[sl]; }
+        }
+        out[i] = v;
+    }
+}
+
+// ... and is rebuilt on the receiving side as the state set_state (:253-286) would produce from
+// those counters (slot i = list position i), hash map included, by one CTA in parallel.
+__global__ void __launch_bounds__(1024) k_spsv_from_record(unsigned char* tmp, long cap, int hcap,
+                                                           const long long* __restrict__ rec) {
+    SpsvView g = spsv_carve(tmp, cap, hcap);
+    const int tid = threadIdx.x;
+    long n = rec[0];
+    n = n < 0 ? 0 : (n > cap ? cap : n);
+    for (int i = tid; i < hcap; i += 1024) g.hval[i] = -1;
+    __syncthreads();
+    for (long i = tid; i < n; i += 1024) {
+        const long long key = rec[2 + 3 * i];
+        g.item[i] = key; g.count[i] = rec[3 + 3 * i]; g.error[i] = rec[4 + 3 * i]; g.last[i] = i;
+        g.order[i] = (int)i; g.pos[i] = (int)i;
+        unsigned idx = hash64(key) & (unsigned)(hcap - 1);
+        for (;;) {
+            if (atomicCAS(&g.hval[idx], -1, (int)i) == -1) { g.hkey[idx] = key; break; }
+            idx = (idx + 1) & (unsigned)(hcap - 1);
+        }
+    }
+    if (tid == 0) {
+        SpsvHdr h; h.capacity = cap; h.size = n; h.hcap = hcap; h.tomb = 0;
+        h.seen = n; h.mixed = 1; h.pad = 0;
+        *g.hdr = h;
+    }
+}
+
 }  // namespace crick
 
 #include "spsv_hh.cuh"
@@ -819,6 +864,41 @@ int crick_spsv_merge(crick_spsv_t* s, crick_spsv_t* const* others, int n_others)
         if (e != cudaSuccess) return fail("spsv_merge", e);
     }
     return 0;
+}
+
+int64_t crick_spsv_record_int64s(crick_spsv_t* s) { return 2 + 3 * (int64_t)s->cap; }
+
+int crick_spsv_export_record(crick_spsv_t* s, int64_t* dev_out, void* stream) {
+    cudaStream_t st = sp_stream(s, stream);
+    if (sp_drain(s, st)) return -1;
+    count_launch();
+    k_spsv_export<<<8, 256, 0, st>>>(s->d, s->cap, s->hcap, reinterpret_cast<long long*>(dev_out));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail("spsv_export_record", e);
+}
+
+int crick_spsv_merge_records(crick_spsv_t* s, const int64_t* dev_recs, int n_records, void* stream) {
+    if (n_records <= 0) return 0;
+    cudaStream_t st = sp_stream(s, stream);
+    if (sp_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    const size_t stride = spsv_bytes(s->cap, s->hcap);
+    unsigned char* tmp = nullptr;
+    cudaError_t e = cudaMallocAsync(&tmp, stride, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(spsv record)", e);
+    if (s->smem > 48 * 1024)
+        e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+    const int64_t nd = 2 + 3 * (int64_t)s->cap;
+    for (int r = 0; r < n_records && e == cudaSuccess; ++r) {
+        count_launch();
+        k_spsv_from_record<<<1, 1024, 0, st>>>(tmp, s->cap, s->hcap,
+                                               reinterpret_cast<const long long*>(dev_recs + (size_t)r * nd));
+        count_launch();
+        k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, tmp, s->cap, s->hcap, 0, 1);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(tmp, st);
+    return e == cudaSuccess ? 0 : fail("spsv_merge_records", e);
 }
 
 int crick_spsv_set_state(crick_spsv_t* s, const int64_t* counters3, int64_t n) {

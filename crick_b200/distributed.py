@@ -120,6 +120,49 @@ def merge_tdigest_records_host(compression, records):
     return out
 
 
+def spsv_record_from_counters(counters, capacity):
+    """Host-side form of the record ``crick_spsv_export_record`` writes: int64
+    ``[size, 0, (item, count, error) x capacity]`` in list order, zero padded."""
+    rec = np.zeros(2 + 3 * int(capacity), dtype=np.int64)
+    n = len(counters)
+    rec[0] = n
+    if n:
+        body = np.stack([np.asarray(counters[f]).view(np.int64) for f in ("item", "count", "error")], 1)
+        rec[2:2 + 3 * n] = body.ravel()
+    return rec
+
+
+def spsv_counters_from_record(rec):
+    """Inverse of :func:`spsv_record_from_counters`: an (n, 3) int64 array."""
+    n = int(rec[0])
+    return np.asarray(rec[2:2 + 3 * n], dtype=np.int64).reshape(n, 3).copy()
+
+
+def allgather_merge_spsv(sp, group=None):
+    """``SpaceSaving(capacity).merge(*[summary of rank 0, 1, ...])`` on every rank: the fixed
+    24 KB (capacity 1000) int64 records are all-gathered and merged on the device in rank order
+    with the reference's merge (space_saving_stubs.c.in:289-364)."""
+    import torch
+    import torch.distributed as dist
+    from .space_saving import SpaceSaving
+
+    world = dist.get_world_size(group)
+    s = torch.cuda.current_stream()
+    if s.cuda_stream == 0:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+    nd = sp.record_int64s()
+    with torch.cuda.stream(s):
+        rec = torch.empty(nd, dtype=torch.int64, device="cuda")
+        gathered = torch.empty((world, nd), dtype=torch.int64, device="cuda")
+        sp.export_record(rec.data_ptr(), stream=s.cuda_stream)
+        dist.all_gather_into_tensor(gathered.view(-1), rec, group=group)
+        out = SpaceSaving(sp.capacity, sp.dtype)
+        out.merge_records(gathered.data_ptr(), world, stream=s.cuda_stream)
+    s.synchronize()
+    return out
+
+
 def allgather_merge_stats(stats, group=None, backend_device="cuda"):
     """All-gather the 9-double SummaryStats records and merge them in rank order."""
     import torch

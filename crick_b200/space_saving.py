@@ -227,6 +227,20 @@ class SpaceSaving:
         arr = handle_array([s._h for s in args])
         check(lib.crick_spsv_merge(self._h, arr, len(args)), "merge")
 
+    # ---- multi-GPU tail (additions; crick_b200/distributed.py) ----
+    def record_int64s(self):
+        """Length of the fixed-size int64 record ``[size, 0, (item, count, error) x capacity]``."""
+        return int(lib.crick_spsv_record_int64s(self._h))
+
+    def export_record(self, device_ptr, stream=None):
+        check(lib.crick_spsv_export_record(self._h, device_ptr, stream), "export_record")
+
+    def merge_records(self, device_ptr, n_records, stream=None):
+        """Merge `n_records` records (same capacity, device memory) one after the other, each
+        exactly like ``self.merge(other)``."""
+        check(lib.crick_spsv_merge_records(self._h, device_ptr, int(n_records), stream),
+              "merge_records")
+
 
 SpaceSaving.__module__ = "crick.space_saving"
 TopKResult.__module__ = "crick.space_saving"

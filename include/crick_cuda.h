@@ -229,6 +229,14 @@ int crick_spsv_update(crick_spsv_t *s, const int64_t *item, const int64_t *count
                       int mode, void *stream);
 int crick_spsv_merge(crick_spsv_t *s, crick_spsv_t *const *others, int n_others); /* :289-364 */
 int crick_spsv_set_state(crick_spsv_t *s, const int64_t *counters3, int64_t n);   /* :253-286 */
+/* Multi-GPU tail: a summary as the fixed-size int64 record
+ * [size, 0, (item, count, error) x capacity] in list order (device buffer of
+ * crick_spsv_record_int64s() values); merge_records folds `n_records` such records -- all of this
+ * handle's capacity -- into the handle one after the other, each exactly like
+ * spsv_merge(self, other) :289-364 would.  Asynchronous on `stream`. */
+int64_t crick_spsv_record_int64s(crick_spsv_t *s);
+int crick_spsv_export_record(crick_spsv_t *s, int64_t *dev_out, void *stream);
+int crick_spsv_merge_records(crick_spsv_t *s, const int64_t *dev_records, int n_records, void *stream);
 int64_t crick_spsv_size(crick_spsv_t *s);
 int64_t crick_spsv_capacity(crick_spsv_t *s);
 /* int64_counters walk, space_saving.pyx:368-386: out = k x (item, count, error); returns rows */

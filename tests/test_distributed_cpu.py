@@ -49,6 +49,27 @@ for r in range(world):
 e = oracle.restated.TDigest(100)
 e.merge(*exp_parts)
 ok = ok and m.centroids().tobytes() == e.centroids().tobytes() and m.size() == e.size()
+# SpaceSaving: fixed-size int64 records, gathered and merged in rank order
+from crick_b200.distributed import spsv_counters_from_record, spsv_record_from_counters
+items = (rng.zipf(1.2, n) % 5000).astype(np.int64)
+sp = oracle.restated.SpaceSaving(100)
+sp.update(items[lo:hi])
+srec = torch.from_numpy(spsv_record_from_counters(sp.counters(), 100))
+sg = gather_records(srec).numpy()
+ok = ok and sg.shape == (world, 302) and np.array_equal(sg[rank], srec.numpy())
+sm_ = oracle.restated.SpaceSaving(100)
+for r in range(world):
+    c3 = spsv_counters_from_record(sg[r])
+    p = oracle.restated.SpaceSaving(100)
+    st_ = np.zeros(len(c3), dtype=oracle.COUNTER_DTYPE)
+    st_["item"], st_["count"], st_["error"] = c3[:, 0], c3[:, 1], c3[:, 2]
+    p.set_state(st_)
+    sm_.merge(p)
+se = oracle.restated.SpaceSaving(100)
+for r in range(world):
+    a, b = shard_bounds(n, r, world)
+    q = oracle.restated.SpaceSaving(100); q.update(items[a:b]); se.merge(q)
+ok = ok and sm_.counters().tobytes() == se.counters().tobytes()
 res = torch.tensor([1 if ok else 0])
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -339,3 +339,57 @@ def test_spsv_counting_path_is_a_valid_summary(cb, kind):
         # a second batch, then a merge with a replayed summary: still valid for the union
         s.update(items[: n // 2].copy(), mode=3)
         _assert_valid_summary(s.counters(), np.concatenate([items, items[: n // 2]]), cap)
+
+
+def test_spsv_records_merge_like_the_reference(cb):
+    """Multi-GPU tail: records exported on the device, concatenated as an
+    all-gather would deliver them, and merged in rank order must equal
+    SpaceSaving(cap).merge(rank0, rank1, ...) of the reference, list order included -- full and
+    non-full summaries, overlapping and disjoint items."""
+    rng = np.random.default_rng(21)
+    for cap, lens in ((50, (4000, 30, 2500, 0)), (1000, (300000, 200000))):
+        parts, refs = [], []
+        for k, n in enumerate(lens):
+            x = (rng.zipf(1.2, n) % (400 if k % 2 else 3000)).astype(np.int64) + 17 * k
+            s, o = cb.SpaceSaving(cap, "i8"), R.SpaceSaving(cap)
+            if n:
+                s.update(x, mode=1)
+                o.update(x)
+            parts.append(s)
+            refs.append(o)
+        nd = parts[0].record_int64s()
+        assert nd == 2 + 3 * cap
+        buf = cb.DeviceArray((len(parts), nd), "i8")
+        for k, s in enumerate(parts):
+            s.export_record(buf.ptr + 8 * nd * k)
+        out, ref = cb.SpaceSaving(cap, "i8"), R.SpaceSaving(cap)
+        out.merge_records(buf.ptr, len(parts))
+        ref.merge(*refs)
+        assert out.counters().tobytes() == ref.counters().tobytes(), cap
+        rec0 = buf.to_numpy()[0]
+        assert rec0[0] == len(refs[0].counters())
+        assert np.array_equal(rec0[2:2 + 3 * int(rec0[0])].reshape(-1, 3),
+                              np.stack([refs[0].counters()[f] for f in ("item", "count", "error")], 1))
+
+
+def test_spsv_allgather_world1_nccl(cb):
+    import torch
+    import torch.distributed as dist
+    from crick_b200.distributed import allgather_merge_spsv
+    rng = np.random.default_rng(5)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29618", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        x = rng.zipf(1.3, 100000).astype(np.int64)
+        s, o = cb.SpaceSaving(100, "i8"), R.SpaceSaving(100)
+        s.update(x, mode=1)
+        o.update(x)
+        m = allgather_merge_spsv(s)
+        mo = R.SpaceSaving(100)
+        mo.merge(o)
+        assert m.counters().tobytes() == mo.counters().tobytes()
+    finally:
+        if created:
+            dist.destroy_process_group()
