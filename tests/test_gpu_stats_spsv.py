@@ -393,3 +393,17 @@ def test_spsv_allgather_world1_nccl(cb):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_spsv_counting_path_degenerate_streams(cb):
+    """One distinct item, two alternating items, and every element distinct but fewer than the
+    capacity: the counting path (auto, >= 4 Mi elements) must still give the reference's bits."""
+    n = 1 << 22
+    streams = [np.full(n, 7, dtype=np.int64),
+               np.where(np.arange(n) % 3 == 0, -5, 11).astype(np.int64),
+               np.concatenate([np.arange(900, dtype=np.int64), np.full(n - 900, 3, dtype=np.int64)])]
+    for items in streams:
+        s, o = cb.SpaceSaving(1000, "i8"), R.SpaceSaving(1000)
+        s.update(cb.DeviceArray.from_numpy(items))
+        o.update(items)
+        assert s.counters().tobytes() == o.counters().tobytes()
