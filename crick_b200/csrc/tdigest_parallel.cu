@@ -38,6 +38,7 @@
 #include "tdigest_ref.cuh"
 
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -55,6 +56,23 @@ __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.w
 __device__ __forceinline__ void grid_dep_launch() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// cudaFuncSetAttribute costs a few microseconds of host time per call and an update makes four:
+// remember the largest dynamic shared-memory size granted per (device, kernel).
+template <typename K>
+static cudaError_t need_smem(K kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kernel));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = granted.find(key);
+    if (it != granted.end() && it->second >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) granted[key] = bytes;
+    return e;
+}
+
 static bool pdl_enabled() {
     static const bool on = [] {
         const char* env = getenv("CRICK_PDL");
@@ -339,7 +357,7 @@ static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double
     *skeys = keys; *svals = vals;
     if (nrun > 1) {
         const size_t msm = (size_t)S * 8;
-        e = cudaFuncSetAttribute(k_merge_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+        e = need_smem(k_merge_runs, msm);
         if (e != cudaSuccess) return e;
         count_launch();
         e = launch_dep(k_merge_runs, dim3((unsigned)(S / kMergeThreads)), dim3(kMergeThreads), msm, st,
@@ -1542,7 +1560,7 @@ static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, c
     cudaError_t e = sort_sample(L.sx, L.sw, L.sx2, L.sw2, S, src, st, &skeys, &svals);
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)S * 8 + 2 * kTabBytes;   // cumulative sample weights + 2 candidate tables
-    e = cudaFuncSetAttribute(k_make_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = need_smem(k_make_edges, smem);
     if (e != cudaSuccess) return e;
     count_launch();
     return launch_dep(k_make_edges, dim3(1), dim3(1024), smem, st, L.hdr, skeys, svals, L.edges, L.tab,
@@ -1643,8 +1661,7 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
     }
 #define CRICK_LAUNCH_ACC_S(HW, VC, SG, SS)                                                        \
     do {                                                                                          \
-        e = cudaFuncSetAttribute(k_bin_accumulate<HW, VC, SG, SS>,                                \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        e = need_smem(k_bin_accumulate<HW, VC, SG, SS>, smem);                                    \
         if (e != cudaSuccess) return e;                                                           \
         count_launch();                                                                           \
         e = launch_dep(k_bin_accumulate<HW, VC, SG, SS>, dim3(grid), dim3(block), smem, st, X, W, \
@@ -1691,8 +1708,7 @@ cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_
     size_t wsb = fin_ws_bytes(v.cap, mmax);
     int use_smem = wsb <= 180 * 1024;
     size_t smem = use_smem ? wsb : 0;
-    cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(use_smem ? wsb : 0));
+    cudaError_t e = need_smem(k_finalize, use_smem ? wsb : 0);
     if (e != cudaSuccess) return e;
     count_launch();
     return launch_dep(k_finalize, dim3(1), dim3(1024), smem, st, v, d, L.hdr, L.edges, L.partial,
