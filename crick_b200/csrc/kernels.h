@@ -64,7 +64,7 @@ cudaError_t parallel_accumulate(const BatchView& v, const double* X, const doubl
                                 long n, void* scratch, int sm_count, cudaStream_t st, int first,
                                 StatsPart* stats_parts, long idx_base);
 cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_count,
-                              cudaStream_t st);
+                              cudaStream_t st, bool honor_badw = false);
 // debug/test accessor: copy the bucket edges of the last parallel update to the host
 int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st);
 int parallel_debug_buckets(void* scratch, double comp, int sm_count, double* out_w, double* out_s,

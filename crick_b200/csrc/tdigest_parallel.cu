@@ -1262,13 +1262,17 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
                                                    const double* __restrict__ edges,
                                                    const double2* __restrict__ partial,
                                                    const double2* __restrict__ minmax,
-                                                   unsigned char* gws, int mmax, int use_smem) {
+                                                   unsigned char* gws, int mmax, int use_smem,
+                                                   int honor_badw) {
     __shared__ int s_scan[1024 + 1];
     __shared__ double s_mm[2];
     __shared__ int s_m;
     __shared__ double s_W;
     const int tid = threadIdx.x;
     grid_dep_wait();          // the partials of k_bin_accumulate
+    // validated update (tdigest.pyx:304-305): the digest is only touched when every weight
+    // passed; the host reads the same flag after this kernel has been enqueued
+    if (honor_badw && hdr->badw) return;
     const int E = hdr->E;
     const int B = E + 1;
     const int ncta = hdr->ncta;
@@ -1702,7 +1706,7 @@ cudaError_t parallel_accumulate(const BatchView& v, const double* X, const doubl
 }
 
 cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_count,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool honor_badw) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     const int mmax = mmax_for(v.comp);
     size_t wsb = fin_ws_bytes(v.cap, mmax);
@@ -1712,7 +1716,7 @@ cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_
     if (e != cudaSuccess) return e;
     count_launch();
     return launch_dep(k_finalize, dim3(1), dim3(1024), smem, st, v, d, L.hdr, L.edges, L.partial,
-                      L.minmax, L.fin, mmax, use_smem);
+                      L.minmax, L.fin, mmax, use_smem, honor_badw ? 1 : 0);
 }
 
 // reads the "some weight is not > 0 and finite" flag of the accumulate calls since the last
@@ -1736,12 +1740,12 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
     if (e != cudaSuccess) return e;
     e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, stats_parts, 0);
     if (e != cudaSuccess) return e;
-    if (bad_weights && W) {
-        // validated update: the digest is only touched when every weight passed
-        e = parallel_bad_weights(scratch, st, bad_weights);
-        if (e != cudaSuccess || *bad_weights) return e;
-    }
-    return parallel_finalize(v, d, scratch, sm_count, st);
+    // validated update: k_finalize leaves the digest alone when the pass flagged a weight; the
+    // flag is read back once everything is enqueued (one synchronisation, at the end)
+    const bool checked = bad_weights && W;
+    e = parallel_finalize(v, d, scratch, sm_count, st, checked);
+    if (e == cudaSuccess && checked) e = parallel_bad_weights(scratch, st, bad_weights);
+    return e;
 }
 
 // test hook: per-bucket (sum w, sum w*x) of the last update, reduced over CTAs in the same
