@@ -434,39 +434,47 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     grid_dep_launch();        // k_bin_accumulate may take the other SMs and clear its tables
     grid_dep_wait();          // the sorted sample
     double* cw = reinterpret_cast<double*>(smem_raw);
-    unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + S * 8);   // [2][kTabLen]
+    unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + (S + 1024) * 8);   // [2][kTabLen]
     // a. inclusive scan of the sample weights (fixed order => deterministic).  Warp w owns the
-    // S / 32 consecutive elements [w * S/32, ...): 16-deep coalesced loads, one shuffle scan per
-    // 32 elements, the chunk totals chained, then the offsets of the 32 warp totals.
+    // S / 32 consecutive elements [w * S/32, ...) and every lane `per` = S / 1024 consecutive
+    // ones of them: coalesced loads go through the warp's slice of shared memory (one pad word
+    // per `per` elements, so both the row-wise writes and the lane-wise reads are conflict
+    // free), a serial prefix per lane, ONE shuffle scan of the lane totals (16 scans of 32
+    // elements each cost 10 k cycles of SHFL throughput), the offsets of the 32 warp totals.
+    // cw stays in the padded layout: element i lives at CW(i).
+    const int seg = (int)(S >> 5);                 // 32 .. 512 (S is a power of two >= 1024)
+    const int per = seg >> 5;                      // 1 .. 16
+    const int lseg = 31 - __clz(seg), lper = 31 - __clz(per);
+    auto CW = [&](long i) -> double& {
+        const int p_ = (int)(i & (seg - 1));
+        return cw[(i >> lseg) * (seg + 32) + p_ + (p_ >> lper)];
+    };
     {
         const int lane = tid & 31, wid = tid >> 5;
-        const int seg = (int)(S >> 5);                 // 32 .. 512 (S is a power of two >= 1024)
         const double* src = sw + (long)wid * seg;
+        double* wbuf = cw + (long)wid * (seg + 32);
         double r[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) r[k] = k * 32 < seg ? src[k * 32 + lane] : 0.0;
-        // the 16 chunk scans are independent (the shuffles pipeline); the chunk totals are
-        // then chained
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k * 32 < seg) {                    // uniform
-                    double o = shfl_up_d(r[k], d);
-                    if (lane >= d) r[k] += o;
-                }
-            }
-        }
-        double carry = 0.0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            if (k * 32 < seg) {
-                const double tot = shfl_d(r[k], 31);
-                r[k] += carry;
-                carry += tot;
-            }
+            const int p_ = k * 32 + lane;
+            if (k * 32 < seg) wbuf[p_ + (p_ >> lper)] = r[k];
         }
-        if (lane == 0) s_wd[wid] = carry;
+        __syncwarp();
+        const int b0 = lane * (per + 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = k < per ? wbuf[b0 + k] : 0.0;
+#pragma unroll
+        for (int k = 1; k < 16; ++k) r[k] += r[k - 1];          // r[15] = the lane's total
+        double inc = r[15];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double o = shfl_up_d(inc, d);
+            if (lane >= d) inc += o;
+        }
+        const double lane_before = inc - r[15];
+        if (lane == 31) s_wd[wid] = inc;
         __syncthreads();
         double t = s_wd[lane];
 #pragma unroll
@@ -474,13 +482,12 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
             double o = shfl_up_d(t, d);
             if (lane >= d) t += o;
         }
-        const double before = wid > 0 ? shfl_d(t, wid - 1) : 0.0;
-        double* mine = cw + (long)wid * seg;
+        const double before = (wid > 0 ? shfl_d(t, wid - 1) : 0.0) + lane_before;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) if (k * 32 < seg) mine[k * 32 + lane] = before + r[k];
+        for (int k = 0; k < 16; ++k) if (k < per) wbuf[b0 + k] = before + r[k];
     }
     __syncthreads();
-    const double Wt = cw[S - 1];
+    const double Wt = CW(S - 1);
     const int c = (int)ceil(comp);
     const int E0 = ov * c - 1;
     // b. raw edges at the k-scale grid
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         long lo = 0, hi = S - 1;                                   // first i with cw[i] >= target
         while (lo < hi) {
             long mid = (lo + hi) >> 1;
-            if (cw[mid] < target) lo = mid + 1; else hi = mid;
+            if (CW(mid) < target) lo = mid + 1; else hi = mid;
         }
         s_raw[j] = sx[lo];
     }
@@ -541,43 +548,54 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         inv = (double)(kNC - 2) / width;
         lin_ok = En >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv);
     }
-    // per grid: count the edges of every cell (edges are sorted and cell() is monotone), then
-    // an inclusive scan over the cells: tab[c] = sum of counts of cells < c
+    // count the edges of every cell (edges are sorted and cell() is monotone) for both grids in
+    // one pass -- grid 0 in the low, grid 1 in the high half-word of the same counter -- then an
+    // inclusive scan over the cells: tab[c] = sum of counts of cells < c
     int* s_cnt2 = reinterpret_cast<int*>(s_buf);
     constexpr int kPer = (kTabLen + 1023) / 1024;   // cells per thread
-    for (int g = 0; g < 2; ++g) {
-        unsigned short* out = s_tab + g * kTabLen;
-        if (g == 1 && !lin_ok) break;
-        __syncthreads();                             // s_buf is free (phase c / previous grid)
+    {
+        __syncthreads();                             // s_buf is free (phase c)
         for (int cc = tid; cc < kTabLen + 6; cc += blockDim.x) s_cnt2[cc] = 0;
         __syncthreads();
         for (int j = tid; j < En; j += blockDim.x) {
-            int ce_ = g == 0 ? cell_key(s_edge[j], kbase, shift) : cell_lin(s_edge[j], x0, inv);
-            atomicAdd(&s_cnt2[ce_ + 1], 1);          // counted at index cell + 1
+            const double e = s_edge[j];
+            atomicAdd(&s_cnt2[cell_key(e, kbase, shift) + 1], 1);          // counted at index cell + 1
+            if (lin_ok) atomicAdd(&s_cnt2[cell_lin(e, x0, inv) + 1], 1 << 16);
         }
         __syncthreads();
-        int local = 0, lmax = 0, run = 0;
-        int vals[kPer];
+        int local[2] = {0, 0}, lmax[2] = {0, 0}, run[2] = {0, 0};
+        int vals[2][kPer];
         const int c0 = tid * kPer;
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
-            int cc = c0 + k;
-            int m = cc < kTabLen ? s_cnt2[cc] : 0;    // = edges in cell cc - 1
-            int lg = m > 0 ? 32 - __clz(m) : 0;       // compares of a binary search over m + 1 outcomes
-            local += m * lg;
-            lmax = m > lmax ? m : lmax;
-            run += m;
-            vals[k] = run;
+            const int cc = c0 + k;
+            const int mm = cc < kTabLen ? s_cnt2[cc] : 0;    // = edges in cell cc - 1, both grids
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int m = g == 0 ? (mm & 0xffff) : (mm >> 16);
+                const int lg = m > 0 ? 32 - __clz(m) : 0;    // compares of a binary search over m + 1 outcomes
+                local[g] += m * lg;
+                lmax[g] = m > lmax[g] ? m : lmax[g];
+                run[g] += m;
+                vals[g][k] = run[g];
+            }
         }
-        const int off = block_scan_incl<int>(run, s_wi) - run;
+        const int pk = block_scan_incl<int>(run[0] | (run[1] << 16), s_wi);   // <= 1023 per field
+        const int off0 = (pk & 0xffff) - run[0], off1 = (pk >> 16) - run[1];
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
-            int cc = c0 + k;
-            if (cc < kTabLen) out[cc] = (unsigned short)(off + vals[k]);
+            const int cc = c0 + k;
+            if (cc < kTabLen) {
+                s_tab[cc] = (unsigned short)(off0 + vals[0][k]);
+                s_tab[kTabLen + cc] = (unsigned short)(off1 + vals[1][k]);
+            }
         }
-        local = __reduce_add_sync(CRICK_FULL, local);
-        lmax = __reduce_max_sync(CRICK_FULL, lmax);
-        if ((tid & 31) == 0) { atomicAdd(&s_cost[g], local); atomicMax(&s_kmax[g], lmax); }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int lsum = __reduce_add_sync(CRICK_FULL, local[g]);
+            const int lmx = __reduce_max_sync(CRICK_FULL, lmax[g]);
+            if ((tid & 31) == 0) { atomicAdd(&s_cost[g], lsum); atomicMax(&s_kmax[g], lmx); }
+        }
     }
     __syncthreads();
     int grid = 0;
@@ -1563,7 +1581,7 @@ static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, c
     const double *skeys, *svals;
     cudaError_t e = sort_sample(L.sx, L.sw, L.sx2, L.sw2, S, src, st, &skeys, &svals);
     if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)S * 8 + 2 * kTabBytes;   // cumulative sample weights + 2 candidate tables
+    const size_t smem = (size_t)(S + 1024) * 8 + 2 * kTabBytes;   // cumulative sample weights (padded) + 2 candidate tables
     e = need_smem(k_make_edges, smem);
     if (e != cudaSuccess) return e;
     count_launch();
