@@ -1246,16 +1246,55 @@ __device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp
         while (i < T && __dadd_rn(ws.kend[i], -k1) <= 1.0) ++i;
         nb[p + 1] = i;
     }
+    // Node q (0 <= q < T) stands for "a centroid starts at item q" (q = 0: the first one, with
+    // k1 = 0) and points to the next start nb[q]; T is the sink.  The starts are the nodes on
+    // the path from node 0: marked by pointer jumping (after r rounds: every node within 2^r - 1
+    // steps is marked and cur = nb^(2^r)) instead of one thread walking ~1.3 c dependent links.
+    // Mark = bit 31 of the node's entry; two arrays (cur / nxt) so that no entry is read and
+    // written in the same phase.  (ws.sb holds 4 ints per slot >= 2 (T + 1).)
+    constexpr unsigned kMark = 0x80000000u;
+    unsigned* cur = reinterpret_cast<unsigned*>(nb);
+    unsigned* nxt = cur + (T + 1);
+    if (tid == 0) { cur[T] = (unsigned)T; nxt[T] = (unsigned)T; }
     __syncthreads();
-    if (tid == 0) {
-        ws.start[0] = 0;
-        int nc_ = 1, i = nb[0];
-        while (i < T && nc_ < cap) {
-            ws.start[nc_++] = i;
-            i = nb[i];                       // p = i - 1
+    if (tid == 0) cur[0] |= kMark;
+    __syncthreads();
+    for (int span = 1; span < T; span <<= 1) {
+        for (int q = tid; q < T; q += blockDim.x) {
+            const unsigned v = cur[q];
+            const unsigned tg = v & ~kMark;
+            if ((v & kMark) && tg < (unsigned)T) atomicOr(&cur[tg], kMark);
         }
-        ws.start[nc_] = T;
-        *s_nc = nc_;
+        __syncthreads();
+        for (int q = tid; q < T; q += blockDim.x) {
+            const unsigned v = cur[q];
+            nxt[q] = (v & kMark) | (cur[v & ~kMark] & ~kMark);
+        }
+        __syncthreads();
+        unsigned* t_ = cur; cur = nxt; nxt = t_;
+    }
+    // the marked nodes in increasing order are start[0], start[1], ...; at most `cap` of them
+    // (the sequential chain stops opening centroids once it has `cap`)
+    {
+        __shared__ int s_scan_w[32];
+        __shared__ int s_tot;
+        int run = 0;
+        for (int base = 0; base < T; base += blockDim.x) {
+            const int q = base + tid;
+            const int f = (q < T && (cur[q] & kMark)) ? 1 : 0;
+            const int incl = block_scan_incl<int>(f, s_scan_w);
+            const int at = run + incl - f;
+            if (f && at < cap) ws.start[at] = q;
+            if (tid == (int)blockDim.x - 1) s_tot = incl;
+            __syncthreads();
+            run += s_tot;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int nc_ = run < cap ? run : cap;
+            ws.start[nc_] = T;
+            *s_nc = nc_;
+        }
     }
     __syncthreads();
     const int nc = *s_nc;
@@ -1550,7 +1589,7 @@ cudaError_t launch_merge_records_bulk(const BatchView& v, long d, const double* 
     if (nrec <= 0) return cudaSuccess;
     if (nrec > 64) return cudaErrorInvalidValue;
     int P = 1;
-    while (P < nrec * v.cap) P <<= 1;
+    while (P < nrec * v.cap + 2) P <<= 1;   // (+2: block_merge_sorted keeps 2 (T + 1) ints in ws.sb)
     size_t t = (size_t)v.cap + P;
     size_t smem = (size_t)P * 20 + 16 + (size_t)v.cap * 16 + (size_t)P * 16 + t * 16 + t * 8 + (t + 1) * 4 + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
