@@ -268,7 +268,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_bin_accumulate", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms_per_launch": k_ms, "kernel_share_of_step": (kms.value / ms) if ms else None,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VALUE * n}
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VALUE * n,
+                # SURVEY.md 8d asks for both denominators: the box-measured copy bandwidth above
+                # and the nominal 8 TB/s of HBM3e
+                "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0}
     try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to n
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
