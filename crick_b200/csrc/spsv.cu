@@ -515,6 +515,7 @@ struct crick_spsv {
     std::vector<long long> pi, pc;  // pending scalar adds
     long size_mirror = 0;
     bool mirror_ok = false;
+    bool known_empty = false;        // nothing has been added since new(): seen == 0, size == 0
 };
 
 static cudaStream_t sp_stream(crick_spsv* s, void* stream) {
@@ -659,9 +660,12 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     HHStatus hs = {};
     long base_seen = 0;
     do {
-        // the stream position of this batch's first element
-        e = cudaMemcpyAsync(&base_seen, s->d + offsetof(SpsvHdr, seen), sizeof(long), cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) break;
+        // the stream position of this batch's first element (0 for a summary nothing was added to)
+        const bool fresh = s->known_empty;
+        if (!fresh) {
+            e = cudaMemcpyAsync(&base_seen, s->d + offsetof(SpsvHdr, seen), sizeof(long), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) break;
+        }
         e = cudaMemsetAsync(tabcnt, 0, (size_t)kHHTabSlots * 4, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(buckets, 0, (size_t)kHHBuckets * 4, st);
         if (e != cudaSuccess) break;
@@ -685,7 +689,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         k_hh_lut<<<1, 1024, 0, st>>>(cand, sel, chunk_eq, lutk, lutv, L, dstatus);
         e = cudaFuncSetAttribute(k_hh_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
         if (e != cudaSuccess) break;
-        e = cudaStreamSynchronize(st);           // base_seen has arrived
+        if (!fresh) e = cudaStreamSynchronize(st);           // base_seen has arrived
         if (e != cudaSuccess) break;
         count_launch();
         k_hh_count<<<G, kHHWarps * 32, smem_cnt, st>>>(item, n, lutk, lutv, L, C, rc, rl, buckets, wm, 0,
@@ -703,13 +707,19 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) break;
         if (hs.fallback) break;                  // *done stays false: nothing was changed
-        // fold the batch's summary into the object (spsv_merge)
-        if (s->smem > 48 * 1024)
-            e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
-        if (e != cudaSuccess) break;
-        count_launch();
-        k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, tmp, s->cap, s->hcap, 0, 0);
-        e = cudaGetLastError();
+        // fold the batch's summary into the object (spsv_merge).  Merging into an empty summary
+        // of the same capacity reproduces the other one slot for slot (:330-350 with m1 = 0), so
+        // a fresh object simply takes the image
+        if (fresh) {
+            e = cudaMemcpyAsync(s->d, tmp, stride, cudaMemcpyDeviceToDevice, st);
+        } else {
+            if (s->smem > 48 * 1024)
+                e = cudaFuncSetAttribute(k_spsv_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+            if (e != cudaSuccess) break;
+            count_launch();
+            k_spsv_merge<<<1, 32, s->smem, st>>>(s->d, s->cap, s->hcap, s->use_smem, tmp, s->cap, s->hcap, 0, 0);
+            e = cudaGetLastError();
+        }
         if (e != cudaSuccess) break;
         *done = true;
         if (hs.others > 0 && hs.others <= kHHMissCap) {
@@ -757,6 +767,7 @@ static int sp_drain(crick_spsv* s, cudaStream_t st) {
     cudaFreeAsync(d, st);
     s->pi.clear(); s->pc.clear();
     s->mirror_ok = false;
+    s->known_empty = false;
     return e == cudaSuccess ? 0 : fail("spsv drain", e);
 }
 
@@ -786,6 +797,7 @@ crick_spsv_t* crick_spsv_new(int64_t capacity) {
     s->last = s->own;
     s->size_mirror = 0;
     s->mirror_ok = true;
+    s->known_empty = true;
     return s;
 }
 
@@ -831,6 +843,7 @@ int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count
         }
     }
     if (e == cudaSuccess) e = sp_launch_update(s, di, dc, count_scalar, n, st, mode);
+    s->known_empty = false;
     if (stage) {
         cudaFreeAsync(stage, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -841,7 +854,7 @@ int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count
 int crick_spsv_merge(crick_spsv_t* s, crick_spsv_t* const* others, int n_others) {
     cudaStream_t st = sp_stream(s, nullptr);
     if (sp_drain(s, st)) return -1;
-    s->mirror_ok = false;
+    s->mirror_ok = false; s->known_empty = false;
     for (int i = 0; i < n_others; ++i) {
         crick_spsv* o = others[i];
         if (o == s) return fail_msg("spsv_merge: cannot merge a summary into itself");
@@ -881,7 +894,7 @@ int crick_spsv_merge_records(crick_spsv_t* s, const int64_t* dev_recs, int n_rec
     if (n_records <= 0) return 0;
     cudaStream_t st = sp_stream(s, stream);
     if (sp_drain(s, st)) return -1;
-    s->mirror_ok = false;
+    s->mirror_ok = false; s->known_empty = false;
     const size_t stride = spsv_bytes(s->cap, s->hcap);
     unsigned char* tmp = nullptr;
     cudaError_t e = cudaMallocAsync(&tmp, stride, st);
@@ -906,7 +919,7 @@ int crick_spsv_set_state(crick_spsv_t* s, const int64_t* counters3, int64_t n) {
     if (n <= 0) return 1;
     cudaStream_t st = sp_stream(s, nullptr);
     if (sp_drain(s, st)) return -1;
-    s->mirror_ok = false;
+    s->mirror_ok = false; s->known_empty = false;
     long long* d = nullptr;
     cudaError_t e = cudaMallocAsync(&d, (size_t)n * 24 + 8, st);
     if (e != cudaSuccess) return fail("cudaMallocAsync(spsv set_state)", e);
