@@ -530,7 +530,7 @@ static cudaStream_t sp_stream(crick_spsv* s, void* stream) {
 
 constexpr long kSpsvParallelMin = 1 << 18;   // below: the bit-exact sequential replay
 constexpr long kSpsvShardMin = 4096;         // elements per shard, at least
-constexpr long kSpsvHHMin = 1 << 22;         // from here: count candidates instead of replaying
+constexpr long kSpsvHHMin = 1 << 16;         // from here: count candidates instead of replaying
 constexpr long kSpsvHHMaxCap = 1024;         // (4 x capacity candidates must fit the lookup image)
 
 // Parallel update: shard summaries -> pairwise merge tree -> merge into the main summary ->
@@ -619,6 +619,10 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     if (C > kHHCandMax) C = kHHCandMax;
     const int L = 2 * C;
     const long S = n / 4 < kHHSampleMax ? n / 4 : kHHSampleMax;
+    // misses are replayed (exactness when #distinct <= capacity) only while they are few: items
+    // the sample did not see are rare, a stream with more distinct items than counters misses ~half
+    long miss_cap = n / 128 > 4096 ? n / 128 : 4096;
+    if (miss_cap > kHHMissCap) miss_cap = kHHMissCap;
     const size_t smem_cnt = (size_t)L * 10 + (size_t)C * 8;
     int G = sm_count() * (2 * smem_cnt + 2048 <= 227 * 1024 ? 2 : 1);
     const long W = (long)G * kHHWarps;
@@ -702,7 +706,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
                                                                clast, dstatus);
         count_launch();
         k_hh_finish<<<1, 1024, smem_fin, st>>>(ccnt, clast, C, cand, n, base_seen, tmp, s->cap, s->hcap,
-                                               dstatus);
+                                               miss_cap, dstatus);
         e = cudaMemcpyAsync(&hs, dstatus, sizeof(HHStatus), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) break;
@@ -722,7 +726,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         }
         if (e != cudaSuccess) break;
         *done = true;
-        if (hs.others > 0 && hs.others <= kHHMissCap) {
+        if (hs.others > 0 && hs.others <= miss_cap) {
             // few elements outside the candidates: collect them in stream order and replay them
             e = cudaMallocAsync(&miss_item, (size_t)hs.others * 16, st);
             if (e != cudaSuccess) break;

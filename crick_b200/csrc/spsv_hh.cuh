@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(1024) k_hh_finish(const long long* __restrict_
                                                     const long long* __restrict__ cand_last, int C,
                                                     const long long* __restrict__ cand_key,
                                                     long n, long base_seen, unsigned char* tmp, long cap,
-                                                    int hcap, HHStatus* status) {
+                                                    int hcap, long miss_cap, HHStatus* status) {
     extern __shared__ __align__(16) unsigned char sm[];
     long long* kc = reinterpret_cast<long long*>(sm);   // [C] counts
     long long* kl = kc + C;                             // [C] latest positions
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(1024) k_hh_finish(const long long* __restrict_
     const long long others = status->others, s_emax = status->emax;
     // bound for every item that is not kept: the next candidate's exact count, or (for items
     // that were never candidates) the fullest miss bucket -- unless the misses are replayed
-    const bool replay = others <= kHHMissCap;
+    const bool replay = others <= miss_cap;
     long long bound = (K < C && kc[K] > 0) ? kc[K] : 0;
     if (!replay && s_emax > bound) bound = s_emax;
     const long long m = K == cap ? kc[K - 1] : 0;   // what the merge will use as the bound (:297-300)

@@ -29,3 +29,16 @@ for n in (10**7, 10**8, 10**9):
             n, mode, best * 1e3, n / best / 1e9, 8 * n / best / 1e9, len(c), c["item"][:3].tolist(),
             c["count"].min(), c["error"].max()), flush=True)
     del x
+
+# mid-size batches (the dask per-chunk shape): counting from 65536 elements
+for n in (65536, 262144, 2 * 10**6):
+    u = torch.rand(n, dtype=torch.float64, device="cuda")
+    x = u.pow_(-10.0).clamp_(max=4.0e18).to(torch.int64)
+    torch.cuda.synchronize()
+    res = []
+    for mode in (0, 2 if n >= 262144 else 1):
+        s = cb.SpaceSaving(1000, "i8")
+        lib.crick_device_synchronize()
+        t0 = time.perf_counter(); s.update(x, mode=mode); s.size(); lib.crick_device_synchronize()
+        res.append(time.perf_counter() - t0)
+    print("n=%8d  auto (counting) %8.3f ms   %s %9.3f ms" % (n, res[0] * 1e3, "shards" if n >= 262144 else "replay", res[1] * 1e3), flush=True)
