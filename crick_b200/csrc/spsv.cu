@@ -586,16 +586,19 @@ static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* ite
 }
 
 static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, long n, cudaStream_t st,
-                                       bool* done);
+                                       bool* done, bool exact_only);
 
 static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const long long* cnt,
                                     long long cs, long n, cudaStream_t st, int mode = 0,
                                     const long long* when = nullptr) {
     // mode: 0 auto, 1 sequential (reference replay), 2 parallel (shards), 3 counting (heavy hitters)
+    // below kSpsvHHMin the reference's bits are kept for every input: a fresh summary still tries
+    // the counting path, but takes its result only when no eviction can have happened
+    const bool small_exact = mode == 0 && n < kSpsvHHMin && s->known_empty;
     if (!when && !cnt && cs == 1 && s->cap <= kSpsvHHMaxCap &&
-        (mode == 3 || (mode == 0 && n >= kSpsvHHMin)) && n >= 4 * 1024) {
+        (mode == 3 || (mode == 0 && n >= kSpsvHHMin) || small_exact) && n >= 4 * 1024) {
         bool done = false;
-        cudaError_t e = sp_launch_update_hh(s, item, n, st, &done);
+        cudaError_t e = sp_launch_update_hh(s, item, n, st, &done, small_exact);
         if (e != cudaSuccess || done) return e;
         // not applicable to this batch (see k_hh_finish): replay it
     }
@@ -612,7 +615,7 @@ static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const 
 
 // Counting path (spsv_hh.cuh).  *done = false: the batch does not suit it, nothing was changed.
 static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, long n, cudaStream_t st,
-                                       bool* done) {
+                                       bool* done, bool exact_only) {
     *done = false;
     int C = 256;
     while (C < 4 * s->cap) C <<= 1;
@@ -711,6 +714,8 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) break;
         if (hs.fallback) break;                  // *done stays false: nothing was changed
+        // exact_only (fresh summary, small batch): every distinct item must get its own counter
+        if (exact_only && (long)hs.npos + hs.others > s->cap) break;
         // fold the batch's summary into the object (spsv_merge).  Merging into an empty summary
         // of the same capacity reproduces the other one slot for slot (:330-350 with m1 = 0), so
         // a fresh object simply takes the image

@@ -39,7 +39,8 @@ constexpr int kHHCandMax = 4096;
 struct HHStatus {
     long long others;   // elements that are not candidates
     long long emax;     // fullest miss bucket
-    int kept, ncand, fallback, pad;
+    int kept, ncand, fallback;
+    int npos;           // candidates that occur in the batch at all
 };
 
 __device__ __forceinline__ unsigned long long hh_mix(unsigned long long z) {
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(1024) k_hh_finish(const long long* __restrict_
         int lo = 0, hi = C;                 // number of entries with a positive count
         while (lo < hi) { int mid = (lo + hi) >> 1; if (kc[mid] > 0) lo = mid + 1; else hi = mid; }
         s_kept = lo < cap ? lo : (int)cap;
+        status->npos = lo;
     }
     __syncthreads();
     const int K = s_kept;

@@ -222,6 +222,8 @@ int crick_spsv_add(crick_spsv_t *s, int64_t item, int64_t count);            /* 
  * that bound exceeds the smallest kept count), merged with :289-364; if only a few elements
  * (<= max(4096, n/128), at most 1 Mi) missed the candidates they are replayed with their stream
  * positions, so the result is still bit-identical to the reference whenever #distinct <= capacity.
+ * Below 65536 elements a summary nothing was added to yet also takes the counting path, but keeps
+ * its result only when no eviction can have happened (else the in-order replay runs).
  * mode 1 forces the sequential replay, mode 2 the shard path, mode 3 the counting path (falls
  * back to 2 when it does not apply). */
 int crick_spsv_update(crick_spsv_t *s, const int64_t *item, const int64_t *count,

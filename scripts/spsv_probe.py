@@ -42,3 +42,15 @@ for n in (65536, 262144, 2 * 10**6):
         t0 = time.perf_counter(); s.update(x, mode=mode); s.size(); lib.crick_device_synchronize()
         res.append(time.perf_counter() - t0)
     print("n=%8d  auto (counting) %8.3f ms   %s %9.3f ms" % (n, res[0] * 1e3, "shards" if n >= 262144 else "replay", res[1] * 1e3), flush=True)
+
+# small batches on a fresh summary, few distinct items (a categorical column)
+for n in (8192, 30000, 60000):
+    x = torch.randint(0, 500, (n,), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    res = []
+    for mode in (0, 1):
+        s = cb.SpaceSaving(1000, "i8")
+        lib.crick_device_synchronize()
+        t0 = time.perf_counter(); s.update(x, mode=mode); s.size(); lib.crick_device_synchronize()
+        res.append(time.perf_counter() - t0)
+    print("n=%6d 500 distinct  auto %7.3f ms   replay %8.3f ms" % (n, res[0] * 1e3, res[1] * 1e3), flush=True)

@@ -407,3 +407,21 @@ def test_spsv_counting_path_degenerate_streams(cb):
         s.update(cb.DeviceArray.from_numpy(items))
         o.update(items)
         assert s.counters().tobytes() == o.counters().tobytes()
+
+
+@pytest.mark.parametrize("distinct", [300, 995, 1005, 20000])
+def test_spsv_small_batches_keep_the_reference_bits(cb, distinct):
+    """Below 65536 elements auto mode promises the reference's bits for every input.  A fresh
+    summary may take the counting path, but only when every distinct item gets a counter (no
+    eviction possible); otherwise -- and on a summary that already holds data -- the stream is
+    replayed in order."""
+    rng = np.random.default_rng(distinct)
+    n = 30000
+    items = (rng.zipf(1.2, n) % distinct).astype(np.int64) * 31 + 5
+    s, o = cb.SpaceSaving(1000, "i8"), R.SpaceSaving(1000)
+    s.update(cb.DeviceArray.from_numpy(items))
+    o.update(items)
+    assert s.counters().tobytes() == o.counters().tobytes()
+    s.update(items[::-1].copy())
+    o.update(items[::-1].copy())
+    assert s.counters().tobytes() == o.counters().tobytes()
