@@ -30,6 +30,7 @@ _SIG = {
     "crick_launch_count": (c_int64, []),
     "crick_profile_enable": (c_int, [c_int]),
     "crick_group_kernel": (c_int, [c_int]),
+    "crick_stats_kernel": (c_int, [c_int]),
     "crick_profile_collect": (c_int, [_P, _P]),
     "crick_host_alloc": (_P, [c_int64]),
     "crick_host_free": (None, [_P]),

@@ -32,7 +32,8 @@ struct StatsState {
     int pad;
 };
 
-constexpr long kStatsParallelMin = 1 << 16;
+constexpr long kStatsParallelMin = 1 << 10;   // the replay is one dependent chain: 1.5 us per element
+static int g_stats_mode = -1;                  // -1 auto, 0 always the sequential replay, 1 always parallel
 
 __host__ __device__ inline void stats_fresh(StatsState& s) {
     s.count = 0; s.sum = 0; s.vmin = DBL_MAX; s.vmax = -DBL_MIN;  // :29-37 (max quirk S0)
@@ -338,7 +339,7 @@ static int ss_sync(crick_stats* s) {
 template <typename XT>
 static cudaError_t stats_launch(crick_stats* s, const XT* x, const long long* c, long long cs, long n,
                                 cudaStream_t st) {
-    if (n < kStatsParallelMin) {
+    if (g_stats_mode == 0 || (g_stats_mode < 0 && n < kStatsParallelMin)) {
         count_launch();
         k_stats_seq<XT><<<1, 32, 0, st>>>(s->d, x, c, cs, n, 1);
         return cudaGetLastError();
@@ -373,6 +374,12 @@ cudaError_t stats_fused_finish(crick_stats* s, int nused, cudaStream_t st) {
 }  // namespace crick
 
 extern "C" {
+
+int crick_stats_kernel(int mode) {
+    int prev = g_stats_mode;
+    if (mode >= -1 && mode <= 1) g_stats_mode = mode;
+    return prev;
+}
 
 crick_stats_t* crick_stats_new(void) {
     if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }

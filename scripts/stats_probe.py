@@ -25,3 +25,15 @@ for n in (10**8, 10**9):
         print("n=%.0e %-8s %.3f ms  %.1f Gval/s  %.0f GB/s (%.2f of 6542)  mean=%.6g" % (
             n, str(dt_).split(".")[1], dt * 1e3, n / dt / 1e9, 8 * n / dt / 1e9, 8 * n / dt / 1e9 / 6542.4, s.mean()), flush=True)
         del x
+
+# small batches: the sequential (bit-exact) kernel below 65536 values
+for n in (1000, 10000, 65535, 65536, 200000):
+    x = torch.randn(n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    s = cb.SummaryStats()
+    s.update(x); lib.crick_device_synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        s.update(x)
+    s.count(); lib.crick_device_synchronize()
+    print("n=%7d  %.3f ms per update" % (n, (time.perf_counter() - t0) / 5 * 1e3), flush=True)

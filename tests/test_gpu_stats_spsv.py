@@ -2,7 +2,8 @@
 through the C ABI, against the oracle and the reference's own known-answer tests
 (crick/tests/test_stats.py, crick/tests/test_space_saving.py).
 
-Bar: SummaryStats bit-exact on the sequential path (n < 65536 per call), `atol 1e-8`-style
+Bar: SummaryStats bit-exact on the sequential replay (auto below 1024 values per call, forced
+here for the 10000-value known answers), moments within 1e-12 relative / `atol 1e-8`-style
 tolerance vs NumPy/SciPy on the parallel path (the reference's own test tolerance,
 test_stats.py:20-21); SpaceSaving counters bit-exact, including list order.
 """
@@ -26,7 +27,17 @@ def cb():
 
 
 # ---- SummaryStats -------------------------------------------------------------------------
-def test_stats_golden_state(cb, golden):
+@pytest.fixture
+def stats_replay():
+    """Force the sequential replay of stats_do_update (bit-exact with the reference); auto mode
+    uses it below 1024 values per call only, because it costs ~1.5 us per element."""
+    from crick_b200._lib import lib
+    prev = lib.crick_stats_kernel(0)
+    yield
+    lib.crick_stats_kernel(prev)
+
+
+def test_stats_golden_state(cb, golden, stats_replay):
     g, _ = golden
     i = np.arange(10000)
     s = cb.SummaryStats()
@@ -41,7 +52,7 @@ def test_stats_golden_state(cb, golden):
 
 
 @pytest.mark.parametrize("case", ["normal_nan", "empty", "one", "duplicate", "different", "ints"])
-def test_stats_sequential_bit_exact(cb, case):
+def test_stats_sequential_bit_exact(cb, case, stats_replay):
     rng = np.random.default_rng(0)
     x = {"normal_nan": np.where(rng.uniform(size=10000) < 0.1, np.nan, rng.normal(50, 10, 10000)),
          "empty": np.array([]), "one": np.array([1.5]), "duplicate": np.array([1.5] * 10),
@@ -56,6 +67,27 @@ def test_stats_sequential_bit_exact(cb, case):
     assert np.array_equal(s.var(ddof=1), o.var(ddof=1), equal_nan=True)
     assert np.array_equal(s.skew(bias=False), o.skew(False), equal_nan=True)
     assert np.array_equal(s.kurt(fisher=False, bias=False), o.kurt(False, False), equal_nan=True)
+
+
+@pytest.mark.parametrize("n", [1024, 3000, 10000, 60000])
+def test_stats_parallel_pass_on_small_arrays(cb, n):
+    """Auto mode from 1024 values: the parallel pass must agree with the reference to ~1e-12
+    relative in every moment and exactly in count / min / max / sum of integers, NaNs skipped
+    and the homogeneous / first-value bookkeeping intact."""
+    rng = np.random.default_rng(n)
+    x = rng.normal(50, 10, n)
+    x[rng.integers(0, n, 7)] = np.nan
+    for data in (x, rng.integers(-50, 50, n), np.full(n, 2.5)):
+        s, o = cb.SummaryStats(), R.SummaryStats()
+        s.update(data)
+        o.update(data)
+        a, b = s.__getstate__(), o.__getstate__()
+        assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3] and a[7] == b[7] and a[8] == b[8]
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-13)                       # sum
+        for f in ("mean", "var", "std", "skew", "kurt"):
+            np.testing.assert_allclose(getattr(s, f)(), getattr(o, f)(), rtol=1e-10, atol=1e-12, equal_nan=True, err_msg=f)
+        m = o.__getstate__()
+        np.testing.assert_allclose(a[4:7], m[4:7], rtol=1e-11, atol=1e-9 * abs(m[4]) if m[4] else 1e-300)
 
 
 def test_stats_quirks(cb):
@@ -81,7 +113,7 @@ def test_stats_quirks(cb):
         s.merge(1)
 
 
-def test_stats_weights_merge_pickle(cb):
+def test_stats_weights_merge_pickle(cb, stats_replay):
     rng = np.random.default_rng(1)
     x = rng.normal(size=4000)
     c = rng.integers(1, 5, 4000)
