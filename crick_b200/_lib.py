@@ -120,7 +120,7 @@ for _name, (_res, _args) in _SIG.items():
     _fn.argtypes = _args
 
 MODE_AUTO, MODE_REFERENCE, MODE_PARALLEL = 0, 1, 2
-PARALLEL_MIN = 8192
+PARALLEL_MIN = 2048
 _MODES = {"auto": MODE_AUTO, "reference": MODE_REFERENCE, "parallel": MODE_PARALLEL}
 
 

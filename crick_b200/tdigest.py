@@ -41,8 +41,8 @@ class TDigest:
     mode : {"auto", "reference", "parallel"}, optional
         ``reference``: the reference's sequential buffer/flush algorithm, bit-exact
         with crick's C path.  ``parallel``: k-bucket pre-aggregation for huge arrays
-        (needs >= 8192 values per call).  ``auto`` (default): reference below
-        8192 values per ``update`` call (where one warp replaying the reference's
+        (needs >= 2048 values per call).  ``auto`` (default): reference below
+        2048 values per ``update`` call (where one warp replaying the reference's
         sequential algorithm is still affordable), parallel at or above.
     """
 

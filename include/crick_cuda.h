@@ -73,7 +73,7 @@ int crick_synth_fill(double *x_dev, double *w_dev, int64_t n, uint64_t seed, int
 #define CRICK_MODE_AUTO 0      /* reference-compatible below CRICK_PARALLEL_MIN values, else parallel */
 #define CRICK_MODE_REFERENCE 1 /* bit-exact with the reference's sequential algorithm */
 #define CRICK_MODE_PARALLEL 2  /* k-bucket pre-aggregation (needs n >= CRICK_PARALLEL_MIN) */
-#define CRICK_PARALLEL_MIN 8192
+#define CRICK_PARALLEL_MIN 2048
 
 /* tdigest_new, tdigest_stubs.c:50-99 (compression clipped to [20, 1000]) */
 crick_tdigest_t *crick_tdigest_new(double compression);
