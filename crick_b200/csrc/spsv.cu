@@ -585,8 +585,8 @@ static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* ite
     return e;
 }
 
-static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, long n, cudaStream_t st,
-                                       bool* done, bool exact_only);
+static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, const long long* cnt,
+                                       long n, cudaStream_t st, bool* done, bool exact_only);
 
 static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const long long* cnt,
                                     long long cs, long n, cudaStream_t st, int mode = 0,
@@ -595,10 +595,10 @@ static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const 
     // below kSpsvHHMin the reference's bits are kept for every input: a fresh summary still tries
     // the counting path, but takes its result only when no eviction can have happened
     const bool small_exact = mode == 0 && n < kSpsvHHMin && s->known_empty;
-    if (!when && !cnt && cs == 1 && s->cap <= kSpsvHHMaxCap &&
+    if (!when && (cnt || cs == 1) && s->cap <= kSpsvHHMaxCap &&
         (mode == 3 || (mode == 0 && n >= kSpsvHHMin) || small_exact) && n >= 4 * 1024) {
         bool done = false;
-        cudaError_t e = sp_launch_update_hh(s, item, n, st, &done, small_exact);
+        cudaError_t e = sp_launch_update_hh(s, item, cnt, n, st, &done, small_exact);
         if (e != cudaSuccess || done) return e;
         // not applicable to this batch (see k_hh_finish): replay it
     }
@@ -614,9 +614,10 @@ static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const 
 }
 
 // Counting path (spsv_hh.cuh).  *done = false: the batch does not suit it, nothing was changed.
-static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, long n, cudaStream_t st,
-                                       bool* done, bool exact_only) {
+static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, const long long* cnt,
+                                       long n, cudaStream_t st, bool* done, bool exact_only) {
     *done = false;
+    const size_t csz = cnt ? 8 : 4;            // counts of the counting pass: u64 with weights
     int C = 256;
     while (C < 4 * s->cap) C <<= 1;
     if (C > kHHCandMax) C = kHHCandMax;
@@ -626,7 +627,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     // the sample did not see are rare, a stream with more distinct items than counters misses ~half
     long miss_cap = n / 128 > 4096 ? n / 128 : 4096;
     if (miss_cap > kHHMissCap) miss_cap = kHHMissCap;
-    const size_t smem_cnt = (size_t)L * 10 + (size_t)C * 8;
+    const size_t smem_cnt = (size_t)L * 10 + (size_t)C * (4 + csz);
     int G = sm_count() * (2 * smem_cnt + 2048 <= 227 * 1024 ? 2 : 1);
     const long W = (long)G * kHHWarps;
     const size_t stride = spsv_bytes(s->cap, s->hcap);
@@ -634,9 +635,9 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_tabkey = take((size_t)kHHTabSlots * 8), o_tabcnt = take((size_t)kHHTabSlots * 4);
-    const size_t o_buckets = take((size_t)kHHBuckets * 4);
+    const size_t o_buckets = take((size_t)kHHBuckets * csz);
     const size_t o_cand = take((size_t)C * 8), o_lutk = take((size_t)L * 8), o_lutv = take((size_t)L * 2);
-    const size_t o_rc = take((size_t)G * C * 4), o_rl = take((size_t)G * C * 4);
+    const size_t o_rc = take((size_t)G * C * csz), o_rl = take((size_t)G * C * 4);
     const size_t o_wm = take((size_t)W * 8), o_wo = take((size_t)W * 8);
     const size_t o_cc = take((size_t)C * 8), o_cl = take((size_t)C * 8);
     const size_t o_hist = take(1024 * 4), o_sel = take(sizeof(HHSel));
@@ -647,11 +648,11 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
     if (e != cudaSuccess) return e;
     long long* tabkey = reinterpret_cast<long long*>(ws + o_tabkey);
     unsigned* tabcnt = reinterpret_cast<unsigned*>(ws + o_tabcnt);
-    unsigned* buckets = reinterpret_cast<unsigned*>(ws + o_buckets);
+    void* buckets = ws + o_buckets;
     long long* cand = reinterpret_cast<long long*>(ws + o_cand);
     long long* lutk = reinterpret_cast<long long*>(ws + o_lutk);
     unsigned short* lutv = reinterpret_cast<unsigned short*>(ws + o_lutv);
-    unsigned* rc = reinterpret_cast<unsigned*>(ws + o_rc);
+    void* rc = ws + o_rc;
     unsigned* rl = reinterpret_cast<unsigned*>(ws + o_rl);
     unsigned long long* wm = reinterpret_cast<unsigned long long*>(ws + o_wm);
     unsigned long long* wo = reinterpret_cast<unsigned long long*>(ws + o_wo);
@@ -674,7 +675,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
             if (e != cudaSuccess) break;
         }
         e = cudaMemsetAsync(tabcnt, 0, (size_t)kHHTabSlots * 4, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(buckets, 0, (size_t)kHHBuckets * 4, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(buckets, 0, (size_t)kHHBuckets * csz, st);
         if (e != cudaSuccess) break;
         e = cudaMemsetAsync(dstatus, 0, sizeof(HHStatus), st);
         if (e != cudaSuccess) break;
@@ -694,19 +695,32 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         k_hh_place<<<kHHNChunk, 1024, 0, st>>>(tabkey, tabcnt, sel, chunk_gt, chunk_eq, cand);
         count_launch();
         k_hh_lut<<<1, 1024, 0, st>>>(cand, sel, chunk_eq, lutk, lutv, L, dstatus);
-        e = cudaFuncSetAttribute(k_hh_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
+        e = cnt ? cudaFuncSetAttribute(k_hh_count<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt)
+                : cudaFuncSetAttribute(k_hh_count<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
         if (e != cudaSuccess) break;
         if (!fresh) e = cudaStreamSynchronize(st);           // base_seen has arrived
         if (e != cudaSuccess) break;
         count_launch();
-        k_hh_count<<<G, kHHWarps * 32, smem_cnt, st>>>(item, n, lutk, lutv, L, C, rc, rl, buckets, wm, 0,
-                                                       nullptr, nullptr, nullptr, base_seen);
+        if (cnt)
+            k_hh_count<unsigned long long><<<G, kHHWarps * 32, smem_cnt, st>>>(
+                item, cnt, n, lutk, lutv, L, C, static_cast<unsigned long long*>(rc), rl,
+                static_cast<unsigned long long*>(buckets), wm, 0, nullptr, nullptr, nullptr, nullptr, base_seen);
+        else
+            k_hh_count<unsigned><<<G, kHHWarps * 32, smem_cnt, st>>>(
+                item, nullptr, n, lutk, lutv, L, C, static_cast<unsigned*>(rc), rl,
+                static_cast<unsigned*>(buckets), wm, 0, nullptr, nullptr, nullptr, nullptr, base_seen);
         const size_t smem_fin = (size_t)C * 20;
         e = cudaFuncSetAttribute(k_hh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
         if (e != cudaSuccess) break;
         count_launch();
-        k_hh_reduce<<<64, 256, (size_t)G * sizeof(long), st>>>(rc, rl, G, C, buckets, wm, n, base_seen, ccnt,
-                                                               clast, dstatus);
+        if (cnt)
+            k_hh_reduce<unsigned long long><<<64, 256, (size_t)G * sizeof(long), st>>>(
+                static_cast<const unsigned long long*>(rc), rl, G, C,
+                static_cast<const unsigned long long*>(buckets), wm, n, base_seen, ccnt, clast, dstatus);
+        else
+            k_hh_reduce<unsigned><<<64, 256, (size_t)G * sizeof(long), st>>>(
+                static_cast<const unsigned*>(rc), rl, G, C, static_cast<const unsigned*>(buckets), wm, n,
+                base_seen, ccnt, clast, dstatus);
         count_launch();
         k_hh_finish<<<1, 1024, smem_fin, st>>>(ccnt, clast, C, cand, n, base_seen, tmp, s->cap, s->hcap,
                                                miss_cap, dstatus);
@@ -733,17 +747,24 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, lon
         *done = true;
         if (hs.others > 0 && hs.others <= miss_cap) {
             // few elements outside the candidates: collect them in stream order and replay them
-            e = cudaMallocAsync(&miss_item, (size_t)hs.others * 16, st);
+            e = cudaMallocAsync(&miss_item, (size_t)hs.others * 24, st);
             if (e != cudaSuccess) break;
             long long* miss_pos = miss_item + hs.others;
+            long long* miss_cnt = cnt ? miss_pos + hs.others : nullptr;
             count_launch();
             k_hh_scan<<<1, 1024, 0, st>>>(wm, (int)W, wo);
             count_launch();
-            k_hh_count<<<G, kHHWarps * 32, smem_cnt, st>>>(item, n, lutk, lutv, L, C, rc, rl, buckets, wm, 1,
-                                                           wo, miss_item, miss_pos, base_seen);
+            if (cnt)
+                k_hh_count<unsigned long long><<<G, kHHWarps * 32, smem_cnt, st>>>(
+                    item, cnt, n, lutk, lutv, L, C, static_cast<unsigned long long*>(rc), rl,
+                    static_cast<unsigned long long*>(buckets), wm, 1, wo, miss_item, miss_pos, miss_cnt, base_seen);
+            else
+                k_hh_count<unsigned><<<G, kHHWarps * 32, smem_cnt, st>>>(
+                    item, nullptr, n, lutk, lutv, L, C, static_cast<unsigned*>(rc), rl,
+                    static_cast<unsigned*>(buckets), wm, 1, wo, miss_item, miss_pos, nullptr, base_seen);
             e = cudaGetLastError();
             if (e != cudaSuccess) break;
-            e = sp_launch_update(s, miss_item, nullptr, 1, (long)hs.others, st,
+            e = sp_launch_update(s, miss_item, miss_cnt, 1, (long)hs.others, st,
                                  hs.others >= kSpsvParallelMin ? 2 : 1, miss_pos);
             if (e != cudaSuccess) break;
         }

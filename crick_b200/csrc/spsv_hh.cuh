@@ -38,7 +38,7 @@ constexpr int kHHCandMax = 4096;
 
 struct HHStatus {
     long long others;   // elements that are not candidates
-    long long emax;     // fullest miss bucket
+    long long emax;     // fullest miss bucket (sum of the counts of its elements)
     int kept, ncand, fallback;
     int npos;           // candidates that occur in the batch at all
 };
@@ -225,19 +225,23 @@ __global__ void __launch_bounds__(1024) k_hh_lut(const long long* __restrict__ c
 
 // The streaming pass.  Warp w of the grid owns the contiguous elements [w n / W, (w+1) n / W).
 // collect == 0: count.  collect == 1: write the misses, in stream order, at miss_off[w] ...
-__global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __restrict__ item, long n,
+// CT: unsigned for unit counts (cnt == nullptr), unsigned long long when every element carries
+// its own count (the candidates' counts and the miss buckets are then sums of counts).
+template <typename CT>
+__global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __restrict__ item,
+                                                            const long long* __restrict__ cnt, long n,
                                                             const long long* __restrict__ lut_key,
                                                             const unsigned short* __restrict__ lut_val,
-                                                            int L, int C, unsigned* rows_cnt,
-                                                            unsigned* rows_last, unsigned* buckets,
+                                                            int L, int C, CT* rows_cnt,
+                                                            unsigned* rows_last, CT* buckets,
                                                             unsigned long long* warp_miss, int collect,
                                                             const unsigned long long* __restrict__ miss_off,
                                                             long long* miss_item, long long* miss_pos,
-                                                            long base_seen) {
+                                                            long long* miss_cnt, long base_seen) {
     extern __shared__ __align__(16) unsigned char sm[];
     long long* s_key = reinterpret_cast<long long*>(sm);                    // [L]
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_key + L);               // [C]
-    unsigned* s_last = s_cnt + C;                                           // [C]
+    CT* s_cnt = reinterpret_cast<CT*>(s_key + L);                           // [C]
+    unsigned* s_last = reinterpret_cast<unsigned*>(s_cnt + C);              // [C]
     unsigned short* s_val = reinterpret_cast<unsigned short*>(s_last + C);  // [L]
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     for (int i = tid; i < L; i += blockDim.x) { s_key[i] = lut_key[i]; s_val[i] = lut_val[i]; }
@@ -253,11 +257,12 @@ __global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __r
     unsigned long long out = collect ? miss_off[w] : 0ull;
     constexpr int U = 4;
     for (long base = lo; base < hi; base += 32 * U) {
-        long long key[U];
+        long long key[U], cv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long i = base + u * 32 + lane;
             key[u] = i < hi ? item[i] : kHHEmpty;
+            cv[u] = (cnt && i < hi) ? cnt[i] : 1;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -277,10 +282,10 @@ __global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __r
             const bool miss = valid && v < 0;
             if (!collect) {
                 if (v >= 0) {
-                    atomicAdd(&s_cnt[v], 1u);
+                    atomicAdd(&s_cnt[v], (CT)cv[u]);
                     atomicMax(&s_last[v], (unsigned)(i - cta_lo) + 1u);
                 } else if (miss) {
-                    atomicAdd(&buckets[hh_bucket(h)], 1u);
+                    atomicAdd(&buckets[hh_bucket(h)], (CT)cv[u]);
                     ++nmiss;
                 }
             } else {
@@ -289,6 +294,7 @@ __global__ void __launch_bounds__(kHHWarps * 32) k_hh_count(const long long* __r
                     const unsigned long long at = out + __popc(mm & ((1u << lane) - 1u));
                     miss_item[at] = key[u];
                     miss_pos[at] = base_seen + i;
+                    if (cnt) miss_cnt[at] = cv[u];
                 }
                 out += __popc(mm);
             }
@@ -327,9 +333,10 @@ __global__ void __launch_bounds__(1024) k_hh_scan(const unsigned long long* warp
 
 // Exact count and latest stream position of every candidate (sum / max over the CTAs of the
 // counting pass), the number of misses and the fullest miss bucket.  Grid-stride, any grid.
-__global__ void __launch_bounds__(256) k_hh_reduce(const unsigned* __restrict__ rows_cnt,
+template <typename CT>
+__global__ void __launch_bounds__(256) k_hh_reduce(const CT* __restrict__ rows_cnt,
                                                    const unsigned* __restrict__ rows_last, int G, int C,
-                                                   const unsigned* __restrict__ buckets,
+                                                   const CT* __restrict__ buckets,
                                                    const unsigned long long* __restrict__ warp_miss,
                                                    long n, long base_seen, long long* cand_cnt,
                                                    long long* cand_last, HHStatus* status) {
@@ -343,27 +350,27 @@ __global__ void __launch_bounds__(256) k_hh_reduce(const unsigned* __restrict__ 
     for (long c = tid; c < C; c += nthr) {
         long long cnt = 0, last = -1;
         for (int g = 0; g < G; ++g) {
-            const unsigned rc = rows_cnt[(size_t)g * C + c], rl = rows_last[(size_t)g * C + c];
-            cnt += rc;
+            const CT rc = rows_cnt[(size_t)g * C + c];
+            const unsigned rl = rows_last[(size_t)g * C + c];
+            cnt += (long long)rc;
             const long long p = rc ? base_seen + s_lo[g] + (long long)rl - 1 : -1;
             last = p > last ? p : last;
         }
         cand_cnt[c] = cnt;
         cand_last[c] = last;
     }
-    unsigned long long oth = 0;
-    unsigned emax = 0;
+    unsigned long long oth = 0, emax = 0;
     for (long i = tid; i < W; i += nthr) oth += warp_miss[i];
-    for (long i = tid; i < kHHBuckets; i += nthr) { const unsigned b = buckets[i]; emax = b > emax ? b : emax; }
+    for (long i = tid; i < kHHBuckets; i += nthr) { const unsigned long long b = buckets[i]; emax = b > emax ? b : emax; }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         oth += __shfl_xor_sync(CRICK_FULL, oth, d);
-        const unsigned o = __shfl_xor_sync(CRICK_FULL, emax, d);
+        const unsigned long long o = __shfl_xor_sync(CRICK_FULL, emax, d);
         emax = o > emax ? o : emax;
     }
     if ((threadIdx.x & 31) == 0) {
         if (oth) atomicAdd(reinterpret_cast<unsigned long long*>(&status->others), oth);
-        if (emax) atomicMax(reinterpret_cast<unsigned long long*>(&status->emax), (unsigned long long)emax);
+        if (emax) atomicMax(reinterpret_cast<unsigned long long*>(&status->emax), emax);
     }
 }
 

@@ -216,11 +216,11 @@ crick_spsv_t *crick_spsv_new(int64_t capacity);                  /* spsv_int64_n
 void crick_spsv_free(crick_spsv_t *s);                           /* :98-109 */
 int crick_spsv_add(crick_spsv_t *s, int64_t item, int64_t count);            /* :213-250 */
 /* spsv_int64_update_ndarray :367-451; count == NULL => scalar.
- * mode 0 auto: below 65536 elements (262144 with a count array) the stream is replayed in order
+ * mode 0 auto: below 65536 elements the stream is replayed in order
  * (bit-exact with the reference, list order included); above, shard summaries are built in parallel and merged with
  * the reference's own merge (:289-364, Cafaro et al.) -- a valid Space-Saving summary for any
  * input, with exact counts and the reference's list order whenever #distinct <= capacity.
- * From 65536 elements with count 1 (capacity <= 1024) the batch is COUNTED instead of replayed:
+ * From 65536 elements (count 1 or a count array; capacity <= 1024) the batch is COUNTED instead of replayed:
  * the 4 x capacity most frequent items of a 1 Mi sample are counted exactly in one streaming
  * pass, the top `capacity` form a summary with error 0 (every other item is bounded by the next
  * candidate / the fullest of 1 Mi miss buckets; counts and errors are raised by the excess if

@@ -308,9 +308,13 @@ def test_spsv_parallel_path(cb):
     assert f.counters().view("i8").tobytes() == of.counters().view("i8").tobytes()
 
 
-def _assert_valid_summary(c, items, capacity):
-    """Metwally's guarantees against the true counts."""
-    vals, counts = np.unique(items, return_counts=True)
+def _assert_valid_summary(c, items, capacity, weights=None):
+    """Metwally's guarantees against the true (weighted) counts."""
+    if weights is None:
+        vals, counts = np.unique(items, return_counts=True)
+    else:
+        vals, inv = np.unique(items, return_inverse=True)
+        counts = np.bincount(inv, weights=weights).astype(np.int64)
     true = dict(zip(vals.tolist(), counts.tolist()))
     assert (np.diff(c["count"]) <= 0).all()
     for it, cn, er in c.tolist():
@@ -457,3 +461,22 @@ def test_spsv_small_batches_keep_the_reference_bits(cb, distinct):
     s.update(items[::-1].copy())
     o.update(items[::-1].copy())
     assert s.counters().tobytes() == o.counters().tobytes()
+
+
+def test_spsv_counting_path_with_counts(cb):
+    """A count per element (pre-aggregated input): candidate counts and miss buckets are sums of
+    counts.  Exact regime == the reference; otherwise every guarantee holds for the weighted
+    truth."""
+    rng = np.random.default_rng(17)
+    n = 400000
+    w = rng.integers(1, 1000, n).astype(np.int64)
+    items = (rng.zipf(1.25, n) % 800).astype(np.int64)
+    s, o = cb.SpaceSaving(1000, "i8"), R.SpaceSaving(1000)
+    s.update(cb.DeviceArray.from_numpy(items), cb.DeviceArray.from_numpy(w))
+    o.update(items, w)
+    assert s.counters().tobytes() == o.counters().tobytes()
+    items = rng.zipf(1.1, n).astype(np.int64)
+    for cap in (1000, 50):
+        s = cb.SpaceSaving(cap, "i8")
+        s.update(items, w, mode=3)
+        _assert_valid_summary(s.counters(), items, cap, w)
