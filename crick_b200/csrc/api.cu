@@ -167,13 +167,36 @@ void* crick_host_alloc(int64_t bytes) {
     return p;
 }
 void crick_host_free(void* p) { if (p) cudaFreeHost(p); }
+// Device buffers of the Python-side DeviceArray come from the stream-ordered pool (a cudaMalloc
+// of tens of MB costs ~0.6 ms, e.g. the output of every large device query): allocated on a
+// per-device helper stream and synchronised, so the memory is valid on every stream; freed after
+// a device synchronisation, so nothing can still be using it.
+static void tune_mempool_once();
+static cudaStream_t alloc_stream() {
+    static cudaStream_t streams[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess)
+        streams[dev] = nullptr;
+    return streams[dev];
+}
 void* crick_device_alloc(int64_t bytes) {
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (size_t)(bytes > 0 ? bytes : 1));
-    if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
+    tune_mempool_once();
+    cudaStream_t st = alloc_stream();
+    cudaError_t e = st ? cudaMallocAsync(&p, (size_t)(bytes > 0 ? bytes : 1), st) : cudaErrorInvalidDevice;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { fail("cudaMallocAsync(device array)", e); return nullptr; }
     return p;
 }
-void crick_device_free(void* p) { if (p) cudaFree(p); }
+void crick_device_free(void* p) {
+    if (!p) return;
+    cudaStream_t st = alloc_stream();
+    cudaDeviceSynchronize();
+    if (st) cudaFreeAsync(p, st); else cudaFree(p);
+}
 int crick_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream) {
     cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice,
                                     reinterpret_cast<cudaStream_t>(stream));

@@ -32,7 +32,7 @@ struct StatsState {
     int pad;
 };
 
-constexpr long kStatsParallelMin = 1 << 10;   // the replay is one dependent chain: 1.5 us per element
+constexpr long kStatsParallelMin = 1 << 8;    // the replay is one dependent chain: 1.5 us per element
 static int g_stats_mode = -1;                  // -1 auto, 0 always the sequential replay, 1 always parallel
 
 __host__ __device__ inline void stats_fresh(StatsState& s) {

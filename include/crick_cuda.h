@@ -194,7 +194,7 @@ int crick_stats_update(crick_stats_t *s, const void *x, int x_is_int64, const in
                        int64_t count_scalar, int64_t n, int x_on_device, int count_on_device,
                        void *stream);
 /* which kernel array updates use: -1 (default) the sequential replay of stats_do_update :47-75
- * (bit-exact with the reference, one dependent chain: ~1.5 us per element) below 1024 elements
+ * (bit-exact with the reference, one dependent chain: ~1.5 us per element) below 256 elements
  * and the parallel pass (Pebay pairwise merges; moments within ~1e-12 relative) from there;
  * 0 always the replay, 1 always the parallel pass.  Returns the previous setting. */
 int crick_stats_kernel(int mode);

@@ -2,7 +2,7 @@
 through the C ABI, against the oracle and the reference's own known-answer tests
 (crick/tests/test_stats.py, crick/tests/test_space_saving.py).
 
-Bar: SummaryStats bit-exact on the sequential replay (auto below 1024 values per call, forced
+Bar: SummaryStats bit-exact on the sequential replay (auto below 256 values per call, forced
 here for the 10000-value known answers), moments within 1e-12 relative / `atol 1e-8`-style
 tolerance vs NumPy/SciPy on the parallel path (the reference's own test tolerance,
 test_stats.py:20-21); SpaceSaving counters bit-exact, including list order.
@@ -30,7 +30,7 @@ def cb():
 @pytest.fixture
 def stats_replay():
     """Force the sequential replay of stats_do_update (bit-exact with the reference); auto mode
-    uses it below 1024 values per call only, because it costs ~1.5 us per element."""
+    uses it below 256 values per call only, because it costs ~1.5 us per element."""
     from crick_b200._lib import lib
     prev = lib.crick_stats_kernel(0)
     yield
@@ -69,9 +69,9 @@ def test_stats_sequential_bit_exact(cb, case, stats_replay):
     assert np.array_equal(s.kurt(fisher=False, bias=False), o.kurt(False, False), equal_nan=True)
 
 
-@pytest.mark.parametrize("n", [1024, 3000, 10000, 60000])
+@pytest.mark.parametrize("n", [256, 1024, 3000, 10000, 60000])
 def test_stats_parallel_pass_on_small_arrays(cb, n):
-    """Auto mode from 1024 values: the parallel pass must agree with the reference to ~1e-12
+    """Auto mode from 256 values: the parallel pass must agree with the reference to ~1e-12
     relative in every moment and exactly in count / min / max / sum of integers, NaNs skipped
     and the homogeneous / first-value bookkeeping intact."""
     rng = np.random.default_rng(n)
