@@ -9,7 +9,12 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <chrono>
+#include <cstdio>
 #include <thread>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 
 namespace crick {
 
@@ -88,6 +93,10 @@ struct crick_tdigest {
     bool buf_clean = false;          // the insertion buffer is known to be empty (no flush needed)
     void* scratch = nullptr;         // parallel-mode scratch (lazy)
     size_t scratch_bytes = 0;
+    // host-input path: copy stream and per-slot events, created once per handle (a stream and six
+    // events cost ~130 us per call to create and destroy)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr};
 };
 
 static cudaStream_t td_stream(crick_tdigest* t, void* stream) {
@@ -266,6 +275,11 @@ void crick_tdigest_free(crick_tdigest_t* t) {
     if (t->last) cudaStreamSynchronize(t->last);
     if (t->own) { cudaStreamSynchronize(t->own); cudaStreamDestroy(t->own); }
     if (t->ev) cudaEventDestroy(t->ev);
+    if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
+    for (int b = 0; b < 3; ++b) {
+        if (t->ev_copied[b]) cudaEventDestroy(t->ev_copied[b]);
+        if (t->ev_done[b]) cudaEventDestroy(t->ev_done[b]);
+    }
     if (t->scratch) cudaFree(t->scratch);
     store_free(t->s);
     delete t;
@@ -300,14 +314,34 @@ static bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// Copy into a pinned staging slot with non-temporal stores: the DMA engine reads the slot right
+// afterwards, and lines left dirty in the caches of several cores slow that read down several
+// times (8 MB: H2D 160 us after streaming stores or one big memcpy, 260-1200 us after eight
+// threads of ordinary stores).  dst must be 16-byte aligned.
+static void stream_copy(double* dst, const double* src, int64_t n) {
+#if defined(__x86_64__) || defined(_M_X64)
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const __m128d a = _mm_loadu_pd(src + i), b = _mm_loadu_pd(src + i + 2);
+        const __m128d c = _mm_loadu_pd(src + i + 4), d = _mm_loadu_pd(src + i + 6);
+        _mm_stream_pd(dst + i, a); _mm_stream_pd(dst + i + 2, b);
+        _mm_stream_pd(dst + i + 4, c); _mm_stream_pd(dst + i + 6, d);
+    }
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+#else
+    memcpy(dst, src, (size_t)n * sizeof(double));
+#endif
+}
+
 static void parallel_memcpy(double* dst, const double* src, int64_t n, int nthreads) {
-    if (nthreads <= 1 || n < (1 << 16)) { memcpy(dst, src, (size_t)n * sizeof(double)); return; }
+    if (nthreads <= 1 || n < (1 << 16)) { stream_copy(dst, src, n); return; }
     std::vector<std::thread> th;
-    const int64_t per = (n + nthreads - 1) / nthreads;
+    const int64_t per = (((n + nthreads - 1) / nthreads) + 1) & ~(int64_t)1;   // even: 16-byte aligned parts
     for (int k = 0; k < nthreads; ++k) {
         const int64_t lo = k * per, hi = lo + per < n ? lo + per : n;
         if (lo >= hi) break;
-        th.emplace_back([=] { memcpy(dst + lo, src + lo, (size_t)(hi - lo) * sizeof(double)); });
+        th.emplace_back([=] { stream_copy(dst + lo, src + lo, hi - lo); });
     }
     for (auto& t : th) t.join();
 }
@@ -338,6 +372,14 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
                                    int64_t n, cudaStream_t st, int* bad_weights,
                                    crick_stats* stats, bool clean) {
     if (td_scratch(t)) return -1;
+    // CRICK_TRACE_HOST=1: one line per call with the host-side time of every phase
+    static const bool trace = getenv("CRICK_TRACE_HOST") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
+    double t_stage = 0.0;
     cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
     if (e != cudaSuccess) return fail("flush", e);
     const long S = parallel_sample_len(n);
@@ -352,8 +394,10 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(parallel_sample_w(t->scratch), sw.data(), S * sizeof(double),
                             cudaMemcpyHostToDevice, st);
+    const auto t1 = now();
     if (e == cudaSuccess) e = parallel_begin_from_sample(t->s.v, S, t->scratch, st);
     if (e != cudaSuccess) return fail("parallel edges", e);
+    const auto t2 = now();
 
     StatsPart* sparts = nullptr;
     int snparts = 0;
@@ -364,18 +408,23 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     const int64_t chunk = staged ? kStageChunk : (int64_t)1 << 24;
     const int nbuf = staged ? kStageSlots : 2;
     unsigned hw = std::thread::hardware_concurrency();
-    const int nthreads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+    int nthreads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+    if (const char* env = getenv("CRICK_STAGE_THREADS")) { int v = atoi(env); if (v >= 1 && v <= 64) nthreads = v; }
     double* dbuf[kStageSlots] = {nullptr, nullptr, nullptr};
     cudaStream_t cst = nullptr;
     cudaEvent_t copied[kStageSlots] = {nullptr, nullptr, nullptr}, done[kStageSlots] = {nullptr, nullptr, nullptr};
     const int64_t cw = ((n < chunk ? n : chunk) + 1) & ~(int64_t)1;  // even: w half stays 16-byte aligned
     const size_t per = (size_t)cw * sizeof(double) * (w ? 2 : 1);
     int rc = 0;
-    e = cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking);
+    static_assert(kStageSlots == 3, "the handle keeps three event pairs");
+    if (!t->copy_stream) e = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
+    cst = t->copy_stream;
     for (int b = 0; b < nbuf && e == cudaSuccess; ++b) {
         e = cudaMallocAsync(reinterpret_cast<void**>(&dbuf[b]), per, st);   // stream-ordered pool: no device sync
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        if (e == cudaSuccess && !t->ev_copied[b]) e = cudaEventCreateWithFlags(&t->ev_copied[b], cudaEventDisableTiming);
+        if (e == cudaSuccess && !t->ev_done[b]) e = cudaEventCreateWithFlags(&t->ev_done[b], cudaEventDisableTiming);
+        copied[b] = t->ev_copied[b];
+        done[b] = t->ev_done[b];
     }
     if (e == cudaSuccess) {
         // the staging buffers come from st's memory pool: the copy stream may touch them only
@@ -384,6 +433,9 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
         e = cudaEventRecord(alloc_ev, st);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(cst, alloc_ev, 0);
         int k = 0;
+        const auto t3 = now();
+        if (trace) fprintf(stderr, "crick host update n=%lld: sample %.0f us, edges enqueue %.0f us, setup %.0f us",
+                           (long long)n, us(t0, t1), us(t1, t2), us(t2, t3));
         for (int64_t off = 0; off < n && e == cudaSuccess; off += chunk, ++k) {
             const int b = k % nbuf;
             const int64_t m = (n - off) < chunk ? (n - off) : chunk;
@@ -393,15 +445,29 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
             if (staged) {
                 // the slot's previous H2D copy must have left the pinned buffer
                 if (k >= nbuf && e == cudaSuccess) e = cudaEventSynchronize(copied[b]);
-                parallel_memcpy(g_stage.slot[b], x + off, m, nthreads);
-                if (w) parallel_memcpy(g_stage.slot[b] + kStageChunk, w + off, m, nthreads);
+                const auto ts = now();
+                // several writers only pay from ~4 MB (thread start-up); the copies use streaming
+                // stores (stream_copy) so that the DMA which follows finds the data in DRAM
+                const int nt = m >= ((int64_t)1 << 19) ? nthreads : 1;
+                parallel_memcpy(g_stage.slot[b], x + off, m, nt);
+                if (w) parallel_memcpy(g_stage.slot[b] + kStageChunk, w + off, m, nt);
+                t_stage += us(ts, now());
                 hx = g_stage.slot[b];
                 hw_ = w ? g_stage.slot[b] + kStageChunk : nullptr;
             }
+            cudaEvent_t tr0 = nullptr, tr1 = nullptr;
+            if (trace && k == 0) { cudaEventCreate(&tr0); cudaEventCreate(&tr1); cudaEventRecord(tr0, cst); }
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(dbuf[b], hx, m * sizeof(double), cudaMemcpyHostToDevice, cst);
             if (e == cudaSuccess && w)
                 e = cudaMemcpyAsync(dbuf[b] + cw, hw_, m * sizeof(double), cudaMemcpyHostToDevice, cst);
+            if (tr0) {
+                cudaEventRecord(tr1, cst);
+                cudaEventSynchronize(tr1);
+                float ms_ = 0; cudaEventElapsedTime(&ms_, tr0, tr1);
+                fprintf(stderr, " [first H2D %.0f us on the copy stream]", ms_ * 1e3);
+                cudaEventDestroy(tr0); cudaEventDestroy(tr1);
+            }
             if (e == cudaSuccess) e = cudaEventRecord(copied[b], cst);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, copied[b], 0);
             if (e == cudaSuccess)
@@ -417,15 +483,16 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
         }
     }
     if (e != cudaSuccess) rc = fail("host-chunked parallel update", e);
+    const auto t4 = now();
     // buffers are freed only after the work that reads them has finished
     cudaStreamSynchronize(st);
-    if (cst) { cudaStreamSynchronize(cst); cudaStreamDestroy(cst); }
-    for (int b = 0; b < nbuf; ++b) {
+    const auto t5 = now();
+    if (cst) cudaStreamSynchronize(cst);
+    for (int b = 0; b < nbuf; ++b)
         if (dbuf[b]) cudaFreeAsync(dbuf[b], st);
-        if (copied[b]) cudaEventDestroy(copied[b]);
-        if (done[b]) cudaEventDestroy(done[b]);
-    }
     if (staged) stage_release();
+    if (trace) fprintf(stderr, ", staging memcpy %.0f us, loop total %.0f us, final sync %.0f us, teardown %.0f us\n",
+                       t_stage, us(t2, t4), us(t4, t5), us(t5, now()));
     if (rc == 0) t->buf_clean = true;   // flushed above, and k_finalize leaves no buffer
     return rc;
 }
