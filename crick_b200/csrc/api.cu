@@ -368,6 +368,43 @@ static void stage_release() {
     g_stage.busy = false;
 }
 
+// Host -> device copy of `n8` 8-byte elements for the other sketches (stats.cu, spsv.cu): pageable
+// sources go through the pinned slots in 4 Mi-element pieces (streaming-store copies by several
+// threads, overlapped with the DMA of the previous piece); pinned sources, or slots in use by
+// another thread, take the plain cudaMemcpyAsync.  Returns when `src` has been consumed.
+extern "C++" {
+namespace crick {
+cudaError_t staged_copy_h2d(void* dst, const void* src, int64_t n8, cudaStream_t st) {
+    if (n8 < (1 << 17) || !is_pageable(src) || !stage_acquire())
+        return cudaMemcpyAsync(dst, src, (size_t)n8 * 8, cudaMemcpyHostToDevice, st);
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+    cudaEvent_t ev[kStageSlots] = {nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < kStageSlots && e == cudaSuccess; ++b)
+        e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+    const int64_t piece = 2 * kStageChunk;                    // a whole slot (x part | w part)
+    int k = 0;
+    for (int64_t off = 0; off < n8 && e == cudaSuccess; off += piece, ++k) {
+        const int b = k % kStageSlots;
+        const int64_t m = (n8 - off) < piece ? (n8 - off) : piece;
+        if (k >= kStageSlots) e = cudaEventSynchronize(ev[b]);      // the slot's previous DMA is done
+        if (e != cudaSuccess) break;
+        parallel_memcpy(g_stage.slot[b], reinterpret_cast<const double*>(src) + off, m,
+                        m >= ((int64_t)1 << 19) ? nthreads : 1);
+        e = cudaMemcpyAsync(reinterpret_cast<double*>(dst) + off, g_stage.slot[b], (size_t)m * 8,
+                            cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+    }
+    // the slots go back to the pool: their last DMAs must have left them
+    for (int b = 0; b < kStageSlots; ++b)
+        if (ev[b]) { if (e == cudaSuccess) e = cudaEventSynchronize(ev[b]); cudaEventDestroy(ev[b]); }
+    stage_release();
+    return e;
+}
+}  // namespace crick
+}  // extern "C++"
+
 static int td_update_host_parallel(crick_tdigest* t, const double* x, const double* w, double wsc,
                                    int64_t n, cudaStream_t st, int* bad_weights,
                                    crick_stats* stats, bool clean) {

@@ -19,6 +19,9 @@ struct DigestStore {
     void* base = nullptr;
     size_t bytes = 0;
 };
+// host -> device copy of n8 8-byte elements; pageable sources are staged through pinned slots
+cudaError_t staged_copy_h2d(void* dst, const void* src, int64_t n8, cudaStream_t st);
+
 int store_alloc(DigestStore& s, double compression, long nd);
 void store_free(DigestStore& s);
 

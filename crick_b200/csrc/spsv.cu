@@ -864,11 +864,11 @@ int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count
         if (e != cudaSuccess) return fail("cudaMallocAsync(spsv stage)", e);
         unsigned char* p = stage;
         if (!item_on_device) {
-            e = cudaMemcpyAsync(p, item, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            e = staged_copy_h2d(p, item, n, st);
             di = reinterpret_cast<const long long*>(p); p += (size_t)n * 8;
         }
         if (e == cudaSuccess && count && !count_on_device) {
-            e = cudaMemcpyAsync(p, count, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            e = staged_copy_h2d(p, count, n, st);
             dc = reinterpret_cast<const long long*>(p);
         }
     }

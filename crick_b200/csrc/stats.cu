@@ -437,11 +437,11 @@ int crick_stats_update(crick_stats_t* s, const void* x, int x_is_int64, const in
         if (e != cudaSuccess) return fail("cudaMallocAsync(stats stage)", e);
         unsigned char* p = stage;
         if (!x_on_device) {
-            e = cudaMemcpyAsync(p, x, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            e = staged_copy_h2d(p, x, n, st);
             dx = p; p += (size_t)n * 8;
         }
         if (e == cudaSuccess && count && !count_on_device) {
-            e = cudaMemcpyAsync(p, count, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+            e = staged_copy_h2d(p, count, n, st);
             dc = reinterpret_cast<const long long*>(p);
         }
     }
