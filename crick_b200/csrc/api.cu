@@ -419,6 +419,30 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
     double t_stage = 0.0;
     cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
     if (e != cudaSuccess) return fail("flush", e);
+    if (n <= kStageChunk) {
+        // one chunk: copy it (pageable sources through the staging slots) and run the
+        // device-resident update on the copy -- the sample is then drawn on the GPU at the very
+        // positions the host loop below would read, so the result is the same
+        const int64_t cw = (n + 1) & ~(int64_t)1;
+        double* d = nullptr;
+        e = cudaMallocAsync(reinterpret_cast<void**>(&d), (size_t)cw * 8 * (w ? 2 : 1), st);
+        if (e != cudaSuccess) return fail("cudaMallocAsync(stage)", e);
+        e = staged_copy_h2d(d, x, n, st);
+        if (e == cudaSuccess && w) e = staged_copy_h2d(d + cw, w, n, st);
+        StatsPart* sp1 = nullptr;
+        int sn1 = 0;
+        if (e == cudaSuccess && stats && stats_fused_begin(stats, st, &sp1, &sn1)) { cudaFreeAsync(d, st); return -1; }
+        if (e == cudaSuccess)
+            e = launch_parallel_update(t->s.v, 0, d, w ? d + cw : nullptr, wsc, n, t->scratch, sm_count(), st,
+                                       bad_weights, sp1);
+        if (e == cudaSuccess && stats && !(bad_weights && *bad_weights)) e = stats_fused_finish(stats, sm_count(), st);
+        cudaFreeAsync(d, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);    // the caller may reuse x / w at once
+        if (trace) fprintf(stderr, "crick host update n=%lld: one chunk, %.0f us\n", (long long)n, us(t0, now()));
+        if (e != cudaSuccess) return fail("host parallel update", e);
+        t->buf_clean = true;
+        return 0;
+    }
     const long S = parallel_sample_len(n);
     std::vector<double> sx((size_t)S), sw((size_t)S);
     for (long i = 0; i < S; ++i) {
