@@ -892,9 +892,8 @@ int crick_tdigest_group_update(crick_tdigest_group_t* g, const double* values, c
     size_t bytes = (size_t)total * sizeof(double) * (weights ? 2 : 1);
     cudaError_t e = cudaMallocAsync(&d, bytes, st);
     if (e != cudaSuccess) return fail("cudaMallocAsync(group stage)", e);
-    e = cudaMemcpyAsync(d, values, total * sizeof(double), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && weights)
-        e = cudaMemcpyAsync(d + total, weights, total * sizeof(double), cudaMemcpyHostToDevice, st);
+    e = staged_copy_h2d(d, values, total, st);
+    if (e == cudaSuccess && weights) e = staged_copy_h2d(d + total, weights, total, st);
     if (e == cudaSuccess && offsets) {
         e = cudaMallocAsync(&doff, (size_t)(ng + 1) * sizeof(long), st);
         if (e == cudaSuccess)
