@@ -191,17 +191,39 @@ static cudaStream_t alloc_stream() {
         streams[dev] = nullptr;
     return streams[dev];
 }
+// (Buffers of 256 MB and more keep cudaMalloc / cudaFree: returning gigabytes to the pool makes it
+// trim at some later synchronisation, i.e. inside somebody else's timed region.)
+static std::mutex g_big_mu;
+static std::vector<void*> g_big;
 void* crick_device_alloc(int64_t bytes) {
     void* p = nullptr;
+    const size_t nb = (size_t)(bytes > 0 ? bytes : 1);
+    if (nb >= ((size_t)1 << 28)) {
+        cudaError_t e = cudaMalloc(&p, nb);
+        if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
+        std::lock_guard<std::mutex> lk(g_big_mu);
+        g_big.push_back(p);
+        return p;
+    }
     tune_mempool_once();
     cudaStream_t st = alloc_stream();
-    cudaError_t e = st ? cudaMallocAsync(&p, (size_t)(bytes > 0 ? bytes : 1), st) : cudaErrorInvalidDevice;
+    cudaError_t e = st ? cudaMallocAsync(&p, nb, st) : cudaErrorInvalidDevice;
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fail("cudaMallocAsync(device array)", e); return nullptr; }
     return p;
 }
 void crick_device_free(void* p) {
     if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_big_mu);
+        for (size_t i = 0; i < g_big.size(); ++i)
+            if (g_big[i] == p) {
+                g_big[i] = g_big.back();
+                g_big.pop_back();
+                cudaFree(p);
+                return;
+            }
+    }
     cudaStream_t st = alloc_stream();
     cudaDeviceSynchronize();
     if (st) cudaFreeAsync(p, st); else cudaFree(p);
