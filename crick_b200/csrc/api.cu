@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <chrono>
+#include <map>
 #include <cstdio>
 #include <thread>
 #if defined(__x86_64__) || defined(_M_X64)
@@ -63,8 +64,10 @@ int store_alloc(DigestStore& s, double compression, long nd) {
     size_t cb = (size_t)nd * s.v.cap * sizeof(double2);
     size_t bb = (((size_t)nd * s.v.bufcap * sizeof(double2)) + 255) & ~(size_t)255;
     s.bytes = hb + 2 * cb + bb;
-    cudaError_t e = cudaMalloc(&s.base, s.bytes);
-    if (e != cudaSuccess) { s.base = nullptr; return fail("cudaMalloc(digest store)", e); }
+    // (crick_device_alloc caches freed blocks by size: creating and freeing digests in a loop does
+    // not go through cudaMalloc / cudaFree each time)
+    s.base = crick_device_alloc((int64_t)s.bytes);
+    if (!s.base) return -1;
     unsigned char* p = reinterpret_cast<unsigned char*>(s.base);
     s.v.hdr = reinterpret_cast<DevHdr*>(p); p += hb;
     s.v.cen = reinterpret_cast<double2*>(p); p += cb;
@@ -73,7 +76,7 @@ int store_alloc(DigestStore& s, double compression, long nd) {
     return 0;
 }
 void store_free(DigestStore& s) {
-    if (s.base) cudaFree(s.base);
+    if (s.base) crick_device_free(s.base);
     s.base = nullptr;
 }
 
@@ -145,8 +148,8 @@ static int td_sync_mirror(crick_tdigest* t) {
 static int td_scratch(crick_tdigest* t) {
     if (t->scratch) return 0;
     size_t b = parallel_scratch_bytes(t->s.v.comp, sm_count());
-    cudaError_t e = cudaMalloc(&t->scratch, b);
-    if (e != cudaSuccess) { t->scratch = nullptr; return fail("cudaMalloc(parallel scratch)", e); }
+    t->scratch = crick_device_alloc((int64_t)b);
+    if (!t->scratch) return -1;
     t->scratch_bytes = b;
     return 0;
 }
@@ -176,57 +179,68 @@ void* crick_host_alloc(int64_t bytes) {
     return p;
 }
 void crick_host_free(void* p) { if (p) cudaFreeHost(p); }
-// Device buffers of the Python-side DeviceArray come from the stream-ordered pool (a cudaMalloc
-// of tens of MB costs ~0.6 ms, e.g. the output of every large device query): allocated on a
-// per-device helper stream and synchronised, so the memory is valid on every stream; freed after
-// a device synchronisation, so nothing can still be using it.
-static void tune_mempool_once();
-static cudaStream_t alloc_stream() {
-    static cudaStream_t streams[64] = {};
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess)
-        streams[dev] = nullptr;
-    return streams[dev];
-}
-// (Buffers of 256 MB and more keep cudaMalloc / cudaFree: returning gigabytes to the pool makes it
-// trim at some later synchronisation, i.e. inside somebody else's timed region.)
-static std::mutex g_big_mu;
-static std::vector<void*> g_big;
+// Device buffers handed out by the library (DeviceArray, digest stores, parallel scratch): plain
+// cudaMalloc, plus a small cache of freed blocks by size.  A cudaMalloc / cudaFree pair costs
+// 0.1-25 ms once the process has tens of GB mapped (bench.py's e2e leg creates and frees a digest
+// per step; every large device query allocates its output), and returning blocks to the driver's
+// stream-ordered pool instead makes it trim at some later synchronisation.  Blocks up to 128 MB
+// are kept, 1 GB in total; a block is only cached after a device synchronisation, so whoever
+// gets it next cannot race with its previous user.
+static std::mutex g_mem_mu;
+static std::map<void*, size_t> g_mem_size;                 // live blocks
+static std::multimap<size_t, void*> g_mem_cache;           // freed blocks by size
+static size_t g_mem_cached = 0;
 void* crick_device_alloc(int64_t bytes) {
-    void* p = nullptr;
     const size_t nb = (size_t)(bytes > 0 ? bytes : 1);
-    if (nb >= ((size_t)1 << 28)) {
-        cudaError_t e = cudaMalloc(&p, nb);
-        if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
-        std::lock_guard<std::mutex> lk(g_big_mu);
-        g_big.push_back(p);
-        return p;
+    void* p = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        auto it = g_mem_cache.find(nb);
+        if (it != g_mem_cache.end()) {
+            p = it->second;
+            g_mem_cache.erase(it);
+            g_mem_cached -= nb;
+            g_mem_size[p] = nb;
+            return p;
+        }
     }
-    tune_mempool_once();
-    cudaStream_t st = alloc_stream();
-    cudaError_t e = st ? cudaMallocAsync(&p, nb, st) : cudaErrorInvalidDevice;
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { fail("cudaMallocAsync(device array)", e); return nullptr; }
+    cudaError_t e = cudaMalloc(&p, nb);
+    if (e != cudaSuccess) {
+        // give the cached blocks back and try once more
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_mem_mu);
+            for (auto& kv : g_mem_cache) drop.push_back(kv.second);
+            g_mem_cache.clear();
+            g_mem_cached = 0;
+        }
+        cudaGetLastError();
+        for (void* q : drop) cudaFree(q);
+        e = cudaMalloc(&p, nb);
+    }
+    if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    g_mem_size[p] = nb;
     return p;
 }
 void crick_device_free(void* p) {
     if (!p) return;
+    size_t nb = 0;
     {
-        std::lock_guard<std::mutex> lk(g_big_mu);
-        for (size_t i = 0; i < g_big.size(); ++i)
-            if (g_big[i] == p) {
-                g_big[i] = g_big.back();
-                g_big.pop_back();
-                cudaFree(p);
-                return;
-            }
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        auto it = g_mem_size.find(p);
+        if (it != g_mem_size.end()) { nb = it->second; g_mem_size.erase(it); }
     }
-    cudaStream_t st = alloc_stream();
-    cudaDeviceSynchronize();
-    if (st) cudaFreeAsync(p, st); else cudaFree(p);
+    if (nb && nb <= ((size_t)128 << 20)) {
+        cudaDeviceSynchronize();
+        std::lock_guard<std::mutex> lk(g_mem_mu);
+        if (g_mem_cached + nb <= ((size_t)1 << 30)) {
+            g_mem_cache.emplace(nb, p);
+            g_mem_cached += nb;
+            return;
+        }
+    }
+    cudaFree(p);
 }
 int crick_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream) {
     cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice,
@@ -302,7 +316,7 @@ void crick_tdigest_free(crick_tdigest_t* t) {
         if (t->ev_copied[b]) cudaEventDestroy(t->ev_copied[b]);
         if (t->ev_done[b]) cudaEventDestroy(t->ev_done[b]);
     }
-    if (t->scratch) cudaFree(t->scratch);
+    if (t->scratch) crick_device_free(t->scratch);
     store_free(t->s);
     delete t;
 }
