@@ -102,8 +102,7 @@ constexpr size_t kTabBytes = ((size_t)kTabLen * 2 + 15) & ~(size_t)15;
 constexpr int kEMax = 1024;      // max edges (buckets - 1)
 constexpr int kBPad = kEMax + 8; // row stride of the per-CTA partial sums
 constexpr long kSMax = 16384;    // max sample size (rank error with 16 Ki = with 64 Ki)
-constexpr int kSortChunk = 1024; // elements sorted per CTA in shared memory (one SM sorts
-                                 // 4096 in 73 us, 16 SMs sort 1024 each in ~9 us: r1_o launch list)
+constexpr int kSortChunk = 1024; // elements per sorted run = threads per CTA of k_sort_runs
 
 struct ParHeader {
     int E;       // number of edges; buckets = E + 1, bucket b = [edge[b-1], edge[b])
@@ -628,18 +627,18 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
 // History (profiles/): (r1_a) resolving intra-warp bucket collisions with __match_any_sync
 // saturates the ADU pipe (92 %) at ~0.5 value/clk/SM; (r1_b) per-warp tables with 8 columns and
 // 4 lane passes: 103 instructions per 32 values on 8 warps, latency bound.  This version:
-//   * ONE table acc[bucket][C] of double2 in shared memory, C = 32 columns when it fits
-//     (c <= 100), else 16 / 8: lane l owns column l % C, so LDS.128 / STS.128 of a warp are
-//     conflict-free and need neither MATCH nor atomics (C < 32: the 32/C lanes that share a
-//     column take turns in passes);
-//   * the warps take turns on the table: a token travels round-robin over named barriers
+//   * TWO tables acc[bucket][C] of double2 in shared memory (acc_cfg below), C = 32 columns
+//     when they fit (c <= 100), else 16 / 8 / 4: lane l owns column l % C, so LDS.128 / STS.128
+//     of a warp are conflict-free and need neither MATCH nor atomics (C < 32: the 32/C lanes
+//     that share a column take turns in passes);
+//   * the 7 warps of a table take turns on it: a token travels round-robin over named barriers
 //     (bar.sync / bar.arrive on 64 threads) and only the holder does its read-modify-writes,
-//     4 LDS + 8 DADD + 4 STS per 128 values; loads, bucket lookup and de-duplication run
-//     outside the critical section on all 12 warps.  The fixed order makes sums deterministic;
+//     8 LDS + 16 DADD + 8 STS per 256-value tile; loads, bucket lookup and de-duplication run
+//     outside the critical section on all 14 warps.  The fixed order makes sums deterministic;
 //   * a lane's 4 values of one group are de-duplicated in registers first (equal buckets are
 //     folded, the later one is redirected to a dummy row), so the 4 read-modify-writes are
 //     independent and overlap.
-// Bucket lookup: one uint16 probe of the 16384-cell table (k_make_edges picks the grid), then a
+// Bucket lookup: one uint16 probe of the 8192-cell table (k_make_edges picks the grid), then a
 // branch-free count of the <= kmax edges of that cell that are <= x.  Shared memory is
 // addressed with 32-bit shared-window addresses (inline PTX) to keep the integer work short.
 constexpr int kU = 4;         // values per lane per group
