@@ -190,25 +190,31 @@ void crick_host_free(void* p) { if (p) cudaFreeHost(p); }
 // digest costs ~0.7 ms -- and go back to the cache, never to the driver.
 static std::mutex g_mem_mu;
 static std::map<void*, size_t> g_mem_size;                 // live blocks (bit 63: carved from a slab)
-static unsigned char* g_slab = nullptr;
-static size_t g_slab_left = 0;
+static std::map<void*, int> g_mem_dev;                     // ... and the device they live on
+static unsigned char* g_slab_of[64] = {};
+static size_t g_slab_left_of[64] = {};
 constexpr size_t kSlabBytes = (size_t)8 << 20, kSlabMaxBlock = (size_t)256 << 10;
 constexpr size_t kCarved = (size_t)1 << 63;
-static std::multimap<size_t, void*> g_mem_cache;           // freed blocks by size
+static std::multimap<std::pair<int, size_t>, void*> g_mem_cache;   // freed blocks by (device, size)
 static size_t g_mem_cached = 0;
 void* crick_device_alloc(int64_t bytes) {
     size_t nb = (size_t)(bytes > 0 ? bytes : 1);
     const bool small = nb <= kSlabMaxBlock;
     if (small) nb = (nb + 255) & ~(size_t)255;
     void* p = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { fail_msg("no CUDA device"); return nullptr; }
     {
         std::lock_guard<std::mutex> lk(g_mem_mu);
-        auto it = g_mem_cache.find(nb);
+        unsigned char*& g_slab = g_slab_of[dev];
+        size_t& g_slab_left = g_slab_left_of[dev];
+        auto it = g_mem_cache.find(std::make_pair(dev, nb));
         if (it != g_mem_cache.end()) {
             p = it->second;
             g_mem_cache.erase(it);
             if (!small) g_mem_cached -= nb;
             g_mem_size[p] = nb | (small ? kCarved : 0);
+            g_mem_dev[p] = dev;
             return p;
         }
         if (small) {
@@ -223,6 +229,7 @@ void* crick_device_alloc(int64_t bytes) {
                 g_slab += nb;
                 g_slab_left -= nb;
                 g_mem_size[p] = nb | kCarved;
+                g_mem_dev[p] = dev;
                 return p;
             }
         }
@@ -234,7 +241,7 @@ void* crick_device_alloc(int64_t bytes) {
         {
             std::lock_guard<std::mutex> lk(g_mem_mu);
             for (auto it = g_mem_cache.begin(); it != g_mem_cache.end();) {
-                if (it->first > kSlabMaxBlock) { drop.push_back(it->second); it = g_mem_cache.erase(it); }
+                if (it->first.second > kSlabMaxBlock) { drop.push_back(it->second); it = g_mem_cache.erase(it); }
                 else ++it;                        // slab pieces cannot be returned one by one
             }
             g_mem_cached = 0;
@@ -246,28 +253,32 @@ void* crick_device_alloc(int64_t bytes) {
     if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
     std::lock_guard<std::mutex> lk(g_mem_mu);
     g_mem_size[p] = nb;
+    g_mem_dev[p] = dev;
     return p;
 }
 void crick_device_free(void* p) {
     if (!p) return;
     size_t nb = 0;
+    int dev = 0;
     {
         std::lock_guard<std::mutex> lk(g_mem_mu);
         auto it = g_mem_size.find(p);
         if (it != g_mem_size.end()) { nb = it->second; g_mem_size.erase(it); }
+        auto jt = g_mem_dev.find(p);
+        if (jt != g_mem_dev.end()) { dev = jt->second; g_mem_dev.erase(jt); }
     }
     if (nb & kCarved) {                       // part of a slab: always back to the cache
         nb &= ~kCarved;
         cudaDeviceSynchronize();
         std::lock_guard<std::mutex> lk(g_mem_mu);
-        g_mem_cache.emplace(nb, p);
+        g_mem_cache.emplace(std::make_pair(dev, nb), p);
         return;
     }
     if (nb && nb <= ((size_t)128 << 20)) {
         cudaDeviceSynchronize();
         std::lock_guard<std::mutex> lk(g_mem_mu);
         if (g_mem_cached + nb <= ((size_t)1 << 30)) {
-            g_mem_cache.emplace(nb, p);
+            g_mem_cache.emplace(std::make_pair(dev, nb), p);
             g_mem_cached += nb;
             return;
         }
