@@ -47,6 +47,8 @@ _SIG = {
     "crick_tdigest_add": (c_int, [_P, c_double, c_double]),
     "crick_tdigest_update": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P]),
     "crick_tdigest_update_checked": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P, _P]),
+    "crick_tdigest_update_deferred": (c_int, [_P, _P, _P, c_double, c_int64, c_int, _P]),
+    "crick_tdigest_take_bad_weights": (c_int, [_P]),
     "crick_tdigest_update_stats": (c_int, [_P, _P, _P, _P, c_double, c_int64, c_int, c_int, _P, _P]),
     "crick_tdigest_flush": (c_int, [_P]),
     "crick_tdigest_merge": (c_int, [_P, _P, c_int]),

@@ -151,6 +151,10 @@ static int td_scratch(crick_tdigest* t) {
     t->scratch = crick_device_alloc((int64_t)b);
     if (!t->scratch) return -1;
     t->scratch_bytes = b;
+    // the header (sticky flags) starts zeroed; ordered before every use: all of them go through
+    // td_stream(), which chains the handle's streams
+    cudaError_t e = cudaMemsetAsync(t->scratch, 0, 256, t->last ? t->last : t->own);
+    if (e != cudaSuccess) return fail("cudaMemsetAsync(scratch)", e);
     return 0;
 }
 
@@ -639,7 +643,7 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
 
 static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                      int64_t n, int x_on_device, int w_on_device, int mode, void* stream,
-                     int* bad_weights, crick_stats* stats);
+                     int* bad_weights, crick_stats* stats, bool defer_check = false);
 
 int crick_tdigest_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                          int64_t n, int x_on_device, int w_on_device, int mode, void* stream) {
@@ -665,9 +669,25 @@ int crick_tdigest_update_stats(crick_tdigest_t* t, crick_stats_t* stats, const d
                      bad_weights, stats);
 }
 
+int crick_tdigest_update_deferred(crick_tdigest_t* t, const double* x, const double* w,
+                                  double w_scalar, int64_t n, int mode, void* stream) {
+    const bool parallel = mode == CRICK_MODE_PARALLEL ||
+                          (mode == CRICK_MODE_AUTO && n >= (int64_t)CRICK_PARALLEL_MIN);
+    if (!parallel) return fail_msg("update_deferred: the deferred weight check exists in parallel mode only");
+    return td_update(t, x, w, w_scalar, n, 1, 1, mode, stream, nullptr, nullptr, true);
+}
+
+int crick_tdigest_take_bad_weights(crick_tdigest_t* t) {
+    if (!t->scratch) return 0;
+    int bad = 0;
+    cudaError_t e = parallel_take_bad_weights(t->scratch, td_stream(t, nullptr), &bad);
+    if (e != cudaSuccess) return fail("take_bad_weights", e);
+    return bad ? 1 : 0;
+}
+
 static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                      int64_t n, int x_on_device, int w_on_device, int mode, void* stream,
-                     int* bad_weights, crick_stats* stats) {
+                     int* bad_weights, crick_stats* stats, bool defer_check) {
     if (n <= 0) return 0;  // tdigest_stubs.c:648-650
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
@@ -680,6 +700,13 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
     const bool w_arr = w != nullptr;
     if (w_arr && (x_on_device != w_on_device))
         return fail_msg("x and w must both be host or both be device arrays");
+    // a scalar weight tdigest_add drops (w <= DBL_EPSILON, tdigest_stubs.c:285) drops every
+    // sample: the digest stays as it is (the parallel pass only tests weights it loads)
+    if (!w_arr && w_scalar <= DBL_EPSILON) {
+        t->buf_clean = clean;
+        // (the fused moments do not depend on the weight: stats.update(x))
+        return stats ? crick_stats_update(stats, x, 0, nullptr, 1, n, x_on_device, 0, stream) : 0;
+    }
     if (!x_on_device) {
         if (parallel) return td_update_host_parallel(t, x, w, w_scalar, n, st, bad_weights, stats, clean);
         // reference mode from host memory: stage the whole (small) input
@@ -708,7 +735,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
         if (stats && stats_fused_begin(stats, st, &sparts, &snparts)) return -1;
         if (e == cudaSuccess)
             e = launch_parallel_update(t->s.v, 0, x, w, w_scalar, n, t->scratch, sm_count(), st,
-                                       bad_weights, sparts);
+                                       bad_weights, sparts, defer_check);
         if (e == cudaSuccess && stats && !(bad_weights && *bad_weights))
             e = stats_fused_finish(stats, sm_count(), st);
         if (e == cudaSuccess) t->buf_clean = true;   // flushed above, and k_finalize leaves no buffer
@@ -842,8 +869,9 @@ int crick_tdigest_reset(crick_tdigest_t* t, void* stream) {
     cudaStream_t st = td_stream(t, stream);
     t->px.clear();
     t->pw.clear();
-    t->mirror_ok = false; t->buf_clean = false;
+    t->mirror_ok = false;
     cudaError_t e = launch_init_hdr(t->s.v.hdr, 1, st);
+    t->buf_clean = e == cudaSuccess;      // an empty digest has an empty buffer
     return e == cudaSuccess ? 0 : fail("reset", e);
 }
 
@@ -864,8 +892,12 @@ int crick_tdigest_record_doubles(crick_tdigest_t* t) { return 4 + 2 * t->s.v.cap
 int crick_tdigest_export_record(crick_tdigest_t* t, double* record_dev, void* stream) {
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
-    t->mirror_ok = false; t->buf_clean = false;
-    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    // (no flush launch when the host knows the insertion buffer is empty, e.g. right after a
+    // parallel-mode update: one launch less on the critical path of a multi-GPU step)
+    const bool clean = t->buf_clean;
+    cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
+    if (!clean) t->mirror_ok = false;
+    t->buf_clean = e == cudaSuccess;
     if (e == cudaSuccess) e = launch_pack_record(t->s.v, 0, record_dev, st);
     return e == cudaSuccess ? 0 : fail("export_record", e);
 }
@@ -883,8 +915,9 @@ int crick_tdigest_merge_records_bulk(crick_tdigest_t* t, const double* records_d
                                      void* stream) {
     cudaStream_t st = td_stream(t, stream);
     if (td_drain(t, st)) return -1;
+    const bool clean = t->buf_clean;
     t->mirror_ok = false; t->buf_clean = false;
-    cudaError_t e = launch_flush(t->s.v, 0, 1, 1, st);
+    cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
     if (e == cudaSuccess) {
         e = launch_merge_records_bulk(t->s.v, 0, records_dev, n_records, st);
         if (e == cudaErrorInvalidValue) {   // union too large for one CTA: sequential merge

@@ -52,8 +52,13 @@ size_t parallel_scratch_bytes(double compression, int sm_count);
 // synchronises, and leaves the digest untouched when *bad_weights comes back non-zero.
 cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
                                    double wsc, long n, void* scratch, int sm_count,
-                                   cudaStream_t st, int* bad_weights, StatsPart* stats_parts);
+                                   cudaStream_t st, int* bad_weights, StatsPart* stats_parts,
+                                   bool defer_check = false);
 cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad);
+// defer_check: validate like bad_weights != nullptr does (a failed check leaves the digest
+// untouched) but keep the verdict on the device, sticky, until parallel_take_bad_weights reads
+// and clears it -- the update then needs no host synchronisation at all
+cudaError_t parallel_take_bad_weights(void* scratch, cudaStream_t st, int* bad);
 // The same pipeline in pieces, for host-resident input streamed in chunks: edges
 // from a caller-provided sample (copied to parallel_sample_x/w), any number of
 // accumulate calls (first = 1 on the first), then one finalize.

@@ -106,16 +106,16 @@ constexpr int kSortChunk = 1024; // elements per sorted run = threads per CTA of
 
 struct ParHeader {
     int E;       // number of edges; buckets = E + 1, bucket b = [edge[b-1], edge[b])
-    int shift;   // grid 0: cell = (((skey(x) >> 1) - kbase) >> shift) + 1
+    int shift;   // grid 0: cell = ((skey32(x) >> 1) - kbase) >> shift, kbase includes the "+ 1 cell"
     int kbase;
-    int pad0;
+    int badw_sticky;  // set by k_finalize when it refused an update because of badw; cleared by the host
     long S;      // sample length (power of two)
     int ncta;    // CTAs that wrote partials
     int grid;    // lookup grid: 0 = linear in the ordered bit pattern, 1 = linear in x
     int kmax;    // most edges in any one cell of that grid
     int badw;    // set by k_bin_accumulate: some weight is not finite or not > 0 (tdigest.pyx:304)
     double sample_total;
-    double x0;   // grid 1: cell = (int)((x - x0) * inv) + 1
+    double x0;   // grid 1: cell = floor(fma(x, inv, x0)), x0 = 1 - (first edge) * inv
     double inv;
 };
 
@@ -374,21 +374,32 @@ static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double
 //  grid 0: linear in the (signed-orderable) HIGH WORD of the bit pattern, i.e. ~ log|x| with
 //          2^-20 relative resolution -- good for heavy-tailed data of one sign;
 //  grid 1: linear in x -- good for data that crosses zero or sits in a narrow band.
-__device__ __forceinline__ int skey_half(double x) {
-    int hi = __double2hiint(x + 0.0);                  // -0.0 -> +0.0: zeros tie
-    return (hi ^ ((hi >> 31) & 0x7fffffff)) >> 1;      // signed order == order of x; >> 1: no overflow below
+// signed 32-bit key of the high word: non-decreasing in x (all the lookup needs), -0.0 ties +0.0
+// (negative values get +1, so the largest negative key, 0, is the key of +0.0) -- integer ALU
+// only: SHF, LOP3, IADD
+__device__ __forceinline__ int skey32(double x) {
+    const int hi = __double2hiint(x);
+    const int m = hi >> 31;
+    return (hi ^ (m & 0x7fffffff)) - m;
 }
-__device__ __forceinline__ int clamp_cell(int c) {     // c = -1 (below) .. -> cell 0 .. kNC - 1
-    c += 1;
+__device__ __forceinline__ int skey_half(double x) { return skey32(x) >> 1; }   // >> 1: no overflow below
+__device__ __forceinline__ int clamp_cell0(int c) {     // -> cell 0 .. kNC - 1
     c = c < 0 ? 0 : c;
     return c > kNC - 1 ? kNC - 1 : c;
 }
-__device__ __forceinline__ int cell_key(double x, int kbase, int shift) {
-    return clamp_cell((skey_half(x) - kbase) >> shift);
+// grid 0: kb1 = kbase - (1 << shift), i.e. ((skey_half - kbase) >> shift) + 1: cell 0 = below the first edge
+__device__ __forceinline__ int cell_key(double x, int kb1, int shift) {
+    return clamp_cell0((skey_half(x) - kb1) >> shift);
 }
-__device__ __forceinline__ int cell_lin(double x, double x0, double inv) {
-    // cvt.rmi.s32.f64 saturates (NaN -> 0): any finite or infinite x gives a valid cell
-    return clamp_cell(__double2int_rd(__dmul_rn(__dadd_rn(x, -x0), inv)));
+// grid 1: t = (x - x0) * inv + 1 as ONE fused multiply-add with c0 = 1 - x0 * inv (monotone in x:
+// a single rounding of an increasing affine map), then cvt.rmi.u32.f64, which saturates (negative
+// and NaN -> 0), and one unsigned min: 3 instructions.  The same function places the edges
+// (k_make_edges) and the values (k_bin_accumulate), so its exact rounding does not matter.
+__device__ __forceinline__ int cell_lin(double x, double c0, double inv) {
+    unsigned c;
+    const double t = __fma_rn(x, inv, c0);
+    asm("cvt.rmi.u32.f64 %0, %1;" : "=r"(c) : "d"(t));
+    return (int)(c > (unsigned)(kNC - 1) ? (unsigned)(kNC - 1) : c);
 }
 
 // inclusive scan over the 1024 threads of the CTA (warp shuffles + one pass of warp 0 over the
@@ -535,17 +546,19 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     // d. lookup tables: tab[c] = #edges whose cell is < c (so the edges of cell c are
     // tab[c] .. tab[c+1]-1), for both grids; keep the one whose fullest cell holds fewer edges
     // (ties: fewer expected compares).
-    int kbase = 0, shift = 0;
-    double x0 = 0.0, inv = 0.0;
+    int kbase = 0, shift = 0, kb1 = 0;
+    double x0 = 0.0, inv = 0.0, c0 = 0.0;
     bool lin_ok = false;
     if (En > 0) {
         kbase = skey_half(s_edge[0]);
         long long span = (long long)skey_half(s_edge[En - 1]) - (long long)kbase;
         while (shift < 31 && ((span >> shift) + 1ll) > (long long)(kNC - 2)) ++shift;
+        kb1 = kbase - (1 << shift);        // shift <= 19 (the span is below 2^32)
         x0 = s_edge[0];
         double width = s_edge[En - 1] - x0;
         inv = (double)(kNC - 2) / width;
-        lin_ok = En >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv);
+        c0 = 1.0 - x0 * inv;
+        lin_ok = En >= 2 && width > 0.0 && is_finite_d(width) && is_finite_d(inv) && is_finite_d(c0);
     }
     // count the edges of every cell (edges are sorted and cell() is monotone) for both grids in
     // one pass -- grid 0 in the low, grid 1 in the high half-word of the same counter -- then an
@@ -558,8 +571,8 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         __syncthreads();
         for (int j = tid; j < En; j += blockDim.x) {
             const double e = s_edge[j];
-            atomicAdd(&s_cnt2[cell_key(e, kbase, shift) + 1], 1);          // counted at index cell + 1
-            if (lin_ok) atomicAdd(&s_cnt2[cell_lin(e, x0, inv) + 1], 1 << 16);
+            atomicAdd(&s_cnt2[cell_key(e, kb1, shift) + 1], 1);          // counted at index cell + 1
+            if (lin_ok) atomicAdd(&s_cnt2[cell_lin(e, c0, inv) + 1], 1 << 16);
         }
         __syncthreads();
         int local[2] = {0, 0}, lmax[2] = {0, 0}, run[2] = {0, 0};
@@ -585,8 +598,13 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         for (int k = 0; k < kPer; ++k) {
             const int cc = c0 + k;
             if (cc < kTabLen) {
-                s_tab[cc] = (unsigned short)(off0 + vals[0][k]);
-                s_tab[kTabLen + cc] = (unsigned short)(off1 + vals[1][k]);
+                // entry = (#edges in the cells before cc) << 2 | min(#edges in cell cc, 3): the
+                // low bits let the hot kernel skip the edge loads of the ~95 % of values whose
+                // cell holds no edge (shared-memory wavefronts are what bounds it)
+                const int nx = s_cnt2[cc + 1];
+                const int n0 = nx & 0xffff, n1 = nx >> 16;
+                s_tab[cc] = (unsigned short)(((off0 + vals[0][k]) << 2) | (n0 < 3 ? n0 : 3));
+                s_tab[kTabLen + cc] = (unsigned short)(((off1 + vals[1][k]) << 2) | (n1 < 3 ? n1 : 3));
             }
         }
 #pragma unroll
@@ -610,13 +628,13 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     if (tid == 0) {
         hdr->E = En;
         hdr->shift = shift;
-        hdr->kbase = kbase;
+        hdr->kbase = kb1;
         hdr->sample_total = Wt;
         hdr->ncta = 0;
         hdr->grid = grid;
         hdr->badw = 0;
         hdr->kmax = s_kmax[grid];
-        hdr->x0 = x0;
+        hdr->x0 = c0;
         hdr->inv = inv;
     }
 }
@@ -672,13 +690,22 @@ __device__ __forceinline__ void bar_arrive64(int id) {
 
 // if (ai == aj) { wj += wi; sj += si; ai = daddr; } without branches: f = 1.0 or 0.0 from one
 // 32-bit select, then two fused multiply-adds (exact: the product is wi or 0).  ptxas turns a
-// predicated add.f64 into DADD + 2 FSEL per double (r1_g profile: 14 FSEL per value).
+// predicated add.f64 -- also one written as "@p add.f64" in PTX -- into DADD + 2 FSEL per double
+// (r1_g profile: 14 FSEL per value; checked again in round 2).
 // Caveat: a non-finite wi / si (w*x overflow) times 0 is NaN.
 __device__ __forceinline__ void fold_if_equal(unsigned& ai, unsigned aj, double& wj, double& sj,
                                               double wi, double si, unsigned daddr) {
     const bool eq = ai == aj;
     const double f = __hiloint2double(eq ? 0x3ff00000 : 0, 0);
     wj = __fma_rn(wi, f, wj);
+    sj = __fma_rn(si, f, sj);
+    ai = eq ? daddr : ai;
+}
+// the same for one sum (unweighted input)
+__device__ __forceinline__ void fold_if_equal1(unsigned& ai, unsigned aj, double& sj, double si,
+                                               unsigned daddr) {
+    const bool eq = ai == aj;
+    const double f = __hiloint2double(eq ? 0x3ff00000 : 0, 0);
     sj = __fma_rn(si, f, sj);
     ai = eq ? daddr : ai;
 }
@@ -707,9 +734,9 @@ __device__ __forceinline__ bool classify_group(const Lookup& L, const double* xs
     for (int u = 0; u < kU; ++u) {
         int cell = GRID == 1 ? cell_lin(xs[u], L.x0, L.inv) : cell_key(xs[u], L.kbase, L.shift);
         unsigned ta = L.tab + 2u * (unsigned)cell;
-        b[u] = (int)lds_u16(ta);
+        b[u] = (int)(lds_u16(ta) >> 2);                    // (low 2 bits: #edges in the cell, unused here)
         if (FAST) ea[u] = L.edges + 8u * (unsigned)b[u];
-        else ea[u] = lds_u16(ta + 2u);                     // hi = first edge of the next cell
+        else ea[u] = lds_u16(ta + 2u) >> 2;                // hi = first edge of the next cell
     }
     if (FAST) {
         // edges of later cells are > x and the pad is +inf: counting kmax entries is exact
@@ -1163,6 +1190,423 @@ __global__ void __launch_bounds__(STATS ? 384 : 448, 1) k_bin_accumulate(const d
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 4b. k_bin_accumulate2 -- the round-2 shape of the hot kernel (the one that runs unless fused
+// moments or the TMA-staged single-table variant are asked for).  Same partition, same token ring,
+// same deterministic order as k_bin_accumulate; what changed (ncu r1_z: 58.6 warp instructions per
+// 32 values at 57 % issue, 28 % of the warp time waiting for the token):
+//   * a TILE-LEVEL screen replaces the per-value filter: one chained compare per value decides
+//     whether the whole 256-value tile is clean (every x finite, every w in (eps, DBL_MAX]); clean
+//     tiles -- all of them in practice -- take classify_lean (no dummy-row selects, no per-value
+//     weight logic, edge compares at immediate offsets), the others the exact round-1 path;
+//   * cells cost 3 instructions (grid 1: one FMA + one saturating convert + one min) or 8 integer
+//     ones (grid 0, no fp64);
+//   * UNWEIGHTED input (w is a scalar: the call dask makes, tdigest.pyx:294-295): sum w is a
+//     COUNT.  It lives in one u32 counter per bucket updated with red.shared.add.u32 (SASS
+//     ATOMS.POPC.INC: the hardware folds equal addresses of a warp, 2.7-3.3 cycles per warp
+//     instruction, tests/tools/mb_atoms.cu) outside the token; only sum x (8 bytes) needs the
+//     ring.  The rows halve, FOUR tables of 32 columns fit where two did, and the rings shorten
+//     from 7 warps to 4 (16 warps per CTA).
+template <int GRID>
+__device__ __forceinline__ int cell_of(const Lookup& L, double x) {
+    return GRID == 1 ? cell_lin(x, L.x0, L.inv) : cell_key(x, L.kbase, L.shift);
+}
+
+// b += (edge at [ea + OFF] <= x): LDS.64 at an immediate offset, DSETP, predicated add
+template <int OFF>
+__device__ __forceinline__ void edge_step(int& b, unsigned ea, double x) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f64 e;\n\t"
+        "ld.shared.f64 e, [%1+%3];\n\t"
+        "setp.le.f64 p, e, %2;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t}"
+        : "+r"(b) : "r"(ea), "d"(x), "n"(OFF));
+}
+
+// buckets of kU values: one uint16 probe + KM predicated edge compares (KM = 0: L.kmax <= kKFast
+// of them; KM < 0: a binary search over the cell's edges -- data whose mass sits in a few narrow
+// far-apart clusters puts many edges into one cell)
+template <int GRID, int KM>
+__device__ __forceinline__ void buckets_of(const Lookup& L, const double* xs, int* b) {
+    unsigned v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        const int cell = cell_of<GRID>(L, xs[u]);
+        const unsigned ta = L.tab + 2u * (unsigned)cell;
+        v[u] = lds_u16(ta);
+        if (KM < 0) v[u] |= lds_u16(ta + 2u) << 16;        // + the entry of the next cell
+    }
+    if (KM < 0) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            int lo = (int)((v[u] & 0xffffu) >> 2), hi = (int)(v[u] >> 18);
+            while (lo < hi) {                              // #edges <= x among the cell's candidates
+                const int mid = (lo + hi) >> 1;
+                if (lds_f64(L.edges + 8u * (unsigned)mid) <= xs[u]) lo = mid + 1; else hi = mid;
+            }
+            b[u] = lo;
+        }
+    } else if (KM > 0) {
+        // the cell holds n = v & 3 <= KM edges: load and compare only those (a lane whose cell has
+        // none issues no shared-memory request at all)
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (KM == 1) {
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .f64 e;\n\t.reg .u32 c, a;\n\t"
+                    "and.b32 c, %1, 3;\n\t"
+                    "shr.u32 %0, %1, 2;\n\t"
+                    "setp.ne.u32 p, c, 0;\n\t"
+                    "mad.lo.u32 a, %0, 8, %2;\n\t"
+                    "@p ld.shared.f64 e, [a];\n\t"
+                    "@p setp.le.f64 p, e, %3;\n\t"
+                    "@p add.s32 %0, %0, 1;\n\t}"
+                    : "=r"(b[u]) : "r"(v[u]), "r"(L.edges), "d"(xs[u]));
+            } else {
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .f64 e;\n\t.reg .u32 c, a;\n\t"
+                    "and.b32 c, %1, 3;\n\t"
+                    "shr.u32 %0, %1, 2;\n\t"
+                    "setp.ne.u32 p, c, 0;\n\t"
+                    "mad.lo.u32 a, %0, 8, %2;\n\t"
+                    "@p ld.shared.f64 e, [a];\n\t"
+                    "@p setp.le.f64 p, e, %3;\n\t"
+                    "@p add.s32 %0, %0, 1;\n\t"
+                    "setp.gt.u32 p, c, 1;\n\t"
+                    "@p ld.shared.f64 e, [a+8];\n\t"
+                    "@p setp.le.f64 p, e, %3;\n\t"
+                    "@p add.s32 %0, %0, 1;\n\t}"
+                    : "=r"(b[u]) : "r"(v[u]), "r"(L.edges), "d"(xs[u]));
+            }
+        }
+    } else {
+        unsigned ea[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { b[u] = (int)(v[u] >> 2); ea[u] = L.edges + 8u * (unsigned)b[u]; }
+#pragma unroll 1
+        for (int j = 0; j < L.kmax; ++j) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .f64 e;\n\t"
+                    "ld.shared.f64 e, [%1];\n\t"
+                    "setp.le.f64 p, e, %2;\n\t"
+                    "@p add.s32 %0, %0, 1;\n\t}"
+                    : "+r"(b[u]) : "r"(ea[u]), "d"(xs[u]));
+                ea[u] += 8u;
+            }
+        }
+    }
+}
+
+struct Lookup2 {
+    Lookup L;
+    unsigned row_bytes;   // byte stride of a bucket row of this warp's table
+    unsigned cnt;         // unweighted: shared-window address of the u32 counters
+};
+
+// every x of the tile finite, every w in (eps, DBL_MAX]?  (w: on the high word -- a weight within
+// 2^-20 relative of eps counts as suspicious and sends the tile down the exact path)
+template <bool HAS_W>
+__device__ __forceinline__ bool tile_clean(const double* xs, const double* ws) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 2 * kU; ++k) ok = ok && (fabs(xs[k]) <= DBL_MAX);
+    if (HAS_W) {
+        unsigned worst = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * kU; ++k) {
+            const unsigned d = (unsigned)__double2hiint(ws[k]) - 0x3CB00001u;   // hi(eps) = 0x3CB00000
+            worst = d > worst ? d : worst;
+        }
+        ok = ok && worst <= 0x7FEFFFFFu - 0x3CB00001u;
+    }
+    return __all_sync(CRICK_FULL, ok);
+}
+
+// clean tile, weighted: addresses + (w, w*x), equal buckets of the lane folded
+template <int GRID, int KM>
+__device__ __forceinline__ bool classify_lean_w(const Lookup2& Q, const double* xs, const double* ws,
+                                                unsigned* addr, double* ww, double* ss) {
+    int b[kU];
+    buckets_of<GRID, KM>(Q.L, xs, b);
+    bool ext = false;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        ext = ext || ((unsigned)b[u] - Q.L.ext_lo >= Q.L.ext_span);
+        addr[u] = Q.L.acc + (unsigned)b[u] * Q.row_bytes;
+        ww[u] = ws[u];
+        ss[u] = __dmul_rn(ws[u], xs[u]);
+    }
+    const unsigned daddr = Q.L.acc + (unsigned)Q.L.dummy * Q.row_bytes;
+#pragma unroll
+    for (int i = 1; i < kU; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) fold_if_equal(addr[i], addr[j], ww[j], ss[j], ww[i], ss[i], daddr);
+    }
+    return ext;
+}
+
+// unweighted: counts go to the u32 counters at once (one red per value, no fold needed), the sums
+// x through the ring.  CLEAN = false: non-finite x (tdigest_add's filter, :285) is routed to the
+// dummy row / dummy counter.
+template <int GRID, int KM, bool CLEAN>
+__device__ __forceinline__ bool classify_lean_u(const Lookup2& Q, const double* xs, unsigned* addr,
+                                                double* ss) {
+    int b[kU];
+    buckets_of<GRID, KM>(Q.L, xs, b);
+    bool ext = false;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        double x = xs[u];
+        if (!CLEAN) {
+            const bool ok = fabs(x) <= DBL_MAX;
+            b[u] = ok ? b[u] : Q.L.dummy;
+            x = ok ? x : 0.0;
+        }
+        ext = ext || ((unsigned)b[u] - Q.L.ext_lo >= Q.L.ext_span);   // (the dummy row counts as "high")
+        addr[u] = Q.L.acc + (unsigned)b[u] * Q.row_bytes;
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(Q.cnt + 4u * (unsigned)b[u]) : "memory");
+        ss[u] = x;
+    }
+    const unsigned daddr = Q.L.acc + (unsigned)Q.L.dummy * Q.row_bytes;
+#pragma unroll
+    for (int i = 1; i < kU; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) fold_if_equal1(addr[i], addr[j], ss[j], ss[i], daddr);
+    }
+    return ext;
+}
+
+__device__ __forceinline__ double lds_f64v(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void rmw1(const unsigned* addr, const double* ss) {
+    double a[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) a[u] = lds_f64v(addr[u]);
+#pragma unroll
+    for (int u = 0; u < N; ++u) a[u] = __dadd_rn(a[u], ss[u]);
+#pragma unroll
+    for (int u = 0; u < N; ++u) sts_f64(addr[u], a[u]);
+}
+
+template <bool HAS_W, bool VEC, int GRID, int KM>
+__device__ __forceinline__ void accumulate_stream2(const Lookup2& Q, const Ring ring,
+                                                   const double* __restrict__ X,
+                                                   const double* __restrict__ W, double wsc, long n,
+                                                   long gw, long tw, int lane, double& vmin,
+                                                   double& vmax, int* badw_flag) {
+    const Lookup& L = Q.L;
+    const long nfull = n / kTile;
+    const long ntiles = (n + kTile - 1) / kTile;
+    const long rounds = (ntiles + tw - 1) / tw;  // the same for every warp: the token needs all
+    double xs[2 * kU], ws[2 * kU];
+    unsigned addr[2 * kU];
+    double ww[2 * kU], ss[2 * kU];
+    bool badw = false;
+    long t = gw;
+    if (t < nfull) {
+        load_tile<HAS_W, VEC>(X, W, t * kTile, lane, xs, ws);
+        if (VEC && t + tw < nfull) l2_prefetch<HAS_W>(X, W, (t + tw) * kTile, lane);
+    }
+    for (long r = 0; r < rounds; ++r, t += tw) {
+        const long tn = t + tw;
+        const bool have = t < ntiles;   // warp-uniform
+        const bool full = t < nfull;
+        if (have && !full) load_partial<HAS_W>(X, W, t * kTile, n, lane, xs, ws);   // pads: x = NaN, w = 1
+        if (have) {
+            bool ext;
+            if (full && tile_clean<HAS_W>(xs, ws)) {
+                if (HAS_W) {
+                    const bool e0 = classify_lean_w<GRID, KM>(Q, xs, ws, addr, ww, ss);
+                    const bool e1 = classify_lean_w<GRID, KM>(Q, xs + kU, ws + kU, addr + kU, ww + kU, ss + kU);
+                    ext = e0 || e1;
+                } else {
+                    const bool e0 = classify_lean_u<GRID, KM, true>(Q, xs, addr, ss);
+                    const bool e1 = classify_lean_u<GRID, KM, true>(Q, xs + kU, addr + kU, ss + kU);
+                    ext = e0 || e1;
+                }
+            } else if (HAS_W) {
+                // the exact per-value filter of round 1 (dummy-row routing, weight verdict)
+                bool susp = false;
+                const bool e0 = classify_group<true, GRID, (KM >= 0)>(L, xs, ws, wsc, addr, ww, ss, susp);
+                const bool e1 = classify_group<true, GRID, (KM >= 0)>(L, xs + kU, ws + kU, wsc, addr + kU,
+                                                                      ww + kU, ss + kU, susp);
+                ext = e0 || e1;
+                if (__any_sync(CRICK_FULL, susp)) badw |= susp && any_illegal_weight(ws);
+            } else {
+                const bool e0 = classify_lean_u<GRID, KM, false>(Q, xs, addr, ss);
+                const bool e1 = classify_lean_u<GRID, KM, false>(Q, xs + kU, addr + kU, ss + kU);
+                ext = e0 || e1;
+            }
+            if (__any_sync(CRICK_FULL, ext)) {
+                minmax_group<HAS_W>(L, xs, ws, wsc, vmin, vmax);
+                minmax_group<HAS_W>(L, xs + kU, ws + kU, wsc, vmin, vmax);
+            }
+        }
+        if (tn < nfull) {
+            load_tile<HAS_W, VEC>(X, W, tn * kTile, lane, xs, ws);
+            if (VEC && tn + tw < nfull) l2_prefetch<HAS_W>(X, W, (tn + tw) * kTile, lane);
+        }
+        if (!(ring.first && r == 0)) bar_sync64(ring.id_in);
+        if (have) {
+            if (ring.passes == 1) {
+                if (HAS_W) { rmw<kU>(addr, ww, ss); rmw<kU>(addr + kU, ww + kU, ss + kU); }
+                else { rmw1<kU>(addr, ss); rmw1<kU>(addr + kU, ss + kU); }
+            } else {
+                for (int p_ = 0; p_ < ring.passes; ++p_) {
+                    if (ring.pass == p_) {
+                        if (HAS_W) { rmw<kU>(addr, ww, ss); rmw<kU>(addr + kU, ww + kU, ss + kU); }
+                        else { rmw1<kU>(addr, ss); rmw1<kU>(addr + kU, ss + kU); }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        bar_arrive64(ring.id_out);
+    }
+    if (ring.first && rounds > 0) bar_sync64(ring.id_in);  // absorb the last hand-over
+    if (HAS_W && __any_sync(CRICK_FULL, badw) && lane == 0) atomicOr(badw_flag, 1);
+}
+
+template <bool HAS_W, bool VEC>
+__global__ void __launch_bounds__(HAS_W ? 448 : 512, 1)
+k_bin_accumulate2(const double* __restrict__ X, const double* __restrict__ W, double wsc, long n,
+                  ParHeader* hdr, const double* __restrict__ g_edges,
+                  const unsigned short* __restrict__ g_tab, double2* __restrict__ partial,
+                  double2* __restrict__ minmax, int bmax, int cols, int ntab, int accumulate_into) {
+    // shared: acc[ntab][bmax + 1][cols] (double2 weighted, double unweighted) | cnt[bmax + 1 (+pad)] u32
+    //         (unweighted) | edges[bmax + kEdgePad] | tab[kTabLen] uint16
+    constexpr int ES = HAS_W ? 16 : 8;            // bytes per accumulator
+    const int nwarps = blockDim.x >> 5;
+    const int rows = bmax + 1;                    // last row = dummy
+    unsigned char* s_acc = smem_raw;
+    const size_t acc_bytes = (size_t)ntab * rows * cols * ES;
+    const int cnt_len = HAS_W ? 0 : ((rows + 3) & ~3);
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_acc + acc_bytes);
+    double* s_edges = reinterpret_cast<double*>(s_acc + acc_bytes + (size_t)cnt_len * 4);
+    unsigned short* s_tab = reinterpret_cast<unsigned short*>(s_edges + bmax + kEdgePad);
+    __shared__ double s_min[32], s_max[32];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    // clearing the tables needs nothing from k_make_edges: it runs before the dependency wait
+    {
+        double2* z = reinterpret_cast<double2*>(s_acc);
+        const int nz = (int)((acc_bytes + (size_t)cnt_len * 4) >> 4);
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = make_double2(0.0, 0.0);
+    }
+    grid_dep_wait();
+    const int E = hdr->E;
+    const int B = E + 1;
+    for (int i = threadIdx.x; i < kTabLen / 2; i += blockDim.x)
+        reinterpret_cast<unsigned*>(s_tab)[i] = reinterpret_cast<const unsigned*>(g_tab)[i];
+    for (int i = threadIdx.x; i < bmax + kEdgePad; i += blockDim.x)
+        s_edges[i] = i < E ? g_edges[i] : INFINITY;
+    __syncthreads();
+    Lookup2 Q;
+    Lookup& L = Q.L;
+    L.tab = (unsigned)__cvta_generic_to_shared(s_tab);
+    L.edges = (unsigned)__cvta_generic_to_shared(s_edges);
+    const int tab_id = warp % ntab, pos = warp / ntab, rsize = nwarps / ntab;
+    L.acc = (unsigned)__cvta_generic_to_shared(s_acc + (size_t)tab_id * rows * cols * ES) +
+            (unsigned)ES * (unsigned)(lane & (cols - 1));
+    L.row_shift = (HAS_W ? 4 : 3) + __ffs(cols) - 1;
+    Q.row_bytes = (unsigned)(cols * ES);
+    Q.cnt = (unsigned)__cvta_generic_to_shared(s_cnt);
+    L.dummy = bmax;
+    L.kbase = hdr->kbase; L.shift = hdr->shift; L.x0 = hdr->x0; L.inv = hdr->inv;
+    L.E = E; L.kmax = hdr->kmax;
+    L.ext_lo = E >= 4 ? 2u : 0u;
+    L.ext_span = E >= 4 ? (unsigned)(E - 3) : 0u;
+    Ring ring;
+    ring.id_in = 1 + tab_id * rsize + pos;
+    ring.id_out = 1 + tab_id * rsize + (pos + 1 == rsize ? 0 : pos + 1);
+    ring.first = pos == 0;
+    ring.passes = 32 / cols;
+    ring.pass = lane / cols;
+    double vmin = INFINITY, vmax = -INFINITY;
+    const long gw = (long)blockIdx.x * nwarps + warp;
+    const long tw = (long)gridDim.x * nwarps;
+    const int km = L.kmax;
+#define CRICK_ACC2(G, K) accumulate_stream2<HAS_W, VEC, G, K>(Q, ring, X, W, wsc, n, gw, tw, lane, vmin, vmax, &hdr->badw)
+    if (hdr->grid == 1) {
+        if (km <= 1) CRICK_ACC2(1, 1); else if (km == 2) CRICK_ACC2(1, 2);
+        else if (km <= kKFast) CRICK_ACC2(1, 0); else CRICK_ACC2(1, -1);
+    } else {
+        if (km <= 1) CRICK_ACC2(0, 1); else if (km == 2) CRICK_ACC2(0, 2);
+        else if (km <= kKFast) CRICK_ACC2(0, 0); else CRICK_ACC2(0, -1);
+    }
+#undef CRICK_ACC2
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        vmin = fmin(vmin, shfl_xor_d(vmin, d));
+        vmax = fmax(vmax, shfl_xor_d(vmax, d));
+    }
+    if (lane == 0) { s_min[warp] = vmin; s_max[warp] = vmax; }
+    __syncthreads();
+    // column sums in place, fixed order (tables into table 0, then a halving tree over the columns)
+    double2* row = partial + (size_t)blockIdx.x * kBPad;
+    const int nrc = B * cols;
+    if (HAS_W) {
+        double2* a2 = reinterpret_cast<double2*>(s_acc);
+        for (int tb = 1; tb < ntab; ++tb) {
+            for (int i = threadIdx.x; i < nrc; i += blockDim.x) {
+                double2 a = a2[i], o = a2[(size_t)tb * rows * cols + i];
+                a2[i] = make_double2(a.x + o.x, a.y + o.y);
+            }
+        }
+        __syncthreads();
+        for (int dcol = cols >> 1; dcol > 0; dcol >>= 1) {
+            const int sh = __ffs(dcol) - 1;
+            for (int i = threadIdx.x; i < B * dcol; i += blockDim.x) {
+                const int bb = i >> sh, c = i & (dcol - 1);
+                double2 a = a2[bb * cols + c], o = a2[bb * cols + c + dcol];
+                a2[bb * cols + c] = make_double2(a.x + o.x, a.y + o.y);
+            }
+            __syncthreads();
+        }
+        for (int bb = threadIdx.x; bb < B; bb += blockDim.x) {
+            double2 a = a2[bb * cols];
+            if (accumulate_into) { double2 o = row[bb]; a.x += o.x; a.y += o.y; }
+            row[bb] = a;
+        }
+    } else {
+        double* a1 = reinterpret_cast<double*>(s_acc);
+        for (int i = threadIdx.x; i < nrc; i += blockDim.x) {
+            double a = a1[i];
+            for (int tb = 1; tb < ntab; ++tb) a += a1[(size_t)tb * rows * cols + i];   // fixed order
+            a1[i] = a;
+        }
+        __syncthreads();
+        for (int dcol = cols >> 1; dcol > 0; dcol >>= 1) {
+            const int sh = __ffs(dcol) - 1;
+            for (int i = threadIdx.x; i < B * dcol; i += blockDim.x) {
+                const int bb = i >> sh, c = i & (dcol - 1);
+                a1[bb * cols + c] += a1[bb * cols + c + dcol];
+            }
+            __syncthreads();
+        }
+        for (int bb = threadIdx.x; bb < B; bb += blockDim.x) {
+            // sum w = count * w (exact for w = 1), sum w x = w * sum x
+            double2 a = make_double2(__dmul_rn((double)s_cnt[bb], wsc), __dmul_rn(wsc, a1[bb * cols]));
+            if (accumulate_into) { double2 o = row[bb]; a.x += o.x; a.y += o.y; }
+            row[bb] = a;
+        }
+    }
+    if (threadIdx.x == 0) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (int wv = 0; wv < nwarps; ++wv) { mn = fmin(mn, s_min[wv]); mx = fmax(mx, s_max[wv]); }
+        if (accumulate_into) { double2 o = minmax[blockIdx.x]; mn = fmin(mn, o.x); mx = fmax(mx, o.y); }
+        minmax[blockIdx.x] = make_double2(mn, mx);
+        if (blockIdx.x == 0) hdr->ncta = gridDim.x;
+    }
+}
+
 // warp_merge_sorted (tdigest_ref.cuh) for a whole CTA: the same phases and the same arithmetic,
 // with the order-independent ones spread over all threads and the two sequential ones on
 // thread 0.  (Integer weights need no special case here: the warp version's parallel scan is
@@ -1328,7 +1772,10 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
     grid_dep_wait();          // the partials of k_bin_accumulate
     // validated update (tdigest.pyx:304-305): the digest is only touched when every weight
     // passed; the host reads the same flag after this kernel has been enqueued
-    if (honor_badw && hdr->badw) return;
+    if (honor_badw && hdr->badw) {
+        if (tid == 0) hdr->badw_sticky = 1;   // read (and cleared) by parallel_take_bad_weights
+        return;
+    }
     const int E = hdr->E;
     const int B = E + 1;
     const int ncta = hdr->ncta;
@@ -1675,6 +2122,34 @@ static AccCfg acc_cfg(int bmax, bool stats) {
     return c;
 }
 
+// Shape of k_bin_accumulate2.  Weighted: two double2 tables, rings of 7 (14 warps), as in round 1.
+// Unweighted: 8-byte rows -> three tables with rings of 5 (15 warps: a ring hop needs a named
+// barrier of its own and there are 15 besides __syncthreads'), or CRICK_ACC2_T=4: four tables with
+// rings of 3.  C = 32 columns when they fit, else 16 / 8 / 4.
+static AccCfg acc_cfg2(int bmax, bool has_w) {
+    const size_t budget = 230000;
+    const size_t es = has_w ? 16 : 8;
+    const size_t fixed = kTabBytes + sizeof(double) * (size_t)(bmax + kEdgePad) +
+                         (has_w ? 0 : (size_t)((bmax + 1 + 3) & ~3) * 4);
+    const size_t col = (size_t)(bmax + 1) * es;
+    AccCfg c;
+    c.stage = 0;
+    c.ntab = has_w ? 2 : 3;
+    if (const char* e = getenv("CRICK_ACC2_T")) { int v = atoi(e); if (v >= 1 && v <= 5) c.ntab = v; }
+    int per = 15 / c.ntab;                                 // warps per ring
+    if (has_w && per > 7) per = 7;                         // launch bounds: 448 threads
+    if (const char* e = getenv("CRICK_ACC2_R")) { int v = atoi(e); if (v >= 1 && v <= per) per = v; }
+    c.nw = per * c.ntab;
+    c.cols = 32;
+    while (c.cols > 2 && fixed + (size_t)c.ntab * c.cols * col > budget) c.cols >>= 1;
+    c.smem = (fixed + (size_t)c.ntab * c.cols * col + 15) & ~(size_t)15;
+    return c;
+}
+static bool acc2_enabled() {
+    static const bool on = [] { const char* e = getenv("CRICK_ACC_V"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 // ---- optional per-launch timing of the hot kernel (bench.py's roofline leg) ------------
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -1707,7 +2182,9 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
                                    int accumulate_into, StatsPart* stats_parts, long idx_base) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     const int bmax = bmax_for(v.comp);
-    const AccCfg cfg = acc_cfg(bmax, stats_parts != nullptr);
+    // the round-2 kernel unless fused moments or the TMA-staged shape are asked for
+    const bool v2 = stats_parts == nullptr && acc2_enabled() && !acc_cfg(bmax, false).stage;
+    const AccCfg cfg = v2 ? acc_cfg2(bmax, W != nullptr) : acc_cfg(bmax, stats_parts != nullptr);
     const size_t smem = cfg.smem;
     const bool vec = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
     const unsigned grid = (unsigned)sm_count;
@@ -1734,8 +2211,21 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
         if (stats_parts) CRICK_LAUNCH_ACC_S(HW, VC, SG, true);                                    \
         else CRICK_LAUNCH_ACC_S(HW, VC, SG, false);                                               \
     } while (0)
+#define CRICK_LAUNCH_ACC2(HW, VC)                                                                  \
+    do {                                                                                          \
+        e = need_smem(k_bin_accumulate2<HW, VC>, smem);                                           \
+        if (e != cudaSuccess) return e;                                                           \
+        count_launch();                                                                           \
+        e = launch_dep(k_bin_accumulate2<HW, VC>, dim3(grid), dim3(block), smem, st, X, W, wsc, n, \
+                       L.hdr, L.edges, L.tab, L.partial, L.minmax, bmax, cfg.cols, cfg.ntab,      \
+                       accumulate_into);                                                          \
+        if (e != cudaSuccess) return e;                                                           \
+    } while (0)
     const bool stage = vec && cfg.stage;   // unaligned input: plain loads, no staging
-    if (W) {
+    if (v2) {
+        if (W) { if (vec) CRICK_LAUNCH_ACC2(true, true); else CRICK_LAUNCH_ACC2(true, false); }
+        else { if (vec) CRICK_LAUNCH_ACC2(false, true); else CRICK_LAUNCH_ACC2(false, false); }
+    } else if (W) {
         if (!vec) CRICK_LAUNCH_ACC(true, false, false);
         else if (stage) CRICK_LAUNCH_ACC(true, true, true);
         else CRICK_LAUNCH_ACC(true, true, false);
@@ -1746,6 +2236,7 @@ static cudaError_t accumulate_impl(const BatchView& v, const double* X, const do
     }
 #undef CRICK_LAUNCH_ACC
 #undef CRICK_LAUNCH_ACC_S
+#undef CRICK_LAUNCH_ACC2
     if (pe0 && pe1) {
         cudaEventRecord(pe1, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -1786,9 +2277,22 @@ cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad) {
     return e;
 }
 
+// sticky verdict of the deferred weight checks since the last call (synchronises `st`)
+cudaError_t parallel_take_bad_weights(void* scratch, cudaStream_t st, int* bad) {
+    ParLayout L = carve(scratch, 100.0, 1);
+    ParHeader h;
+    cudaError_t e = cudaMemcpyAsync(&h, L.hdr, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    *bad = (e == cudaSuccess) ? h.badw_sticky : 0;
+    if (e == cudaSuccess && h.badw_sticky)
+        e = cudaMemsetAsync(&L.hdr->badw_sticky, 0, sizeof(int), st);
+    return e;
+}
+
 cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, const double* W,
                                    double wsc, long n, void* scratch, int sm_count,
-                                   cudaStream_t st, int* bad_weights, StatsPart* stats_parts) {
+                                   cudaStream_t st, int* bad_weights, StatsPart* stats_parts,
+                                   bool defer_check) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     long S = sample_len(n);
     SampleSrc src{X, W, wsc, n, L.hdr};
@@ -1798,9 +2302,10 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
     if (e != cudaSuccess) return e;
     // validated update: k_finalize leaves the digest alone when the pass flagged a weight; the
     // flag is read back once everything is enqueued (one synchronisation, at the end)
-    const bool checked = bad_weights && W;
+    // (defer_check: the same, but the verdict stays on the device -- no synchronisation here)
+    const bool checked = (bad_weights || defer_check) && W;
     e = parallel_finalize(v, d, scratch, sm_count, st, checked);
-    if (e == cudaSuccess && checked) e = parallel_bad_weights(scratch, st, bad_weights);
+    if (e == cudaSuccess && checked && !defer_check) e = parallel_bad_weights(scratch, st, bad_weights);
     return e;
 }
 

@@ -1,12 +1,14 @@
-"""SpaceSaving -- drop-in for ``crick.SpaceSaving`` (reference: crick/space_saving.pyx) for the
-int64 and float64 item types, on the GPU.  The object dtype needs ``PyObject_Hash`` /
-``RichCompare`` per item (space_saving_stubs.c.in:20-29) and cannot run on a GPU: it is out of
-this build's scope and raises NotImplementedError."""
+"""SpaceSaving -- drop-in for ``crick.SpaceSaving`` (reference: crick/space_saving.pyx).  The
+int64 and float64 item types run on the GPU.  The object dtype needs ``PyObject_Hash`` /
+``RichCompare`` per item (space_saving_stubs.c.in:20-29), which only the interpreter can
+evaluate: that one dtype is a host-side Stream-Summary (``_spsv_object.py``)."""
 import numpy as np
 
 from ._arrays import device_view, korder_pair
 from ._lib import check, check_handle, handle_array, lib
+from ._spsv_object import ObjectSummary
 
+COUNTER_OBJECT_DTYPE = np.dtype([("item", object), ("count", np.int64), ("error", np.int64)])
 COUNTER_INT64_DTYPE = np.dtype([("item", np.int64), ("count", np.int64), ("error", np.int64)])
 COUNTER_FLOAT64_DTYPE = np.dtype([("item", np.float64), ("count", np.int64), ("error", np.int64)])
 
@@ -49,12 +51,15 @@ class TopKResult(tuple):
 
 
 def _as_int(v, name):
-    if isinstance(v, (str, bytes)) or v is None or (isinstance(v, float) and v != int(v)):
-        raise TypeError("%s must be an integer" % name)
+    """Cython's conversion of an ``int`` argument (space_saving.pyx:179,247,304): numbers go
+    through ``__int__`` (NaN -> ValueError, +-inf -> OverflowError, both from float.__int__),
+    anything without one is a TypeError."""
+    if isinstance(v, (str, bytes, bytearray)) or v is None:
+        raise TypeError("%s must be an integer, not %s" % (name, type(v).__name__))
     try:
         return int(v)
-    except (TypeError, ValueError):
-        raise TypeError("%s must be an integer" % name)
+    except TypeError:
+        raise TypeError("%s must be an integer, not %s" % (name, type(v).__name__))
 
 
 class SpaceSaving:
@@ -65,18 +70,19 @@ class SpaceSaving:
     Integer dtypes are tracked as int64, float dtypes as float64 (by bit pattern).
     """
 
-    __slots__ = ("_h", "dtype", "__weakref__")
+    __slots__ = ("_h", "_obj", "dtype", "__weakref__")
 
     def __init__(self, capacity=20, dtype="f8"):
         self._h = None
+        self._obj = None
         capacity = _as_int(capacity, "capacity")
         if capacity <= 0:  # space_saving.pyx:180-181
             raise ValueError("capacity must be > 0")
         dtype = np.dtype(dtype)
-        if dtype.kind == "O":
-            raise NotImplementedError(
-                "SpaceSaving(dtype=object) needs Python hashing/equality per item and is "
-                "outside the GPU build's scope; use dtype='i8' or 'f8'")
+        if dtype.kind == "O":  # :185-186: host-side Stream-Summary (Python hashing / equality)
+            self.dtype = dtype
+            self._obj = ObjectSummary(capacity)
+            return
         elif dtype.kind in "iu":
             dtype = np.dtype(np.int64)
         elif dtype.kind == "f":
@@ -97,10 +103,14 @@ class SpaceSaving:
 
     @property
     def capacity(self):
+        if self._obj is not None:
+            return self._obj.capacity
         return int(lib.crick_spsv_capacity(self._h))
 
     def size(self):
         """The number of active counters."""
+        if self._obj is not None:
+            return self._obj.size
         return int(check(lib.crick_spsv_size(self._h), "size"))
 
     def counters(self):
@@ -114,6 +124,10 @@ class SpaceSaving:
         return (self.counters(),)
 
     def __setstate__(self, state):  # space_saving.pyx:235-245
+        if self._obj is not None:
+            c = state[0]
+            self._obj.set_state(c["item"].tolist(), c["count"].tolist(), c["error"].tolist())
+            return
         counters = np.ascontiguousarray(state[0])
         if self.dtype.kind == "f":
             counters = counters.view(COUNTER_INT64_DTYPE)
@@ -124,14 +138,25 @@ class SpaceSaving:
             raise ValueError(last_error())
 
     def _item_bits(self, item):
+        """Cython's conversion of `item` to the C argument of spsv_int64_add
+        (space_saving.pyx:265-268): ``asint64(<double>item)`` for float summaries, else
+        ``<npy_int64>item`` -- through ``__int__``, so NaN is a ValueError and +-inf an
+        OverflowError, and anything that is not a number a TypeError."""
+        if isinstance(item, (str, bytes, bytearray)) or item is None:
+            raise TypeError("item must be a number, not %s" % type(item).__name__)
         if self.dtype.kind == "f":
-            return int(np.asarray(item, dtype=np.float64).reshape(()).view(np.int64))
-        if isinstance(item, (str, bytes)) or item is None:
-            raise TypeError("an integer is required")
-        if isinstance(item, float):
-            if item != int(item):
-                raise TypeError("an integer is required")
-        return int(item)
+            try:
+                v = float(item)
+            except (TypeError, ValueError):
+                raise TypeError("item must be a number, not %s" % type(item).__name__)
+            return int(np.float64(v).view(np.int64))
+        try:
+            v = int(item)
+        except TypeError:
+            raise TypeError("item must be a number, not %s" % type(item).__name__)
+        if not -(1 << 63) <= v < (1 << 63):
+            raise OverflowError("Python int too large to convert to C long")
+        return v
 
     def add(self, item, count=1):
         """add(self, item, count=1)
@@ -141,11 +166,10 @@ class SpaceSaving:
         count = _as_int(count, "count")
         if count <= 0:
             raise ValueError("count must be > 0")
-        try:
-            bits = self._item_bits(item)
-        except (ValueError, OverflowError):
-            raise TypeError("item cannot be converted to %s" % self.dtype)
-        check(lib.crick_spsv_add(self._h, bits, count), "add")
+        if self._obj is not None:
+            self._obj.add(item, count)
+            return
+        check(lib.crick_spsv_add(self._h, self._item_bits(item), count), "add")
 
     def update(self, item, count=1, stream=None, mode=0):
         """update(self, item, count=1)
@@ -156,6 +180,8 @@ class SpaceSaving:
         (see ``crick_spsv_update`` in include/crick_cuda.h).
         """  # space_saving.pyx:270-302
         mode = int(mode)
+        if self._obj is not None:
+            return self._update_object(item, count)
         idv = device_view(item)
         if idv is not None:
             if idv.dtype != self.dtype:
@@ -194,6 +220,27 @@ class SpaceSaving:
             check(lib.crick_spsv_update(self._h, xf.ctypes.data, None, int(cf), xf.size, 0, 0, mode,
                                         stream), "update")
 
+    def _update_object(self, item, count):
+        """spsv_object_update_ndarray, space_saving_stubs.c.in:367-451: the same coercion,
+        broadcasting and K-order walk as the numeric dtypes, one ``add`` per element."""
+        item = np.asarray(item)
+        check_count = not (np.isscalar(count) and count == 1)
+        count = np.asarray(count)
+        item = item.astype(self.dtype, casting="safe", copy=False)
+        count = count.astype(np.int64, casting="safe", copy=False)
+        if check_count and (count <= 0).any():
+            raise ValueError("count must be > 0")
+        if item.size == 0 or count.size == 0:
+            return
+        add = self._obj.add
+        with np.nditer([item, count], flags=["refs_ok", "external_loop", "buffered"],
+                       op_flags=[["readonly", "aligned"], ["readonly", "aligned"]], order="K",
+                       casting="safe", op_dtypes=[object, np.int64]) as it:
+            for xs, cs in it:
+                for x, c in zip(xs.tolist(), cs.tolist()):
+                    add(x, c)
+                del xs, cs
+
     def topk(self, k, astuples=False):
         """topk(self, k, astuples=False)
 
@@ -204,13 +251,18 @@ class SpaceSaving:
         if k < 0:
             raise ValueError("k must be >= 0")
         k = min(self.size(), k)
-        out = np.empty(k, dtype=COUNTER_INT64_DTYPE)
-        if k:
-            check(lib.crick_spsv_counters(self._h, out.ctypes.data, k), "topk")
-        if self.dtype.kind == "f":
-            out = out.view(COUNTER_FLOAT64_DTYPE)
+        if self._obj is not None:
+            out = np.empty(k, dtype=COUNTER_OBJECT_DTYPE)
+            for i, rec in enumerate(self._obj.counters(k)):
+                out[i] = rec
+        else:
+            out = np.empty(k, dtype=COUNTER_INT64_DTYPE)
+            if k:
+                check(lib.crick_spsv_counters(self._h, out.ctypes.data, k), "topk")
+            if self.dtype.kind == "f":
+                out = out.view(COUNTER_FLOAT64_DTYPE)
         if astuples:
-            return [TopKResult(*i) for i in out.tolist()]
+            return [TopKResult(*i) for i in out]  # NumPy scalars, like space_saving.pyx:339-340
         return out
 
     def merge(self, *args):
@@ -223,6 +275,10 @@ class SpaceSaving:
         if not all(i.dtype == self.dtype for i in args):
             raise ValueError("All arguments to merge must have same dtype")
         if not args:
+            return
+        if self._obj is not None:
+            for o in args:
+                self._obj.merge(o._obj)
             return
         arr = handle_array([s._h for s in args])
         check(lib.crick_spsv_merge(self._h, arr, len(args)), "merge")

@@ -46,10 +46,11 @@ class TDigest:
         sequential algorithm is still affordable), parallel at or above.
     """
 
-    __slots__ = ("_h", "_mode", "_keepalive", "__weakref__")
+    __slots__ = ("_h", "_mode", "_keepalive", "_deferred", "__weakref__")
 
     def __init__(self, compression=100.0, mode="auto"):
         self._h = None
+        self._deferred = False
         c = _as_double(compression, "compression")
         if not math.isfinite(c):  # tdigest.pyx:81-82
             raise ValueError("Compression must be finite")
@@ -75,6 +76,16 @@ class TDigest:
 
     def _flush(self):
         check(lib.crick_tdigest_flush(self._h), "flush")
+        if self._deferred:
+            self.check_weights()
+
+    def check_weights(self):
+        """Verdict of the deferred weight checks (``update(..., check_w="deferred")``) since the
+        last call: raises the ValueError the synchronous check would have raised at the call
+        (an update whose weights failed left the digest as it was).  Synchronises."""
+        self._deferred = False
+        if check(lib.crick_tdigest_take_bad_weights(self._h), "check_weights"):
+            raise ValueError("w must be > 0 and finite")
 
     def min(self):
         """min(self)
@@ -131,6 +142,8 @@ class TDigest:
             xin = np.ascontiguousarray(xin)
         out = np.empty(xin.shape, dtype=np.float64)
         check(fn(self._h, xin.ctypes.data, out.ctypes.data, xin.size, 0, None), name)
+        if self._deferred:
+            self.check_weights()
         if out.ndim == 0:  # :140-142
             return np.float64(out)
         return out
@@ -196,15 +209,12 @@ class TDigest:
             left -= 0.5
             right += 0.5
 
-        if isinstance(bins, (int, np.integer)) and not isinstance(bins, bool):
+        if isinstance(bins, int):  # (like the reference: a NumPy integer is an array_like here)
             if bins < 1:
                 raise ValueError("bins must be >= 1")
             bin_edges = np.linspace(left, right, bins + 1, endpoint=True)
         else:
-            try:
-                bin_edges = np.asarray(bins).astype("f8", copy=False)
-            except (TypeError, ValueError):
-                raise ValueError("bins must be an int or a numeric array")
+            bin_edges = np.asarray(bins).astype("f8", copy=False)
             if bin_edges.ndim != 1:
                 raise ValueError("bins must be a 1-dimensional array")
             elif not np.isfinite(bin_edges).all():
@@ -213,7 +223,7 @@ class TDigest:
                 raise ValueError("bins must increase monotonically")
 
         hist_size = bin_edges.size - 1
-        hist = np.zeros(max(hist_size, 0), dtype=np.float64)
+        hist = np.zeros(hist_size, dtype=np.float64)  # no edges at all: ValueError, as in :224-226
         if size != 0 and hist_size > 0:
             cdf = self.cdf(bin_edges)
             hist[:] = (cdf[1:] - cdf[:-1]) * size  # _cdf_to_hist, :46-50
@@ -299,7 +309,12 @@ class TDigest:
         check_w : CUDA-array weights only.  True (default): raise ValueError like the
             reference when a weight is not finite or not > 0 -- checked on the device, which
             synchronises the stream.  False: fully asynchronous, ``w <= eps`` is dropped by
-            the kernel exactly like ``tdigest_add`` does.
+            the kernel exactly like ``tdigest_add`` does.  ``"deferred"`` (parallel path): the
+            same check, but nothing waits for it -- a failed update leaves the digest as it
+            was and the ValueError is raised by the next call that synchronises anyway
+            (``centroids``, ``min``, ``max``, ``quantile`` / ``cdf`` of host arrays, pickling)
+            or by ``check_weights()``: update -> export -> all-gather -> merge become one
+            enqueue chain.
         """  # tdigest.pyx:282-308
         m = self._mode if mode is None else _lib.mode_code(mode)
         if stats is not None:
@@ -419,6 +434,14 @@ class TDigest:
                 raise ValueError("x and w CUDA arrays must have the same number of elements")
             parallel = eff == _lib.MODE_PARALLEL or (eff == _lib.MODE_AUTO
                                                      and n >= _lib.PARALLEL_MIN)
+            if isinstance(check_w, str):
+                if check_w != "deferred":
+                    raise ValueError("check_w must be True, False or 'deferred'")
+                if parallel:
+                    check(lib.crick_tdigest_update_deferred(self._h, xd.ptr, wd.ptr, 0.0, n, eff,
+                                                            stream), "update")
+                    self._deferred = True
+                    return
             if check_w and parallel:
                 bad = ctypes.c_int(0)
                 check(lib.crick_tdigest_update_checked(self._h, xd.ptr, wd.ptr, 0.0, n, 1, 1, eff,

@@ -94,6 +94,14 @@ int crick_tdigest_update(crick_tdigest_t *t, const double *x, const double *w, d
 int crick_tdigest_update_checked(crick_tdigest_t *t, const double *x, const double *w,
                                  double w_scalar, int64_t n, int x_on_device, int w_on_device,
                                  int mode, void *stream, int *bad_weights);
+/* The checked update for device-resident x and w WITHOUT any host synchronisation (parallel mode
+ * only): the verdict of the weight check stays on the device; an update whose weights failed leaves
+ * the digest as it was, and crick_tdigest_take_bad_weights() later returns 1 (and clears the
+ * flag; it synchronises) if any deferred update since the last call was refused.  Lets a
+ * multi-GPU step enqueue update -> export -> all-gather -> merge as one chain. */
+int crick_tdigest_update_deferred(crick_tdigest_t *t, const double *x, const double *w,
+                                  double w_scalar, int64_t n, int mode, void *stream);
+int crick_tdigest_take_bad_weights(crick_tdigest_t *t);
 /* Parallel-mode update with the SummaryStats moments of x (count 1 per element, NaN skipped:
  * stats_update_ndarray, stats_stubs.c:199-210) accumulated into `stats` IN THE SAME PASS over
  * the data.  n >= CRICK_PARALLEL_MIN.  bad_weights may be NULL (no weight validation). */

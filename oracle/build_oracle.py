@@ -75,10 +75,30 @@ def build_reference(force=False):
     return out
 
 
+def stage_reference_tests():
+    """The reference's own pytest files (crick/tests/*.py) are the parity contract of the drop-in
+    package: tests/test_reference_suite.py runs them UNMODIFIED against the
+    `crick` shim.  /root/reference does not exist on the GPU box, so they are staged -- like the
+    built reference .so -- under oracle/_ref/ (git-ignored: nothing of the reference enters the
+    repository's history; the directory travels with the gpurun snapshot).  Returns the staged
+    directory, or None when there is neither a reference tree nor a staged copy."""
+    import shutil
+    src = os.path.join(REF, "crick", "tests")
+    dst = os.path.join(REF_OUT, "ref_tests")
+    if not os.path.isdir(src):
+        return dst if os.path.isdir(dst) else None
+    os.makedirs(dst, exist_ok=True)
+    for name in sorted(os.listdir(src)):
+        if name.startswith("test_") and name.endswith(".py"):
+            shutil.copyfile(os.path.join(src, name), os.path.join(dst, name))
+    return dst
+
+
 def main():
     force = "--force" in sys.argv
     print("restatement:", build_restatement(force))
     print("reference:  ", build_reference(force))
+    print("ref tests:  ", stage_reference_tests())
 
 
 if __name__ == "__main__":

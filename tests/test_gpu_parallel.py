@@ -238,6 +238,40 @@ def test_weights_validated_on_the_device(cb):
     assert abs(t3.size() - w.sum()) <= 1e-12 * w.sum()
 
 
+def test_deferred_weight_check_needs_no_sync_and_is_sticky(cb):
+    """check_w="deferred": the same validation with the verdict kept on the device -- a refused
+    update leaves the digest untouched and the ValueError surfaces at the next synchronising
+    call; the accepted update is bit-identical with the synchronous form."""
+    rng = np.random.default_rng(13)
+    n = 200000
+    x = rng.lognormal(size=n)
+    w = rng.uniform(0.5, 1.5, n)
+    dx, dw = cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w)
+    t = cb.TDigest(100, mode="parallel")
+    t.update(dx, dw, check_w="deferred")
+    ref = cb.TDigest(100, mode="parallel")
+    ref.update(dx, dw)
+    good = t.centroids()
+    assert good.tobytes() == ref.centroids().tobytes()
+    for bad in (0.0, -2.0, np.nan, np.inf):
+        wb = w.copy()
+        wb[n // 2] = bad
+        t.update(dx, cb.DeviceArray.from_numpy(wb), check_w="deferred")
+        t.update(dx, dw, check_w="deferred")          # a later good update does not clear the verdict
+        with pytest.raises(ValueError):
+            t.centroids()
+        t.check_weights()                              # cleared by the raise above
+    ref.update(dx, dw); ref.update(dx, dw); ref.update(dx, dw); ref.update(dx, dw)
+    assert t.centroids().tobytes() == ref.centroids().tobytes()
+    with pytest.raises(ValueError):
+        t.update(dx, dw, check_w="later")
+    # the scalar weight tdigest_add drops (w <= eps) drops everything (test_tdigest.py:183-193)
+    t4 = cb.TDigest()
+    t4.update(x, np.finfo("f8").eps)
+    t4.update(dx, np.finfo("f8").eps)
+    assert t4.size() == 0 and len(t4.centroids()) == 0
+
+
 def test_fused_moments_in_the_same_pass(cb):
     """north_star: SummaryStats moments fused into the t-digest pass.  The digest must be the one
     the plain update builds (bit for bit) and the moments must match the stand-alone stats pass
