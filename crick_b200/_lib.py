@@ -106,6 +106,7 @@ _SIG = {
     "crick_spsv_free": (None, [_P]),
     "crick_spsv_add": (c_int, [_P, c_int64, c_int64]),
     "crick_spsv_update": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "crick_spsv_update_stats": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "crick_spsv_merge": (c_int, [_P, _P, c_int]),
     "crick_spsv_set_state": (c_int, [_P, _P, c_int64]),
     "crick_spsv_record_int64s": (c_int64, [_P]),

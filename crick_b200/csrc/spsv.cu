@@ -16,6 +16,7 @@
 // on the merge's early `break` (:334/:345, segfault) -- nothing is inserted here.
 #include "../../include/crick_cuda.h"
 #include "api_common.h"
+#include "stats_dev.cuh"
 
 namespace crick {
 
@@ -585,8 +586,16 @@ static cudaError_t sp_launch_update_parallel(crick_spsv* s, const long long* ite
     return e;
 }
 
+// fused moments (crick_spsv_update_stats): per-CTA StatsPart slots of the counting pass
+struct HHFuse { StatsPart* parts; int item_is_f64; int used; };
 static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, const long long* cnt,
-                                       long n, cudaStream_t st, bool* done, bool exact_only);
+                                       long n, cudaStream_t st, bool* done, bool exact_only,
+                                       HHFuse* fuse = nullptr);
+static bool hh2_enabled() {
+    static const bool on = [] { const char* e = getenv("CRICK_HH_V"); return !(e && e[0] == '1'); }();
+    return on;
+}
+constexpr int kHH2Buckets = 24000;   // per-CTA miss buckets: with L = 8192 the CTA uses 64 + 32 + 32 + 94 KB
 
 static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const long long* cnt,
                                     long long cs, long n, cudaStream_t st, int mode = 0,
@@ -615,8 +624,14 @@ static cudaError_t sp_launch_update(crick_spsv* s, const long long* item, const 
 
 // Counting path (spsv_hh.cuh).  *done = false: the batch does not suit it, nothing was changed.
 static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, const long long* cnt,
-                                       long n, cudaStream_t st, bool* done, bool exact_only) {
+                                       long n, cudaStream_t st, bool* done, bool exact_only,
+                                       HHFuse* fuse) {
     *done = false;
+    // unit counts: the round-2 counting pass (k_hh_count2: shared-memory buckets, one CTA of 32
+    // warps per SM); per-element counts keep the round-1 kernel with its 64-bit counters
+    const bool v2 = cnt == nullptr && hh2_enabled();
+    const int NB = kHH2Buckets;
+    const int nw2 = fuse ? 20 : 24;            // warps per CTA of k_hh_count2 (registers)
     const size_t csz = cnt ? 8 : 4;            // counts of the counting pass: u64 with weights
     int C = 256;
     while (C < 4 * s->cap) C <<= 1;
@@ -627,17 +642,20 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
     // the sample did not see are rare, a stream with more distinct items than counters misses ~half
     long miss_cap = n / 128 > 4096 ? n / 128 : 4096;
     if (miss_cap > kHHMissCap) miss_cap = kHHMissCap;
-    const size_t smem_cnt = (size_t)L * 10 + (size_t)C * (4 + csz);
-    int G = sm_count() * (2 * smem_cnt + 2048 <= 227 * 1024 ? 2 : 1);
-    const long W = (long)G * kHHWarps;
+    const size_t smem_cnt = v2 ? (size_t)L * 16 + (size_t)NB * 4
+                               : (size_t)L * 10 + (size_t)C * (4 + csz);
+    const size_t smem_col = (size_t)L * 8;                           // v2, collecting pass: keys only
+    int G = v2 ? sm_count() : sm_count() * (2 * smem_cnt + 2048 <= 227 * 1024 ? 2 : 1);
+    const long W = (long)G * (v2 ? nw2 : kHHWarps);
     const size_t stride = spsv_bytes(s->cap, s->hcap);
     // one allocation: sample table | buckets | candidates | lookup image | rows | miss counts | status | tmp
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_tabkey = take((size_t)kHHTabSlots * 8), o_tabcnt = take((size_t)kHHTabSlots * 4);
-    const size_t o_buckets = take((size_t)kHHBuckets * csz);
+    const size_t o_buckets = take(v2 ? (size_t)G * NB * 4 : (size_t)kHHBuckets * csz);
     const size_t o_cand = take((size_t)C * 8), o_lutk = take((size_t)L * 8), o_lutv = take((size_t)L * 2);
-    const size_t o_rc = take((size_t)G * C * csz), o_rl = take((size_t)G * C * 4);
+    const size_t o_rc = take((size_t)G * (v2 ? L : C) * csz), o_rl = take((size_t)G * (v2 ? L : C) * 4);
+    const size_t o_cslot = take((size_t)C * 4);
     const size_t o_wm = take((size_t)W * 8), o_wo = take((size_t)W * 8);
     const size_t o_cc = take((size_t)C * 8), o_cl = take((size_t)C * 8);
     const size_t o_hist = take(1024 * 4), o_sel = take(sizeof(HHSel));
@@ -654,6 +672,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
     unsigned short* lutv = reinterpret_cast<unsigned short*>(ws + o_lutv);
     void* rc = ws + o_rc;
     unsigned* rl = reinterpret_cast<unsigned*>(ws + o_rl);
+    int* cslot = reinterpret_cast<int*>(ws + o_cslot);
     unsigned long long* wm = reinterpret_cast<unsigned long long*>(ws + o_wm);
     unsigned long long* wo = reinterpret_cast<unsigned long long*>(ws + o_wo);
     long long* ccnt = reinterpret_cast<long long*>(ws + o_cc);
@@ -675,7 +694,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
             if (e != cudaSuccess) break;
         }
         e = cudaMemsetAsync(tabcnt, 0, (size_t)kHHTabSlots * 4, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(buckets, 0, (size_t)kHHBuckets * csz, st);
+        if (e == cudaSuccess && !v2) e = cudaMemsetAsync(buckets, 0, (size_t)kHHBuckets * csz, st);
         if (e != cudaSuccess) break;
         e = cudaMemsetAsync(dstatus, 0, sizeof(HHStatus), st);
         if (e != cudaSuccess) break;
@@ -694,14 +713,30 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
         count_launch();
         k_hh_place<<<kHHNChunk, 1024, 0, st>>>(tabkey, tabcnt, sel, chunk_gt, chunk_eq, cand);
         count_launch();
-        k_hh_lut<<<1, 1024, 0, st>>>(cand, sel, chunk_eq, lutk, lutv, L, dstatus);
-        e = cnt ? cudaFuncSetAttribute(k_hh_count<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt)
-                : cudaFuncSetAttribute(k_hh_count<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
+        if (v2) k_hh_lut2<<<1, 1024, 0, st>>>(cand, sel, chunk_eq, lutk, cslot, L, dstatus);
+        else k_hh_lut<<<1, 1024, 0, st>>>(cand, sel, chunk_eq, lutk, lutv, L, dstatus);
+        if (v2) {
+            e = fuse ? cudaFuncSetAttribute(k_hh_count2<0, true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt)
+                     : cudaFuncSetAttribute(k_hh_count2<0, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
+        } else {
+            e = cnt ? cudaFuncSetAttribute(k_hh_count<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt)
+                    : cudaFuncSetAttribute(k_hh_count<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cnt);
+        }
         if (e != cudaSuccess) break;
         if (!fresh) e = cudaStreamSynchronize(st);           // base_seen has arrived
         if (e != cudaSuccess) break;
         count_launch();
-        if (cnt)
+        if (v2 && fuse) {
+            k_hh_count2<0, true, 20><<<G, 20 * 32, smem_cnt, st>>>(
+                item, n, lutk, L, NB, sel, static_cast<unsigned*>(rc), rl,
+                static_cast<unsigned*>(buckets), wm, nullptr, nullptr, nullptr, base_seen, fuse->parts,
+                fuse->item_is_f64);
+            fuse->used = G;
+        } else if (v2)
+            k_hh_count2<0, false, 24><<<G, 24 * 32, smem_cnt, st>>>(
+                item, n, lutk, L, NB, sel, static_cast<unsigned*>(rc), rl,
+                static_cast<unsigned*>(buckets), wm, nullptr, nullptr, nullptr, base_seen, nullptr, 0);
+        else if (cnt)
             k_hh_count<unsigned long long><<<G, kHHWarps * 32, smem_cnt, st>>>(
                 item, cnt, n, lutk, lutv, L, C, static_cast<unsigned long long*>(rc), rl,
                 static_cast<unsigned long long*>(buckets), wm, 0, nullptr, nullptr, nullptr, nullptr, base_seen);
@@ -713,7 +748,11 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
         e = cudaFuncSetAttribute(k_hh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
         if (e != cudaSuccess) break;
         count_launch();
-        if (cnt)
+        if (v2)
+            k_hh_reduce2<<<148, 256, (size_t)G * sizeof(long), st>>>(
+                static_cast<const unsigned*>(rc), rl, static_cast<const unsigned*>(buckets), G, nw2, C, L, NB, cslot,
+                wm, n, base_seen, sel, ccnt, clast, dstatus);
+        else if (cnt)
             k_hh_reduce<unsigned long long><<<64, 256, (size_t)G * sizeof(long), st>>>(
                 static_cast<const unsigned long long*>(rc), rl, G, C,
                 static_cast<const unsigned long long*>(buckets), wm, n, base_seen, ccnt, clast, dstatus);
@@ -727,7 +766,7 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
         e = cudaMemcpyAsync(&hs, dstatus, sizeof(HHStatus), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) break;
-        if (hs.fallback) break;                  // *done stays false: nothing was changed
+        if (hs.fallback || hs.lutfail) break;    // *done stays false: nothing was changed
         // exact_only (fresh summary, small batch): every distinct item must get its own counter
         if (exact_only && (long)hs.npos + hs.others > s->cap) break;
         // fold the batch's summary into the object (spsv_merge).  Merging into an empty summary
@@ -754,7 +793,19 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
             count_launch();
             k_hh_scan<<<1, 1024, 0, st>>>(wm, (int)W, wo);
             count_launch();
-            if (cnt)
+            if (v2) {
+                e = nw2 == 20 ? cudaFuncSetAttribute(k_hh_count2<1, false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col)
+                              : cudaFuncSetAttribute(k_hh_count2<1, false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
+                if (e != cudaSuccess) break;
+                if (nw2 == 20)
+                    k_hh_count2<1, false, 20><<<G, 20 * 32, smem_col, st>>>(
+                        item, n, lutk, L, NB, sel, nullptr, nullptr, nullptr, nullptr, wo, miss_item,
+                        miss_pos, base_seen, nullptr, 0);
+                else
+                    k_hh_count2<1, false, 24><<<G, 24 * 32, smem_col, st>>>(
+                        item, n, lutk, L, NB, sel, nullptr, nullptr, nullptr, nullptr, wo, miss_item,
+                        miss_pos, base_seen, nullptr, 0);
+            } else if (cnt)
                 k_hh_count<unsigned long long><<<G, kHHWarps * 32, smem_cnt, st>>>(
                     item, cnt, n, lutk, lutv, L, C, static_cast<unsigned long long*>(rc), rl,
                     static_cast<unsigned long long*>(buckets), wm, 1, wo, miss_item, miss_pos, miss_cnt, base_seen);
@@ -879,6 +930,51 @@ int crick_spsv_update(crick_spsv_t* s, const int64_t* item, const int64_t* count
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
     return e == cudaSuccess ? 0 : fail("spsv_update", e);
+}
+
+// SpaceSaving.update(item) and SummaryStats.update(item) in ONE pass over the items (BASELINE
+// config 5).  Unit counts.  The moments are fused into the counting pass of the heavy-hitter path;
+// where that path does not apply (short batches, capacity > 1024, a batch it hands back) the two
+// sketches are updated one after the other -- same results, two passes.
+int crick_spsv_update_stats(crick_spsv_t* s, crick_stats_t* stats, const int64_t* item, int64_t n,
+                            int item_on_device, int item_is_f64, void* stream) {
+    if (!stats) return fail_msg("spsv_update_stats: stats must not be NULL");
+    if (n <= 0) return 0;
+    cudaStream_t st = sp_stream(s, stream);
+    if (sp_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    const long long* di = reinterpret_cast<const long long*>(item);
+    unsigned char* stage = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!item_on_device) {
+        e = cudaMallocAsync(&stage, (size_t)n * 8, st);
+        if (e != cudaSuccess) return fail("cudaMallocAsync(spsv stage)", e);
+        e = staged_copy_h2d(stage, item, n, st);
+        di = reinterpret_cast<const long long*>(stage);
+    }
+    bool done = false;
+    if (e == cudaSuccess && s->cap <= kSpsvHHMaxCap && n >= kSpsvHHMin && hh2_enabled()) {
+        HHFuse fuse{nullptr, item_is_f64 ? 1 : 0, 0};
+        int nparts = 0;
+        if (stats_fused_begin(stats, st, &fuse.parts, &nparts)) { if (stage) cudaFreeAsync(stage, st); return -1; }
+        if (sm_count() <= nparts) {
+            e = sp_launch_update_hh(s, di, nullptr, n, st, &done, false, &fuse);
+            if (e == cudaSuccess && done) e = stats_fused_finish(stats, fuse.used, st);
+        }
+    }
+    int rc = 0;
+    if (e == cudaSuccess && !done) {
+        // two passes (the device copy is reused, so host input crosses the bus once)
+        rc = crick_stats_update(stats, di, item_is_f64 ? 0 : 1, nullptr, 1, n, 1, 0, st);
+        if (rc == 0) e = sp_launch_update(s, di, nullptr, 1, n, st, 0);
+    }
+    s->known_empty = false;
+    if (stage) {
+        cudaFreeAsync(stage, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (rc) return rc;
+    return e == cudaSuccess ? 0 : fail("spsv_update_stats", e);
 }
 
 int crick_spsv_merge(crick_spsv_t* s, crick_spsv_t* const* others, int n_others) {

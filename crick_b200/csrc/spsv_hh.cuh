@@ -41,6 +41,7 @@ struct HHStatus {
     long long emax;     // fullest miss bucket (sum of the counts of its elements)
     int kept, ncand, fallback;
     int npos;           // candidates that occur in the batch at all
+    int lutfail, pad;   // k_hh_lut2 could not place every candidate (cuckoo insertion gave up)
 };
 
 __device__ __forceinline__ unsigned long long hh_mix(unsigned long long z) {
@@ -448,6 +449,304 @@ __global__ void __launch_bounds__(1024) k_hh_finish(const long long* __restrict_
         h.seen = base_seen + n; h.mixed = 0; h.pad = 0;
         *g.hdr = h;
         status->others = others; status->emax = s_emax; status->kept = K; status->fallback = fallback ? 1 : 0;
+    }
+}
+
+// ---- round 2: the counting pass for unit counts -------------------------------------------------
+// ncu of k_hh_count on Zipf(1.1) items (profiles/r1_hh_count_summary.md, r2_b): 0.32 of the HBM
+// peak, 88 warp instructions per item-row (64-bit hash multiply, 64-bit index arithmetic, a
+// branchy probe loop; 18 of 32 lanes active), `wait` the top stall, and every second item (the
+// ones that are no candidates) a REDG into the 1 Mi L2 bucket counters.  This version:
+//   * 32-bit arithmetic throughout: a 2-multiply hash of the two key halves, int offsets inside the
+//     warp's range, 32-bit miss counts;
+//   * the lookup image is keys only: the counters are indexed by the SLOT the key sits in (the
+//     reduction maps slots back to candidates), so a hit needs no second load;
+//   * the first probe of all items of a round is batched, the second is predicated on the lanes
+//     that need one, only the rare third and later probes loop;
+//   * ONE atomic per item, whatever it is: hits go to the slot's u32 counter, misses to one of NB
+//     per-CTA miss buckets, both in shared memory and both by `red.shared.add.u32 ..., 1` (SASS
+//     ATOMS.POPC.INC: the hardware folds the lanes of a warp that hit the same address -- a Zipf
+//     stream's top items arrive several per warp), selected by address, not by a branch; no
+//     global atomics.  The per-CTA bucket rows are summed by k_hh_reduce2;
+//   * the latest position of a candidate (ATOMS.MAX) is only tracked while the summary may come
+//     out exact -- every distinct sampled item is a candidate (sel->tstar == 0); list order by
+//     latest update is only defined for exact summaries;
+//   * STATS: the SummaryStats moments of the items (stats_update_ndarray :199-210, count 1) ride
+//     in the same pass -- BASELINE config 5 reads its 8 B per item once for both sketches.
+// MODE 0: count.  MODE 1: collect the misses in stream order at miss_off[w] (same warp ranges).
+constexpr int kHH2U = 8;   // warps per CTA: a template parameter (24 plain, 16 with fused moments: registers)
+
+__device__ __forceinline__ unsigned hh2_hash(long long k) {
+    const unsigned lo = (unsigned)k, hi = (unsigned)((unsigned long long)k >> 32);
+    return lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+}
+// three slot choices per key (3-way cuckoo hashing: at load 0.5 the insertion succeeds with
+// overwhelming probability and a lookup is three INDEPENDENT probes -- no probe loop whose trip
+// count is the maximum over the 32 lanes of a warp)
+__device__ __forceinline__ unsigned hh2_slot(unsigned h, int lbits, int which) {
+    if (which == 0) return h >> (32 - lbits);
+    if (which == 1) return (h * 0xC2B2AE3Du) >> (32 - lbits);
+    return ((h ^ (h >> 15)) * 0x27D4EB2Fu) >> (32 - lbits);
+}
+__device__ __forceinline__ unsigned hh2_bucket(unsigned h, unsigned NB) {
+    return __umulhi(__funnelshift_l(h, h, 13) * 0xC2B2AE3Du, NB);     // NB need not be a power of two
+}
+
+// lookup image for k_hh_count2: keys only, 3-way cuckoo (parallel insertion with atomicExch: a
+// thread that displaces a key carries it to that key's next choice).  Which slot a key ends up in
+// depends on the interleaving, but nothing downstream does: counters are per slot, and
+// cand_slot[j] = the slot candidate j landed in.
+__global__ void __launch_bounds__(1024) k_hh_lut2(const long long* __restrict__ cand_key,
+                                                  const HHSel* __restrict__ sel,
+                                                  const int* __restrict__ chunk_eq, long long* lut_key,
+                                                  int* cand_slot, int L, HHStatus* status) {
+    __shared__ int s_w32[32];
+    __shared__ int s_ncand;
+    const int tid = threadIdx.x;
+    int te = 0;
+    for (int j = tid; j < kHHNChunk; j += 1024) te += chunk_eq[j];
+    te = hh_block_scan(te, s_w32);
+    if (tid == 1023) s_ncand = sel->above + (te < sel->quota ? te : sel->quota);
+    for (int i = tid; i < L; i += 1024) lut_key[i] = kHHEmpty;
+    __syncthreads();
+    const int ncand = s_ncand;
+    const int lbits = 31 - __clz(L);
+    bool failed = false;
+    for (int j = tid; j < ncand; j += 1024) {
+        long long key = cand_key[j];
+        int which = 0;
+        for (int iter = 0; iter < 2000 && key != kHHEmpty; ++iter) {
+            const unsigned pos = hh2_slot(hh2_hash(key), lbits, which);
+            const long long old = (long long)atomicExch(reinterpret_cast<unsigned long long*>(&lut_key[pos]),
+                                                        (unsigned long long)key);
+            if (old != kHHEmpty) {        // displaced: it moves on to the choice after the one it had here
+                const unsigned ho = hh2_hash(old);
+                const int w = hh2_slot(ho, lbits, 0) == pos ? 0 : (hh2_slot(ho, lbits, 1) == pos ? 1 : 2);
+                which = w == 2 ? 0 : w + 1;
+            }
+            key = old;
+        }
+        failed |= key != kHHEmpty;
+    }
+    if (__syncthreads_or(failed) && tid == 0) status->lutfail = 1;
+    __threadfence_block();
+    for (int j = tid; j < ncand; j += 1024) {
+        const long long key = cand_key[j];
+        const unsigned h = hh2_hash(key);
+        int slot = -1;
+        for (int wch = 0; wch < 3; ++wch) {
+            const unsigned pos = hh2_slot(h, lbits, wch);
+            if (lut_key[pos] == key) { slot = (int)pos; break; }
+        }
+        cand_slot[j] = slot < 0 ? 0 : slot;
+    }
+    if (tid == 0) status->ncand = ncand;
+}
+
+// predicated 8-byte shared load: only the lanes with `p` issue a request (no branch)
+__device__ __forceinline__ void hh2_lds_if(bool p, unsigned addr, unsigned& x, unsigned& y) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
+                 : "+r"(x), "+r"(y) : "r"(addr), "r"((unsigned)p));
+}
+
+struct HH2Ctx {
+    unsigned a_key, a_cnt, a_last, a_bkt, NB, off_cta;
+    int lbits;
+};
+
+// One round: U items per lane.  FULL: all 32 * U items exist (no validity logic at all).
+// Branch-free: the second and third cuckoo choices are predicated loads, hit / miss pick the
+// address of the single atomic.
+template <int MODE, bool FULL, bool TRACK, int U>
+__device__ __forceinline__ void hh2_round(const HH2Ctx& c, const long long* key, int base, int len,
+                                          int lane, unsigned& nmiss, unsigned long long& out,
+                                          long long* __restrict__ miss_item,
+                                          long long* __restrict__ miss_pos, long pos0) {
+    unsigned h[U], ix[U], kx[U], ky[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        h[u] = hh2_hash(key[u]);
+        ix[u] = hh2_slot(h[u], c.lbits, 0);
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(kx[u]), "=r"(ky[u]) : "r"(c.a_key + 8u * ix[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned klo = (unsigned)key[u], khi = (unsigned)((unsigned long long)key[u] >> 32);
+        bool hit = ((kx[u] ^ klo) | (ky[u] ^ khi)) == 0u;
+        const unsigned p1 = hh2_slot(h[u], c.lbits, 1), p2 = hh2_slot(h[u], c.lbits, 2);
+        unsigned x1 = ~klo, y1 = 0u, x2 = ~klo, y2 = 0u;            // (never equal to the key)
+        hh2_lds_if(!hit, c.a_key + 8u * p1, x1, y1);
+        const bool hit1 = ((x1 ^ klo) | (y1 ^ khi)) == 0u;
+        hh2_lds_if(!hit && !hit1, c.a_key + 8u * p2, x2, y2);
+        const bool hit2 = ((x2 ^ klo) | (y2 ^ khi)) == 0u;
+        ix[u] = hit1 ? p1 : (hit2 ? p2 : ix[u]);
+        // kHHEmpty itself (INT64_MIN, also what padding lanes carry) is never a candidate
+        hit = (hit || hit1 || hit2) && ((klo | (khi ^ 0x80000000u)) != 0u);
+        const int i = base + u * 32 + lane;
+        const bool valid = FULL || i < len;
+        const bool miss = valid && !hit;
+        if (MODE == 0) {
+            const unsigned a = hit ? c.a_cnt + 4u * ix[u] : c.a_bkt + 4u * hh2_bucket(h[u], c.NB);
+            if (FULL) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+            else if (valid) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+            if (TRACK && hit && valid)
+                asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(c.a_last + 4u * ix[u]), "r"(c.off_cta + (unsigned)i + 1u) : "memory");
+            nmiss += miss ? 1u : 0u;
+        } else {
+            const unsigned mm = __ballot_sync(CRICK_FULL, miss);
+            if (miss) {
+                const unsigned long long at = out + __popc(mm & ((1u << lane) - 1u));
+                miss_item[at] = key[u];
+                miss_pos[at] = pos0 + i;
+            }
+            out += __popc(mm);
+        }
+    }
+}
+
+template <int MODE, bool STATS, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_hh_count2(const long long* __restrict__ item, long n, const long long* __restrict__ lut_key, int L,
+            int NB, const HHSel* __restrict__ sel, unsigned* __restrict__ rows_cnt,
+            unsigned* __restrict__ rows_last, unsigned* __restrict__ rows_bkt,
+            unsigned long long* __restrict__ warp_miss, const unsigned long long* __restrict__ miss_off,
+            long long* __restrict__ miss_item, long long* __restrict__ miss_pos, long base_seen,
+            StatsPart* __restrict__ stats_parts, int item_is_f64) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint2* s_key = reinterpret_cast<uint2*>(sm);                            // [L] (lo, hi)
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_key + L);               // [L]   (MODE 0)
+    unsigned* s_last = s_cnt + L;                                           // [L]
+    unsigned* s_bkt = s_last + L;                                           // [NB]
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    for (int i = tid; i < L; i += blockDim.x) s_key[i] = reinterpret_cast<const uint2*>(lut_key)[i];
+    if (MODE == 0) {
+        for (int i = tid; i < 2 * L + NB; i += blockDim.x) s_cnt[i] = 0;    // cnt | last | buckets
+    }
+    __syncthreads();
+    const bool track_last = MODE == 0 && sel->tstar == 0;
+    const long W = (long)gridDim.x * NW;
+    const long w = (long)blockIdx.x * NW + wib;
+    const long cta_lo = (long)(((__int128)((long)blockIdx.x * NW) * n) / W);
+    const long lo = (long)(((__int128)w * n) / W), hi = (long)(((__int128)(w + 1) * n) / W);
+    const int len = (int)(hi - lo);                     // a warp's range: < 2^31 items
+    const long long* __restrict__ src = item + lo;
+    HH2Ctx c;
+    c.a_key = (unsigned)__cvta_generic_to_shared(s_key);
+    c.a_cnt = (unsigned)__cvta_generic_to_shared(s_cnt);
+    c.a_last = (unsigned)__cvta_generic_to_shared(s_last);
+    c.a_bkt = (unsigned)__cvta_generic_to_shared(s_bkt);
+    c.NB = (unsigned)NB;
+    c.off_cta = (unsigned)(lo - cta_lo);                // position of the range inside the CTA's
+    c.lbits = 31 - __clz(L);
+    unsigned nmiss = 0;
+    unsigned long long out = MODE == 1 ? miss_off[w] : 0ull;
+    const long pos0 = base_seen + lo;
+    StatsAcc sa;
+    StatsPart sp;
+    stats_acc_fresh(sa);
+    part_fresh(sp);
+    constexpr int U = kHH2U;
+    int base = 0;
+    for (; base + 32 * U <= len; base += 32 * U) {
+        long long key[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) key[u] = __ldg(src + base + u * 32 + lane);
+        if (STATS) {
+            double xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = item_is_f64 ? __longlong_as_double(key[u]) : (double)key[u];
+            if (item_is_f64) stats_block_unit2<U, true>(sa, sp, xv, [&](int k) { return pos0 + base + k * 32 + lane; });
+            else stats_block_unit2<U, false>(sa, sp, xv, [&](int k) { return pos0 + base + k * 32 + lane; });
+        }
+        if (track_last) hh2_round<MODE, true, true, U>(c, key, base, len, lane, nmiss, out, miss_item, miss_pos, pos0);
+        else hh2_round<MODE, true, false, U>(c, key, base, len, lane, nmiss, out, miss_item, miss_pos, pos0);
+    }
+    if (base < len) {
+        long long key[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * 32 + lane;
+            key[u] = i < len ? __ldg(src + i) : kHHEmpty;
+            if (STATS && i < len)
+                stats_one<true>(sa, sp, item_is_f64 ? __longlong_as_double(key[u]) : (double)key[u], 1, pos0 + i);
+        }
+        hh2_round<MODE, false, true, U>(c, key, base, len, lane, nmiss, out, miss_item, miss_pos, pos0);
+    }
+    if (MODE == 0) {
+        nmiss = __reduce_add_sync(CRICK_FULL, nmiss);
+        if (lane == 0) warp_miss[w] = nmiss;
+        __shared__ StatsPart s_sp[STATS ? NW : 1];
+        if (STATS) {
+            stats_thread_finish2(sa, sp);
+            sp = stats_warp_reduce(sp);
+            if (lane == 0) s_sp[wib] = sp;
+        }
+        __syncthreads();
+        for (int i = tid; i < L; i += blockDim.x) {
+            rows_cnt[(size_t)blockIdx.x * L + i] = s_cnt[i];
+            rows_last[(size_t)blockIdx.x * L + i] = s_last[i];
+        }
+        for (int i = tid; i < NB; i += blockDim.x) rows_bkt[(size_t)blockIdx.x * NB + i] = s_bkt[i];
+        if (STATS && tid == 0) {
+            StatsPart t = s_sp[0];
+            for (int wv = 1; wv < NW; ++wv) part_merge(t, s_sp[wv]);
+            stats_parts[blockIdx.x] = t;
+        }
+    }
+}
+
+// Sums over the counting CTAs: exact count and latest position of every candidate, the number of
+// misses and the fullest miss bucket.  Candidates first (C threads' worth of work), then the
+// bucket columns; any grid.
+__global__ void __launch_bounds__(256) k_hh_reduce2(const unsigned* __restrict__ rows_cnt,
+                                                    const unsigned* __restrict__ rows_last,
+                                                    const unsigned* __restrict__ rows_bkt, int G, int nw,
+                                                    int C, int L, int NB, const int* __restrict__ cand_slot,
+                                                    const unsigned long long* __restrict__ warp_miss,
+                                                    long n, long base_seen, const HHSel* __restrict__ sel,
+                                                    long long* cand_cnt, long long* cand_last,
+                                                    HHStatus* status) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    long* s_lo = reinterpret_cast<long*>(sm);   // [G] first element of every counting CTA
+    const long W = (long)G * nw;
+    for (int g = threadIdx.x; g < G; g += blockDim.x)
+        s_lo[g] = (long)(((__int128)((long)g * nw) * n) / W);
+    __syncthreads();
+    const bool tracked = sel->tstar == 0;
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+    const int ncand = status->ncand;
+    for (long c = tid; c < C; c += nthr) {
+        long long cnt = 0, last = -1;
+        if (c < ncand) {
+            const int slot = cand_slot[c];              // the counters are indexed by lookup slot
+            for (int g = 0; g < G; ++g) {
+                const unsigned rc = rows_cnt[(size_t)g * L + slot];
+                const unsigned rl = rows_last[(size_t)g * L + slot];
+                cnt += (long long)rc;
+                const long long p = rc ? base_seen + s_lo[g] + (long long)rl - 1 : -1;
+                last = p > last ? p : last;
+            }
+        }
+        cand_cnt[c] = cnt;
+        // untracked (the summary cannot come out exact): ties fall by candidate index
+        cand_last[c] = tracked ? last : (cnt ? base_seen + n - 1 : -1);
+    }
+    unsigned long long oth = 0, emax = 0;
+    for (long i = tid; i < W; i += nthr) oth += warp_miss[i];
+    for (long b = tid; b < NB; b += nthr) {
+        unsigned long long t = 0;
+        for (int g = 0; g < G; ++g) t += rows_bkt[(size_t)g * NB + b];
+        emax = t > emax ? t : emax;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        oth += __shfl_xor_sync(CRICK_FULL, oth, d);
+        const unsigned long long o = __shfl_xor_sync(CRICK_FULL, emax, d);
+        emax = o > emax ? o : emax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (oth) atomicAdd(reinterpret_cast<unsigned long long*>(&status->others), oth);
+        if (emax) atomicMax(reinterpret_cast<unsigned long long*>(&status->emax), emax);
     }
 }
 

@@ -21,6 +21,7 @@ __device__ __forceinline__ double u01(unsigned long long r) {  // (0, 1)
 // kind 2: x = N(0, 1),                 w = U(0.5, 1.5)
 // kind 3: x = Zipf(1.1)-like heavy-tailed positive integers stored as f64 (inverse-CDF of the
 //         continuous Pareto with the same tail, floored), w = 1
+// kind 4: the same integers stored as int64 bit patterns (BASELINE config 5's int64 stream)
 __global__ void k_synth(double* __restrict__ x, double* __restrict__ w, long n,
                         unsigned long long seed, long offset, int kind) {
     long stride = (long)gridDim.x * blockDim.x;
@@ -32,15 +33,15 @@ __global__ void k_synth(double* __restrict__ x, double* __restrict__ w, long n,
         double u0 = u01(r0), u1 = u01(r1), u2 = u01(r2);
         double v;
         if (kind == 1) v = u0;
-        else if (kind == 3) {
+        else if (kind == 3 || kind == 4) {
             double p = pow(u0, -10.0);           // Pareto(alpha = 0.1): tail ~ k^-1.1
             v = p > 9.0e18 ? 9.0e18 : floor(p);
         } else {
             double nrm = sqrt(-2.0 * log(u0)) * cospi(2.0 * u1);
             v = (kind == 0) ? exp(nrm) : nrm;
         }
-        x[i] = v;
-        if (w) w[i] = (kind == 3) ? 1.0 : 0.5 + u2;
+        x[i] = kind == 4 ? __longlong_as_double((long long)v) : v;
+        if (w) w[i] = (kind == 3 || kind == 4) ? 1.0 : 0.5 + u2;
     }
 }
 

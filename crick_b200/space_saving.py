@@ -171,17 +171,23 @@ class SpaceSaving:
             return
         check(lib.crick_spsv_add(self._h, self._item_bits(item), count), "add")
 
-    def update(self, item, count=1, stream=None, mode=0):
+    def update(self, item, count=1, stream=None, mode=0, stats=None):
         """update(self, item, count=1)
 
         Add many elements to the summary.  `item` may be NumPy-compatible or an
         int64 / float64 CUDA array matching the summary's dtype.  ``mode`` (an addition) picks
         the kernel: 0 auto, 1 in-order replay, 2 shard summaries, 3 candidate counting
-        (see ``crick_spsv_update`` in include/crick_cuda.h).
+        (see ``crick_spsv_update`` in include/crick_cuda.h).  ``stats`` (an addition): a
+        :class:`SummaryStats` that receives ``stats.update(item)`` in the same pass over the
+        items (count 1 only; ``crick_spsv_update_stats``).
         """  # space_saving.pyx:270-302
         mode = int(mode)
         if self._obj is not None:
+            if stats is not None:
+                raise TypeError("stats= needs a numeric summary dtype")
             return self._update_object(item, count)
+        if stats is not None:
+            return self._update_with_stats(item, count, stream, stats)
         idv = device_view(item)
         if idv is not None:
             if idv.dtype != self.dtype:
@@ -219,6 +225,30 @@ class SpaceSaving:
         else:
             check(lib.crick_spsv_update(self._h, xf.ctypes.data, None, int(cf), xf.size, 0, 0, mode,
                                         stream), "update")
+
+    def _update_with_stats(self, item, count, stream, stats):
+        from .stats import SummaryStats
+        if not isinstance(stats, SummaryStats):
+            raise TypeError("stats must be a SummaryStats")
+        if not (np.isscalar(count) and count == 1):
+            raise ValueError("stats= needs count == 1")
+        f64 = int(self.dtype.kind == "f")
+        idv = device_view(item)
+        if idv is not None:
+            if idv.dtype != self.dtype:
+                raise TypeError("CUDA item array must have dtype %s" % self.dtype)
+            if idv.size:
+                check(lib.crick_spsv_update_stats(self._h, stats._h, idv.ptr, idv.size, 1, f64, stream),
+                      "update")
+            return
+        item = np.asarray(item).astype(self.dtype, casting="safe", copy=False)
+        if item.size == 0:
+            return
+        if f64:
+            item = item.view("i8")
+        xf, _ = korder_pair(item, np.int64(1), w_dtype="i8", x_dtype="i8")
+        check(lib.crick_spsv_update_stats(self._h, stats._h, xf.ctypes.data, xf.size, 0, f64, stream),
+              "update")
 
     def _update_object(self, item, count):
         """spsv_object_update_ndarray, space_saving_stubs.c.in:367-451: the same coercion,

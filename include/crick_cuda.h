@@ -242,6 +242,14 @@ int crick_spsv_add(crick_spsv_t *s, int64_t item, int64_t count);            /* 
 int crick_spsv_update(crick_spsv_t *s, const int64_t *item, const int64_t *count,
                       int64_t count_scalar, int64_t n, int item_on_device, int count_on_device,
                       int mode, void *stream);
+/* spsv_int64_update_ndarray :367-451 (count 1) and stats_update_ndarray (stats_stubs.c:139-226,
+ * count 1) of the SAME items in ONE pass over them (BASELINE config 5: 8 B per item read once for
+ * both sketches): the moments are accumulated inside the counting pass.  item_is_f64: the items
+ * are float64 bit patterns (SpaceSaving dtype f8), else int64 (cast to double for the moments
+ * like NumPy's safe cast).  Batches the counting path does not take (fewer than 65536 items,
+ * capacity > 1024) update the two sketches one after the other: same results, two passes. */
+int crick_spsv_update_stats(crick_spsv_t *s, crick_stats_t *stats, const int64_t *item, int64_t n,
+                            int item_on_device, int item_is_f64, void *stream);
 int crick_spsv_merge(crick_spsv_t *s, crick_spsv_t *const *others, int n_others); /* :289-364 */
 int crick_spsv_set_state(crick_spsv_t *s, const int64_t *counters3, int64_t n);   /* :253-286 */
 /* Multi-GPU tail: a summary as the fixed-size int64 record

@@ -377,6 +377,42 @@ def test_spsv_counting_path_is_a_valid_summary(cb, kind):
         _assert_valid_summary(s.counters(), np.concatenate([items, items[: n // 2]]), cap)
 
 
+@pytest.mark.parametrize("dtype,n", [("i8", 3 * 10**6), ("f8", 400000), ("i8", 30000)])
+def test_spsv_and_moments_in_one_pass(cb, dtype, n):
+    """BASELINE config 5: SummaryStats moments + SpaceSaving over the same items in ONE pass
+    (crick_spsv_update_stats): the summary is the one the plain update builds, byte for byte, and
+    the moments are those of the stand-alone SummaryStats pass (count / min / max exactly, the
+    rest within the 1e-12 class of the parallel pass; test_stats.py:20-21 style check vs NumPy)."""
+    rng = np.random.default_rng(n)
+    items = rng.zipf(1.2, n).astype(np.int64)
+    if dtype == "f8":
+        items = (items % 5000).astype(np.float64) * 0.25
+        items[::1000] = np.nan
+    for dev in (True, False):
+        s1, st1 = cb.SpaceSaving(1000, dtype), cb.SummaryStats()
+        s2, st2 = cb.SpaceSaving(1000, dtype), cb.SummaryStats()
+        x = cb.DeviceArray.from_numpy(items) if dev else items
+        s1.update(x, stats=st1)
+        s2.update(x)
+        st2.update(x)
+        assert s1.counters().tobytes() == s2.counters().tobytes()
+        a, b = st1.__getstate__(), st2.__getstate__()
+        assert a[0] == b[0] == np.count_nonzero(~np.isnan(items.astype(np.float64)))
+        assert a[2] == b[2] and a[3] == b[3] and a[7] == b[7] and a[8] == b[8]
+        for u, v in zip(a[1:7], b[1:7]):
+            assert abs(u - v) <= 1e-11 * abs(v)
+        xs = items.astype(np.float64)
+        assert abs(st1.mean() - np.nanmean(xs)) <= 1e-12 * abs(np.nanmean(xs))
+        assert abs(st1.var() - np.nanvar(xs)) <= 1e-9 * np.nanvar(xs)
+    # a second batch on top (the summary is no longer fresh), stats accumulate
+    s1.update(x, stats=st1)
+    s2.update(x)
+    assert s1.counters().tobytes() == s2.counters().tobytes()
+    assert st1.count() == 2 * a[0]
+    with pytest.raises(ValueError):
+        s1.update(x, 2, stats=st1)
+
+
 def test_spsv_records_merge_like_the_reference(cb):
     """Multi-GPU tail: records exported on the device, concatenated as an
     all-gather would deliver them, and merged in rank order must equal
