@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the crick hot path on B200 (contract: see DESIGN.md 6).
+"""bench.py -- headline benchmark of the crick hot path on B200 (contract: see DESIGN.md 5).
 
-Metric (BASELINE.json): TDigest.update Gvalues/s over 1e9 float64 values with float64 weights
-(lognormal x, U(0.5,1.5) w, compression 100) -- BASELINE.json configs[1] -- per GPU, weak
-scaling: every rank owns a 1e9-value shard of one logical stream; with N > 1 each step ends with
-the all-gather of the (3.2 KB) centroid records and the on-device merge in rank order.
+Metric (BASELINE.json): TDigest.update Gvalues/s over ONE stream of 1e9 float64 values with
+float64 weights (lognormal x, U(0.5,1.5) w, compression 100) -- BASELINE.json configs[1] --
+sharded over the N GPUs of the node: rank r owns the contiguous range [r n / N, (r + 1) n / N)
+(strong scaling: the total stays 1e9), builds its partial digest, and with N > 1 every step ends
+with the all-gather of the 3.2 KB centroid records and the on-device merge in rank order.  The
+weak-scaling figure (1e9 values per GPU) of the same step is reported next to it under "weak".
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n VALUES]
 
 One JSON line on rank 0.  `value` = device-resident throughput (inputs in HBM before the timed
 region), `e2e` = the same through TDigest.update() on pinned HOST arrays (H2D inside the timed
-region, centroids read back every step), `roofline` = the hot kernel (k_bin_accumulate) against
-the measured HBM peak, `cpu_baseline` = the reference's own C code on this box's host cores.
+region, centroids read back every step), `e2e_pageable` = the same on ordinary NumPy arrays,
+`roofline` = the hot kernel (k_bin_accumulate2) against the measured HBM peak (weighted,
+16 B/value) and `roofline_unweighted` the w = 1 call dask makes (8 B/value), `cpu_baseline` = the
+reference's own C code on this box's host cores, `other_configs` = BASELINE configs 3, 4 and 5
+at full size (value, roofline fraction, parity mismatches against the oracle, CPU baseline).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -40,10 +46,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT, help="values per GPU per step")
+    ap.add_argument("--n", type=int, default=N_DEFAULT, help="values of the whole stream per step")
     ap.add_argument("--cpu-sample", type=int, default=2 * 10**8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip BASELINE configs 3, 4, 5")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling leg (N > 1)")
     return ap.parse_args()
 
 
@@ -53,6 +61,10 @@ def peak_hbm():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def shard_bounds(n, rank, world):
+    return (rank * n) // world, ((rank + 1) * n) // world
 
 
 class ClockSampler:
@@ -143,7 +155,7 @@ def run_reference(args, rank, world):
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "config2: single TDigest compression=100 over lognormal f64 + f64 weights",
                    "values_per_step": n, "host_threads": threads,
@@ -167,6 +179,122 @@ def emit(obj):
         os.write(_STDOUT_FD, line)
 
 
+class Bench:
+    """State shared by the legs of one run (one process per GPU)."""
+
+    def __init__(self, args):
+        import torch
+        import crick_b200 as cb
+        from crick_b200._lib import lib
+        self.args, self.torch, self.cb, self.lib = args, torch, cb, lib
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        lib.crick_set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.stream = torch.cuda.Stream()
+        self.sptr = self.stream.cuda_stream
+        self.peak, self.peak_src = peak_hbm()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.dist is None:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        if self.dist is None:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def profile_collect(self):
+        kms, kn = ctypes.c_double(0), ctypes.c_int64(0)
+        self.lib.crick_profile_collect(ctypes.addressof(kms), ctypes.addressof(kn))
+        return kms.value, kn.value
+
+    # ---- config 2: one stream, `m` values on this rank -----------------------------------
+    def timed_updates(self, dx, dw, K, W, reducer, sampler=None):
+        """W warm-up + K timed steps of update(+ all-gather + merge); device time on the launching
+        stream, max over ranks.  Returns (ms, kernel ms total, kernel launches, merged digest,
+        library launches)."""
+        cb, lib, torch = self.cb, self.lib, self.torch
+        digest = cb.TDigest(COMPRESSION, mode="parallel")
+
+        def step():
+            # weights validated on the device ("deferred": the verdict is collected after the
+            # timed region, nothing waits for it inside a step)
+            if dw is not None:
+                digest.update(dx, dw, mode="parallel", stream=self.sptr, check_w="deferred")
+            else:
+                digest.update(dx, mode="parallel", stream=self.sptr)
+            if reducer is not None:
+                with torch.cuda.stream(self.stream):
+                    return reducer(digest)
+            return digest
+
+        merged = None
+        for _ in range(W):
+            merged = step()
+        self.barrier()
+        launches0 = cb.launch_count()
+        lib.crick_profile_enable(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record(self.stream)
+        for _ in range(K):
+            merged = step()
+        ev1.record(self.stream)
+        self.barrier()
+        ms = self.max_over_ranks(ev0.elapsed_time(ev1))
+        lib.crick_profile_enable(0)
+        kms, kn = self.profile_collect()
+        launches = cb.launch_count() - launches0
+        if sampler is not None:
+            # nvidia-smi needs ~0.1-0.3 s for its first line and the timed region may be shorter:
+            # keep the identical load running (untimed) until a few samples exist
+            n_extra = int(min(400, max(0, 600.0 / max(ms / K, 1e-3))))
+            for _ in range(n_extra):
+                step()
+            torch.cuda.synchronize()
+        digest.check_weights()      # raises if any deferred weight check failed
+        return ms, kms, kn, merged, launches
+
+
+def kernel_roofline(bench, name, k_ms_total, k_launches, bytes_per_launch, step_ms_total, traffic_key):
+    k_ms = k_ms_total / max(k_launches, 1)
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    r = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": bench.peak, "unit": "GB/s",
+         "frac": achieved / bench.peak, "traffic": None, "peak_source": bench.peak_src,
+         "kernel_ms_per_launch": k_ms,
+         "kernel_share_of_step": (k_ms_total / step_ms_total) if step_ms_total else None,
+         "algorithmic_bytes_per_launch": bytes_per_launch,
+         # SURVEY.md 8d asks for both denominators: the box-measured copy bandwidth above and
+         # the nominal 8 TB/s of HBM3e
+         "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0}
+    try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        r["traffic"] = tj[traffic_key] * (bytes_per_launch / tj[traffic_key + "_algorithmic"])
+        r["traffic_source"] = tj["source"]
+    except Exception:
+        pass
+    return r
+
+
 def main():
     # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version
     # banner under torchrun, for one) goes to stderr instead
@@ -175,149 +303,109 @@ def main():
     _STDOUT_FD = os.dup(1)
     os.dup2(2, 1)
     args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
 
-    import torch
-    import torch.distributed as dist
-    import crick_b200 as cb
-    from crick_b200._lib import lib
-    from crick_b200.distributed import allgather_merge_tdigest
-
-    torch.cuda.set_device(local_rank)
-    lib.crick_set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = Bench(args)
+    cb, lib, torch = B.cb, B.lib, B.torch
+    rank, world = B.rank, B.world
+    from crick_b200.distributed import TDigestAllReduce, allgather_merge_tdigest
 
     n = args.n
     K, W = args.steps, args.warmup
-    stream = torch.cuda.Stream()
-    sptr = stream.cuda_stream
+    lo, hi = shard_bounds(n, rank, world)
+    m = hi - lo
 
     # ---- synthetic, device-resident shard: element i of the stream depends on (seed, i) only
-    dx, dw = cb.DeviceArray((n,)), cb.DeviceArray((n,))
-    lib.crick_synth_fill(dx.ptr, dw.ptr, n, SEED, rank * n, 0, None)
+    dx, dw = cb.DeviceArray((m,)), cb.DeviceArray((m,))
+    lib.crick_synth_fill(dx.ptr, dw.ptr, m, SEED, lo, 0, None)
     lib.crick_device_synchronize()
+    reducer = TDigestAllReduce(COMPRESSION, exact=False) if world > 1 else None
 
-    reducer = None
-    if world > 1:
-        from crick_b200.distributed import TDigestAllReduce
-        reducer = TDigestAllReduce(COMPRESSION, exact=False)
-
-    def step(t):
-        t.update(dx, dw, mode="parallel", stream=sptr)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                return reducer(t)
-        return t
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    digest = cb.TDigest(COMPRESSION, mode="parallel")
-    merged = None
     # clocks are sampled every 100 ms from before the warm-up (the same load) to the end of
     # the timed region, which by itself may be shorter than one sample period
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(B.local_rank)
     sampler.start()
-    for _ in range(W):
-        merged = step(digest)
-    barrier()
-    launches0 = cb.launch_count()
-    lib.crick_profile_enable(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(K):
-        merged = step(digest)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    lib.crick_profile_enable(0)
-    import ctypes
-    kms, kn = ctypes.c_double(0), ctypes.c_int64(0)
-    lib.crick_profile_collect(ctypes.addressof(kms), ctypes.addressof(kn))
-    launches = cb.launch_count() - launches0
-    # nvidia-smi needs ~0.1-0.3 s to print its first line and the timed region may be shorter:
-    # keep the identical load running (untimed) until a few samples exist
-    if world > 1:   # the same count on every rank (a step holds a collective)
-        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    n_extra = int(min(400, max(0, 600.0 / max(ms / K, 1e-3))))
-    for _ in range(n_extra):
-        step(digest)
-    torch.cuda.synchronize()
+    ms, kms, kn, merged, launches = B.timed_updates(dx, dw, K, W, reducer, sampler)
     clocks = sampler.stop()
     clocks["note"] = "sampled every 100 ms from the warm-up through the timed region and an identical untimed tail"
-    value = world * n * K / (ms * 1e-3) / 1e9
+    value = n * K / (ms * 1e-3) / 1e9
     nc = len(merged.centroids())
     total_size = merged.size()
+    roofline = kernel_roofline(B, "k_bin_accumulate2<weighted>", kms, kn, ALGO_BYTES_PER_VALUE * m, ms,
+                               "k_bin_accumulate2_weighted_dram_bytes")
 
-    # ---- roofline of the dominant kernel (k_bin_accumulate), CUDA events around each launch
-    peak, peak_src = peak_hbm()
-    k_ms = kms.value / max(kn.value, 1)
-    achieved = (ALGO_BYTES_PER_VALUE * n) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_bin_accumulate", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms_per_launch": k_ms, "kernel_share_of_step": (kms.value / ms) if ms else None,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VALUE * n,
-                # SURVEY.md 8d asks for both denominators: the box-measured copy bandwidth above
-                # and the nominal 8 TB/s of HBM3e
-                "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0}
-    try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to n
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-        roofline["traffic"] = tj["k_bin_accumulate_dram_bytes_per_value"] * n
-        roofline["traffic_source"] = tj["source"]
-    except Exception:
-        pass
+    # ---- the unweighted call (w = 1: what dask's percentile makes), same shard, 8 B/value
+    ums, ukms, ukn, _, _ = B.timed_updates(dx, None, K, W, reducer)
+    roofline_unweighted = kernel_roofline(B, "k_bin_accumulate2<unweighted>", ukms, ukn, 8 * m, ums,
+                                          "k_bin_accumulate2_unweighted_dram_bytes")
+    roofline_unweighted["value_gvalues_s"] = n * K / (ums * 1e-3) / 1e9
+    roofline_unweighted["ms_per_step"] = ums / K
 
-    # ---- e2e: public API on pinned HOST arrays; H2D every step, centroids read back every step
-    e2e = None
+    # ---- weak scaling next to it (N > 1): 1e9 values on EVERY GPU, same step
+    weak = None
+    if world > 1 and not args.no_weak:
+        del dx, dw
+        dx, dw = cb.DeviceArray((n,)), cb.DeviceArray((n,))
+        lib.crick_synth_fill(dx.ptr, dw.ptr, n, SEED, rank * n, 0, None)
+        lib.crick_device_synchronize()
+        wms, wkms, wkn, _, _ = B.timed_updates(dx, dw, K, W, reducer)
+        weak = {"scaling": "weak", "value": world * n * K / (wms * 1e-3) / 1e9, "unit": UNIT,
+                "ms_per_step": wms / K, "values_per_gpu_per_step": n,
+                "kernel_frac_of_peak": (ALGO_BYTES_PER_VALUE * n) / (wkms / max(wkn, 1) * 1e-3) / 1e9 / B.peak}
+        del dx, dw
+        dx, dw = cb.DeviceArray((m,)), cb.DeviceArray((m,))
+        lib.crick_synth_fill(dx.ptr, dw.ptr, m, SEED, lo, 0, None)
+        lib.crick_device_synchronize()
+
+    # ---- e2e: public API on HOST arrays; H2D every step, centroids read back every step
+    e2e = e2e_pageable = None
     if not args.no_e2e:
         import psutil
-        need = 16 * n
-        avail = psutil.virtual_memory().available
-        ne = n
-        while 16 * ne * (world if world > 1 else 1) * 2 > avail and ne > 10**7:
-            ne //= 2
-        try:
-            hx, hw = cb.PinnedArray(ne), cb.PinnedArray(ne)
-            lib.crick_memcpy_d2h(hx.ptr, dx.ptr, 8 * ne, None)
-            lib.crick_memcpy_d2h(hw.ptr, dw.ptr, 8 * ne, None)
-            ke = max(1, min(K, 5))
+        me = m
+        while 16 * me * world * 2 > psutil.virtual_memory().available and me > 10**7:
+            me //= 2
+
+        def e2e_leg(hx, hw, steps, api):
             def e2e_step():
                 t = cb.TDigest(COMPRESSION, mode="parallel")
-                t.update(hx.array, hw.array)
+                t.update(hx, hw)
                 if world > 1:
                     t = allgather_merge_tdigest(t)
                 return t.centroids()
             e2e_step()
-            barrier()
+            B.barrier()
             t0 = time.perf_counter()
-            for _ in range(ke):
+            for _ in range(steps):
                 cen = e2e_step()
-            barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-                dt = float(tdt.item())
-            e2e = {"value": world * ne * ke / dt / 1e9, "unit": UNIT,
-                   "h2d_bytes_per_step": 16 * ne, "d2h_bytes_per_step": int(cen.nbytes),
-                   "values_per_step_per_gpu": ne, "steps": ke,
-                   "api": "crick_b200.TDigest.update(numpy over pinned host memory) + centroids()"}
+            B.barrier()
+            dt = B.max_over_ranks(time.perf_counter() - t0)
+            tot = B.sum_over_ranks(me)
+            return {"value": tot * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 16 * me,
+                    "d2h_bytes_per_step": int(cen.nbytes), "values_per_step_per_gpu": me,
+                    "steps": steps, "h2d_gbs_per_rank": 16 * me * steps / dt / 1e9, "api": api}
+        try:
+            hx, hw = cb.PinnedArray(me), cb.PinnedArray(me)
+            lib.crick_memcpy_d2h(hx.ptr, dx.ptr, 8 * me, None)
+            lib.crick_memcpy_d2h(hw.ptr, dw.ptr, 8 * me, None)
+            e2e = e2e_leg(hx.array, hw.array, max(1, min(K, 5)),
+                          "crick_b200.TDigest.update(numpy over pinned host memory) + centroids()")
+            # ordinary (pageable) NumPy arrays: what a caller who never heard of pinned memory has
+            px, pw = np.array(hx.array), np.array(hw.array)
             del hx, hw
+            e2e_pageable = e2e_leg(px, pw, max(1, min(K, 3)),
+                                   "crick_b200.TDigest.update(ordinary numpy arrays) + centroids()")
+            del px, pw
         except MemoryError as exc:
-            e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+            e2e = e2e or {"value": None, "unit": UNIT, "error": str(exc)}
+    del dx, dw
+
+    # ---- the other configs of BASELINE.json at full size
+    others = None
+    if not args.no_others:
+        from bench_configs import run_other_configs
+        others = run_other_configs(B, cpu=(world == 1 and not args.no_cpu))
 
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     cpu = None
@@ -331,20 +419,24 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config2: single TDigest compression=100 over 1e9 lognormal f64 + "
-                                   "f64 weights per GPU, parallel k-bucket mode"
-                                   + ("; centroid all-gather + one-pass merge of the gathered records every step" if world > 1 else ""),
-                       "values_per_gpu_per_step": n, "compression": COMPRESSION,
-                       "l2": "inputs (16 B x %d = %.1f GB per step) far exceed the 126 MB L2" % (n, 16 * n / 1e9),
+            "config": {"workload": "config2: single TDigest compression=100 over ONE stream of %d lognormal "
+                                   "f64 + f64 weights, parallel k-bucket mode, sharded over %d GPU(s) by "
+                                   "contiguous ranges" % (n, world)
+                                   + ("; centroid all-gather + one-pass merge of the gathered records every step"
+                                      if world > 1 else ""),
+                       "values_per_step": n, "values_per_gpu_per_step": m, "compression": COMPRESSION,
+                       "l2": "inputs (16 B x %d = %.1f GB per GPU per step) far exceed the 126 MB L2" % (m, 16 * m / 1e9),
+                       "weights": "validated on the device in the same pass (deferred verdict, no host sync in a step)",
                        "centroids": nc, "digest_size": total_size},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "roofline": roofline, "roofline_unweighted": roofline_unweighted, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_pageable": e2e_pageable, "weak": weak, "other_configs": others,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(out)
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -81,6 +81,7 @@ _SIG = {
     "crick_tdigest_group_update": (c_int, [_P, _P, _P, c_double, _P, c_int64, c_int64, c_int, _P]),
     "crick_tdigest_group_flush": (c_int, [_P]),
     "crick_tdigest_group_merge_tree": (c_int, [_P, _P]),
+    "crick_tdigest_group_merge_all": (c_int, [_P, _P]),
     "crick_tdigest_group_quantile": (c_int, [_P, _P, c_int, _P, c_int, _P]),
     "crick_tdigest_group_cdf": (c_int, [_P, _P, c_int, _P, c_int, _P]),
     "crick_tdigest_group_meta": (c_int, [_P, _P]),

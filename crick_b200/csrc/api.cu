@@ -355,7 +355,8 @@ crick_tdigest_t* crick_tdigest_new(double compression) {
 
 void crick_tdigest_free(crick_tdigest_t* t) {
     if (!t) return;
-    if (t->last) cudaStreamSynchronize(t->last);
+    // (only streams this handle owns are touched: `last` may be a caller's stream that no longer
+    // exists; crick_device_free waits for the device before a block is reused or released)
     if (t->own) { cudaStreamSynchronize(t->own); cudaStreamDestroy(t->own); }
     if (t->ev) cudaEventDestroy(t->ev);
     if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
@@ -519,6 +520,7 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
             e = launch_parallel_update(t->s.v, 0, d, w ? d + cw : nullptr, wsc, n, t->scratch, sm_count(), st,
                                        bad_weights, sp1);
         if (e == cudaSuccess && stats && !(bad_weights && *bad_weights)) e = stats_fused_finish(stats, sm_count(), st);
+        if (stats) crick_stats_release_stream(stats, st);
         cudaFreeAsync(d, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);    // the caller may reuse x / w at once
         if (trace) fprintf(stderr, "crick host update n=%lld: one chunk, %.0f us\n", (long long)n, us(t0, now()));
@@ -626,6 +628,7 @@ static int td_update_host_parallel(crick_tdigest* t, const double* x, const doub
             if (e == cudaSuccess && stats) e = stats_fused_finish(stats, sm_count(), st);
         }
     }
+    if (stats) crick_stats_release_stream(stats, st);
     if (e != cudaSuccess) rc = fail("host-chunked parallel update", e);
     const auto t4 = now();
     // buffers are freed only after the work that reads them has finished
@@ -738,6 +741,7 @@ static int td_update(crick_tdigest_t* t, const double* x, const double* w, doubl
                                        bad_weights, sparts, defer_check);
         if (e == cudaSuccess && stats && !(bad_weights && *bad_weights))
             e = stats_fused_finish(stats, sm_count(), st);
+        if (stats) crick_stats_release_stream(stats, st);
         if (e == cudaSuccess) t->buf_clean = true;   // flushed above, and k_finalize leaves no buffer
     } else {
         e = launch_ingest(t->s.v, 1, x, w, w_scalar, 1, 1, nullptr, n, 0, nullptr, 0, st);
@@ -970,7 +974,6 @@ crick_tdigest_group_t* crick_tdigest_group_new(double compression, int64_t n_gro
 
 void crick_tdigest_group_free(crick_tdigest_group_t* g) {
     if (!g) return;
-    if (g->last) cudaStreamSynchronize(g->last);
     if (g->own) { cudaStreamSynchronize(g->own); cudaStreamDestroy(g->own); }
     if (g->ev) cudaEventDestroy(g->ev);
     store_free(g->s);
@@ -1048,6 +1051,55 @@ int crick_tdigest_group_merge_tree(crick_tdigest_group_t* g, crick_tdigest_t* ou
     if (e == cudaSuccess) e = launch_copy_digest(out->s.v, 0, g->s.v, 0, ost);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ost);
     return e == cudaSuccess ? 0 : fail("merge_tree copy", e);
+}
+
+// All digests of the group merged into `out` in ONE pass: their centroids are (mean, weight)
+// points -- exactly what tdigest_merge feeds to tdigest_add (:600-602) -- so the union goes through
+// the parallel k-bucket update (sample -> k-scale edges -> one streaming pass -> one greedy
+// compression) instead of 16 levels of dependent pairwise merges.  Not bit-identical with nested
+// merge() calls (that is crick_tdigest_group_merge_tree); same accuracy class.
+int crick_tdigest_group_merge_all(crick_tdigest_group_t* g, crick_tdigest_t* out) {
+    if (out->s.v.cap != g->s.v.cap || out->s.v.bufcap != g->s.v.bufcap)
+        return fail_msg("merge_all: output digest has a different compression");
+    cudaStream_t st = grp_stream(g, nullptr);
+    const long ng = g->s.nd;
+    cudaError_t e = launch_flush(g->s.v, 0, 1, ng, st);      // tdigest_merge flushes `other` (:595)
+    if (e == cudaSuccess) g->pend = 0;
+    long* off = nullptr;
+    double *mm = nullptr, *xw = nullptr;
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&off), (size_t)(ng + 1) * 8 + 64, st);
+    if (e != cudaSuccess) return fail("merge_all", e);
+    mm = reinterpret_cast<double*>(off + ng + 2);
+    e = launch_group_offsets(g->s.v, ng, off, mm, st);
+    long total = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, off + ng, sizeof(long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    int rc = 0;
+    if (e == cudaSuccess && total > 0) {
+        const long tw = (total + 1) & ~1L;                   // W stays 16-byte aligned
+        e = cudaMallocAsync(reinterpret_cast<void**>(&xw), (size_t)tw * 16, st);
+        if (e == cudaSuccess) e = launch_group_gather(g->s.v, ng, off, xw, xw + tw, st);
+        if (e == cudaSuccess) {
+            // `out` works on its own stream: order it behind the gather, and the frees behind it
+            cudaStream_t ost = td_stream(out, nullptr);
+            e = cudaEventRecord(g->ev, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ost, g->ev, 0);
+            if (e == cudaSuccess) {
+                // fewer points than the sampler wants: the reference's own sequential algorithm
+                rc = td_update(out, xw, xw + tw, 0.0, total, 1, 1,
+                               total >= CRICK_PARALLEL_MIN ? CRICK_MODE_PARALLEL : CRICK_MODE_REFERENCE,
+                               nullptr, nullptr, nullptr);
+                if (rc == 0) e = launch_widen_minmax(out->s.v, 0, mm, ost);
+                out->mirror_ok = false;
+                if (e == cudaSuccess) e = cudaEventRecord(out->ev, ost);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(st, out->ev, 0);
+            }
+        }
+    }
+    if (xw) cudaFreeAsync(xw, st);
+    cudaFreeAsync(off, st);
+    if (rc) return rc;
+    return e == cudaSuccess ? 0 : fail("merge_all", e);
 }
 
 static int grp_query(crick_tdigest_group* g, bool cdf, const double* in, int nq, double* out,

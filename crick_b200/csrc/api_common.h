@@ -26,3 +26,8 @@ int store_alloc(DigestStore& s, double compression, long nd);
 void store_free(DigestStore& s);
 
 }  // namespace crick
+
+// stats.cu: a call enqueued a SummaryStats handle's work on a stream that belongs to somebody
+// else (fused passes): order the handle's own stream behind it and forget the foreign stream
+struct crick_stats;
+int crick_stats_release_stream(crick_stats* s, void* stream);

@@ -42,6 +42,12 @@ cudaError_t launch_merge_records_bulk(const BatchView& v, long d, const double* 
 cudaError_t launch_copy_digest(const BatchView& dv, long dd, const BatchView& sv, long sd,
                                cudaStream_t st);
 cudaError_t launch_group_meta(const BatchView& v, long ng, double* out, cudaStream_t st);
+// all centroids of a (flushed) group as dense arrays: offsets[ng + 1] (exclusive scan of the
+// centroid counts), minmax[2] (over the non-empty digests), then X / W gathered
+cudaError_t launch_group_offsets(const BatchView& v, long ng, long* offsets, double* minmax, cudaStream_t st);
+cudaError_t launch_group_gather(const BatchView& v, long ng, const long* offsets, double* X, double* W,
+                                cudaStream_t st);
+cudaError_t launch_widen_minmax(const BatchView& v, long d, const double* minmax, cudaStream_t st);
 
 // ---- parallel k-bucket path (tdigest_parallel.cu)
 size_t parallel_scratch_bytes(double compression, int sm_count);

@@ -884,7 +884,8 @@ crick_spsv_t* crick_spsv_new(int64_t capacity) {
 
 void crick_spsv_free(crick_spsv_t* s) {
     if (!s) return;
-    if (s->last) cudaStreamSynchronize(s->last);
+    // (only streams this handle owns are touched: `last` may be a caller's stream that no longer
+    // exists; cudaFree below waits for the whole device before the memory goes away)
     if (s->own) { cudaStreamSynchronize(s->own); cudaStreamDestroy(s->own); }
     if (s->ev) cudaEventDestroy(s->ev);
     if (s->d) cudaFree(s->d);
@@ -961,11 +962,13 @@ int crick_spsv_update_stats(crick_spsv_t* s, crick_stats_t* stats, const int64_t
             e = sp_launch_update_hh(s, di, nullptr, n, st, &done, false, &fuse);
             if (e == cudaSuccess && done) e = stats_fused_finish(stats, fuse.used, st);
         }
+        crick_stats_release_stream(stats, st);
     }
     int rc = 0;
     if (e == cudaSuccess && !done) {
         // two passes (the device copy is reused, so host input crosses the bus once)
         rc = crick_stats_update(stats, di, item_is_f64 ? 0 : 1, nullptr, 1, n, 1, 0, st);
+        if (rc == 0) rc = crick_stats_release_stream(stats, st);     // `st` is this summary's stream, not theirs
         if (rc == 0) e = sp_launch_update(s, di, nullptr, 1, n, st, 0);
     }
     s->known_empty = false;

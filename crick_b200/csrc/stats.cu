@@ -369,9 +369,29 @@ int stats_fused_begin(crick_stats* s, cudaStream_t st, StatsPart** parts, int* n
 cudaError_t stats_fused_finish(crick_stats* s, int nused, cudaStream_t st) {
     count_launch();
     k_stats_final<<<1, 1024, 0, st>>>(s->d, s->parts, nused);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    // `st` belongs to ANOTHER handle (the digest's / the summary's own stream) and may be
+    // destroyed before this one: hand the ordering back to the stats handle's own stream now
+    // instead of remembering a stream that is not ours
+    if (e == cudaSuccess && st != s->own) {
+        e = cudaEventRecord(s->ev, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s->own, s->ev, 0);
+        s->last = s->own;
+    }
+    return e;
 }
 }  // namespace crick
+
+// a call enqueued this handle's work on a stream that belongs to somebody else: order the
+// handle's own stream behind it and forget the foreign stream
+int crick_stats_release_stream(crick_stats_t* s, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!st || st == s->own) return 0;
+    cudaError_t e = cudaEventRecord(s->ev, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->own, s->ev, 0);
+    s->last = s->own;
+    return e == cudaSuccess ? 0 : fail("stats release stream", e);
+}
 
 extern "C" {
 
@@ -401,7 +421,8 @@ crick_stats_t* crick_stats_new(void) {
 
 void crick_stats_free(crick_stats_t* s) {
     if (!s) return;
-    if (s->last) cudaStreamSynchronize(s->last);
+    // (only streams this handle owns are touched: `last` may be a caller's stream that no longer
+    // exists; cudaFree below waits for the whole device before the memory goes away)
     if (s->own) { cudaStreamSynchronize(s->own); cudaStreamDestroy(s->own); }
     if (s->ev) cudaEventDestroy(s->ev);
     if (s->d) cudaFree(s->d);

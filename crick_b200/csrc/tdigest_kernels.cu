@@ -378,8 +378,97 @@ __global__ void k_group_meta(BatchView v, long ng, double* out) {
     out[4 * g] = (double)h.n; out[4 * g + 1] = h.total; out[4 * g + 2] = h.vmin; out[4 * g + 3] = h.vmax;
 }
 
+// ---- all centroids of a group as two dense arrays (crick_tdigest_group_merge_all) -------------
+// offsets[g] = number of centroids in the digests before g (offsets[ng] = total); one CTA: every
+// thread sums a contiguous slice of the counts, one scan of the 1024 slice sums, slice written.
+__global__ void __launch_bounds__(1024) k_group_offsets(BatchView v, long ng, long* offsets,
+                                                        double* minmax_total) {
+    __shared__ long s_w[32];
+    __shared__ double s_mn[32], s_mx[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long per = (ng + 1023) / 1024;
+    const long g0 = tid * per, g1 = g0 + per < ng ? g0 + per : ng;
+    long run = 0;
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (long g = g0; g < g1; ++g) {
+        const DevHdr h = v.hdr[g];
+        run += h.n;
+        if (h.total != 0.0) { mn = fmin(mn, h.vmin); mx = fmax(mx, h.vmax); }   // empty ones are skipped (:596)
+    }
+    long inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long o = __shfl_up_sync(CRICK_FULL, inc, d);
+        if (lane >= d) inc += o;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { mn = fmin(mn, shfl_xor_d(mn, d)); mx = fmax(mx, shfl_xor_d(mx, d)); }
+    if (lane == 31) s_w[wid] = inc;
+    if (lane == 0) { s_mn[wid] = mn; s_mx[wid] = mx; }
+    __syncthreads();
+    long t = s_w[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long o = __shfl_up_sync(CRICK_FULL, t, d);
+        if (lane >= d) t += o;
+    }
+    long before = (wid > 0 ? __shfl_sync(CRICK_FULL, t, wid - 1) : 0) + inc - run;
+    for (long g = g0; g < g1; ++g) { offsets[g] = before; before += v.hdr[g].n; }
+    if (tid == 1023) offsets[ng] = __shfl_sync(CRICK_FULL, t, 31);
+    if (tid == 0) {
+        double a = DBL_MAX, b = -DBL_MAX;
+        for (int k = 0; k < 32; ++k) { a = fmin(a, s_mn[k]); b = fmax(b, s_mx[k]); }
+        minmax_total[0] = a; minmax_total[1] = b;
+    }
+}
+
+// one warp per digest: its centroids -> X[off ..), W[off ..)
+__global__ void __launch_bounds__(256) k_group_gather(BatchView v, long ng, const long* __restrict__ offsets,
+                                                      double* __restrict__ X, double* __restrict__ W) {
+    const int lane = lane_id();
+    const long g = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= ng) return;
+    const long off = offsets[g];
+    const int n = (int)(offsets[g + 1] - off);
+    const double2* c = v.cen + g * (long)v.cap;
+    for (int i = lane; i < n; i += 32) {
+        const double2 a = c[i];
+        X[off + i] = a.x;
+        W[off + i] = a.y;
+    }
+}
+
+// the merged digest's min / max are those of the inputs' (tdigest_merge :603-604), not of their
+// centroid means
+__global__ void k_widen_minmax(BatchView v, long d, const double* __restrict__ minmax) {
+    if (threadIdx.x || blockIdx.x) return;
+    DevHdr h = v.hdr[d];
+    if (minmax[0] <= minmax[1]) {
+        if (h.vmin > minmax[0]) h.vmin = minmax[0];
+        if (h.vmax < minmax[1]) h.vmax = minmax[1];
+        v.hdr[d] = h;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host-side launchers
+cudaError_t launch_group_offsets(const BatchView& v, long ng, long* offsets, double* minmax, cudaStream_t st) {
+    count_launch();
+    k_group_offsets<<<1, 1024, 0, st>>>(v, ng, offsets, minmax);
+    return cudaGetLastError();
+}
+cudaError_t launch_group_gather(const BatchView& v, long ng, const long* offsets, double* X, double* W,
+                                cudaStream_t st) {
+    count_launch();
+    k_group_gather<<<(unsigned)((ng + 7) / 8), 256, 0, st>>>(v, ng, offsets, X, W);
+    return cudaGetLastError();
+}
+cudaError_t launch_widen_minmax(const BatchView& v, long d, const double* minmax, cudaStream_t st) {
+    count_launch();
+    k_widen_minmax<<<1, 32, 0, st>>>(v, d, minmax);
+    return cudaGetLastError();
+}
+
 static int pick_wpc(int cap, int bufcap, int maxw, size_t* smem_out) {
     size_t wsb = warp_ws_bytes(cap, bufcap);
     size_t budget = 200 * 1024;

@@ -180,6 +180,12 @@ int crick_tdigest_group_flush(crick_tdigest_group_t *g);
 /* pairwise, level-by-level tree merge (left operand = self, right = other, exactly a nest of
  * tdigest_merge calls); the result lands in group 0 and is copied into `out` */
 int crick_tdigest_group_merge_tree(crick_tdigest_group_t *g, crick_tdigest_t *out);
+/* all digests of the group merged into `out` in ONE pass over their centroids: the centroids are
+ * the (mean, weight) points tdigest_merge feeds to tdigest_add (:600-602), taken through the
+ * parallel k-bucket update in one go.  Not bit-identical with nested merge() calls (use
+ * crick_tdigest_group_merge_tree for that), same accuracy class; 65536 digests in well under a
+ * millisecond instead of 16 dependent levels.  The group's digests are flushed, not consumed. */
+int crick_tdigest_group_merge_all(crick_tdigest_group_t *g, crick_tdigest_t *out);
 /* per-group queries: out[g*nq + j]; q on host or device per on_device */
 int crick_tdigest_group_quantile(crick_tdigest_group_t *g, const double *q, int nq, double *out,
                                  int on_device, void *stream);

@@ -407,6 +407,38 @@ def test_tree_merge_vs_nested_oracle_merges(cb, ngroups):
     assert tm.cdf(xs).tobytes() == ds[0].cdf(xs).tobytes()
 
 
+@pytest.mark.parametrize("ngroups,per,comp", [(3, 50, 100), (700, 1500, 200), (4096, 300, 100)])
+def test_merge_all_one_pass_vs_the_exact_tree(cb, ngroups, per, comp):
+    """TDigestGroup.merge_all: every centroid of every digest as a (mean, weight) point through
+    one parallel k-bucket update.  Not the reference's bits (merge_tree has those); checked like
+    SURVEY.md 8c prescribes for the parallel mode: exact min / max, total weight, and a rank error
+    at the 9 standard q's no worse than the bit-exact tree's (plus the reference tests' caps,
+    test_tdigest.py:399-405).  The group is left usable (flushed, not consumed)."""
+    rng = np.random.default_rng(ngroups)
+    v = rng.lognormal(size=(ngroups, per)) * np.linspace(0.5, 2.0, ngroups)[:, None]
+    g = cb.TDigestGroup(ngroups, comp)
+    g.update(v)
+    fast = g.merge_all()
+    again = g.merge_all()
+    assert fast.centroids().tobytes() == again.centroids().tobytes()     # deterministic, group intact
+    # merging INTO a digest that already holds data keeps it
+    t = cb.TDigest(comp)
+    t.update(np.full(1000, -5.0))
+    from crick_b200._lib import lib, check
+    check(lib.crick_tdigest_group_merge_all(g._h, t._h))
+    assert t.min() == -5.0 and t.max() == v.max() and abs(t.size() - (v.size + 1000)) <= 1e-9 * v.size
+    tree = g.merge_tree()                                                # (consumes the group)
+    assert fast.min() == v.min() == tree.min() and fast.max() == v.max() == tree.max()
+    assert abs(fast.size() - v.size) <= 1e-9 * v.size
+    assert len(fast.centroids()) <= 2 * int(np.ceil(comp))
+    flat = np.sort(v.ravel())
+    rank = lambda q: np.searchsorted(flat, q) / flat.size
+    ef = np.abs(rank(fast.quantile(QS9)) - QS9).max()
+    et = np.abs(rank(tree.quantile(QS9)) - QS9).max()
+    assert ef <= max(1.5 * et, 2e-3 if ngroups > 3 else 0.012), (ef, et)
+    assert (np.diff(fast.quantile(np.linspace(0, 1, 101))) >= 0).all()
+
+
 def test_large_query_batch_vs_oracle(cb):
     """Config-4 query shape: millions of device-resident queries, bit-exact vs the oracle, plus
     the size-independent properties (monotone, cdf(quantile(q)) ~ q)."""
