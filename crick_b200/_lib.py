@@ -102,6 +102,8 @@ _SIG = {
     "crick_stats_kurt": (c_double, [_P, c_int, c_int]),
     "crick_stats_export_record": (c_int, [_P, _P]),
     "crick_stats_merge_record": (c_int, [_P, _P]),
+    "crick_stats_export_record_dev": (c_int, [_P, _P, _P]),
+    "crick_stats_merge_records_dev": (c_int, [_P, _P, c_int, c_int64, _P]),
     # space saving
     "crick_spsv_new": (_P, [c_int64]),
     "crick_spsv_free": (None, [_P]),
@@ -110,9 +112,12 @@ _SIG = {
     "crick_spsv_update_stats": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "crick_spsv_merge": (c_int, [_P, _P, c_int]),
     "crick_spsv_set_state": (c_int, [_P, _P, c_int64]),
+    "crick_spsv_reset": (c_int, [_P, _P]),
+    "crick_stats_reset": (c_int, [_P, _P]),
     "crick_spsv_record_int64s": (c_int64, [_P]),
     "crick_spsv_export_record": (c_int, [_P, _P, _P]),
     "crick_spsv_merge_records": (c_int, [_P, _P, c_int, _P]),
+    "crick_spsv_merge_records_bulk": (c_int, [_P, _P, c_int, _P]),
     "crick_spsv_size": (c_int64, [_P]),
     "crick_spsv_capacity": (c_int64, [_P]),
     "crick_spsv_counters": (c_int64, [_P, _P, c_int64]),

@@ -94,6 +94,8 @@ struct crick_tdigest {
     DevHdr mirror;                   // host copy of the header
     bool mirror_ok = false;
     bool buf_clean = false;          // the insertion buffer is known to be empty (no flush needed)
+    bool lazy_reset = false;         // crick_tdigest_reset was asked for but not launched yet: the
+                                     // one-pass record merge takes the digest as empty by itself
     void* scratch = nullptr;         // parallel-mode scratch (lazy)
     size_t scratch_bytes = 0;
     // host-input path: copy stream and per-slot events, created once per handle (a stream and six
@@ -102,7 +104,7 @@ struct crick_tdigest {
     cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr};
 };
 
-static cudaStream_t td_stream(crick_tdigest* t, void* stream) {
+static cudaStream_t td_stream(crick_tdigest* t, void* stream, bool keep_lazy_reset = false) {
     // Chain work across streams: if this op runs on a different stream than the previous
     // one, make it wait for everything enqueued so far.
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : t->own;
@@ -111,6 +113,10 @@ static cudaStream_t td_stream(crick_tdigest* t, void* stream) {
         cudaStreamWaitEvent(st, t->ev, 0);
     }
     t->last = st;
+    if (t->lazy_reset && !keep_lazy_reset) {      // whoever comes next needs the reset header in memory
+        t->lazy_reset = false;
+        launch_init_hdr(t->s.v.hdr, 1, st);
+    }
     return st;
 }
 
@@ -870,13 +876,16 @@ int crick_tdigest_set_state(crick_tdigest_t* t, const double* centroids, int n, 
 }
 
 int crick_tdigest_reset(crick_tdigest_t* t, void* stream) {
-    cudaStream_t st = td_stream(t, stream);
+    td_stream(t, stream, true);
     t->px.clear();
     t->pw.clear();
     t->mirror_ok = false;
-    cudaError_t e = launch_init_hdr(t->s.v.hdr, 1, st);
-    t->buf_clean = e == cudaSuccess;      // an empty digest has an empty buffer
-    return e == cudaSuccess ? 0 : fail("reset", e);
+    // the header is rewritten by whatever touches the digest next (td_stream), or not at all when
+    // that is the one-pass record merge, which starts from an empty digest by itself: one launch
+    // less on the critical path of a multi-GPU step
+    t->lazy_reset = true;
+    t->buf_clean = true;                  // an empty digest has an empty buffer
+    return 0;
 }
 
 int crick_tdigest_debug_edges(crick_tdigest_t* t, double* out, int max_out) {
@@ -917,17 +926,20 @@ int crick_tdigest_merge_records(crick_tdigest_t* t, const double* records_dev, i
 
 int crick_tdigest_merge_records_bulk(crick_tdigest_t* t, const double* records_dev, int n_records,
                                      void* stream) {
-    cudaStream_t st = td_stream(t, stream);
+    const bool fresh = t->lazy_reset && t->px.empty();
+    cudaStream_t st = td_stream(t, stream, fresh);
     if (td_drain(t, st)) return -1;
     const bool clean = t->buf_clean;
     t->mirror_ok = false; t->buf_clean = false;
     cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
     if (e == cudaSuccess) {
-        e = launch_merge_records_bulk(t->s.v, 0, records_dev, n_records, st);
+        e = launch_merge_records_bulk(t->s.v, 0, records_dev, n_records, st, fresh);
         if (e == cudaErrorInvalidValue) {   // union too large for one CTA: sequential merge
             cudaGetLastError();
-            e = launch_merge_records(t->s.v, 0, records_dev, n_records, -1, st);
+            e = fresh ? launch_init_hdr(t->s.v.hdr, 1, st) : cudaSuccess;
+            if (e == cudaSuccess) e = launch_merge_records(t->s.v, 0, records_dev, n_records, -1, st);
         }
+        t->lazy_reset = false;
     }
     return e == cudaSuccess ? 0 : fail("merge_records_bulk", e);
 }

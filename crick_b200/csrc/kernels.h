@@ -37,8 +37,9 @@ cudaError_t launch_merge_records(const BatchView& v, long d, const double* recs,
                                  cudaStream_t st);
 // all records in one greedy pass over the sorted union (tdigest_parallel.cu);
 // cudaErrorInvalidValue = does not fit, use launch_merge_records
+// fresh: the digest is to be taken as empty whatever its memory holds (a reset that was not launched)
 cudaError_t launch_merge_records_bulk(const BatchView& v, long d, const double* recs, int nrec,
-                                      cudaStream_t st);
+                                      cudaStream_t st, bool fresh = false);
 cudaError_t launch_copy_digest(const BatchView& dv, long dd, const BatchView& sv, long sd,
                                cudaStream_t st);
 cudaError_t launch_group_meta(const BatchView& v, long ng, double* out, cudaStream_t st);

@@ -499,6 +499,158 @@ __global__ void __launch_bounds__(1024) k_spsv_from_record(unsigned char* tmp, l
     }
 }
 
+
+// inclusive scan of one int per thread over a 1024-thread CTA
+__device__ __forceinline__ int hh_block_scan_fwd(int v, int* s_w32) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(CRICK_FULL, v, d);
+        if (lane >= d) v += o;
+    }
+    __syncthreads();
+    if (lane == 31) s_w32[wid] = v;
+    __syncthreads();
+    int t = s_w32[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(CRICK_FULL, t, d);
+        if (lane >= d) t += o;
+    }
+    const int before = __shfl_sync(CRICK_FULL, t, wid > 0 ? wid - 1 : 0);
+    return wid > 0 ? v + before : v;
+}
+
+// ---- k-way merge of gathered records in ONE pass (multi-GPU tail, crick_spsv_merge_records_bulk) --
+// Cafaro et al.'s merge (spsv_merge, :289-364) for K summaries at once: an item monitored by
+// summary r contributes (count_r, error_r), one that is not contributes r's bound (m_r, m_r) with
+// m_r = r's smallest count if r is full, else 0; the `capacity` largest by (count desc, error asc)
+// are kept.  Same guarantees as K - 1 pairwise merges (count - error <= true <= count; everything
+// dropped is bounded by the smallest kept count) without their K - 1 dependent single-warp list
+// walks: sort the <= K * capacity entries by item, reduce equal items, sort by count.  One CTA.
+// Not the list order nested merge() calls would produce: crick_spsv_merge_records keeps that.
+__device__ __forceinline__ void spsv_bitonic(long long* k1, long long* k2, int* id, int P) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int q = i | j;
+                const bool up = (i & k) == 0;
+                const bool q_first = k1[q] < k1[i] || (k1[q] == k1[i] && (k2[q] < k2[i] || (k2[q] == k2[i] && id[q] < id[i])));
+                if (q_first == up) {
+                    long long a = k1[i]; k1[i] = k1[q]; k1[q] = a;
+                    a = k2[i]; k2[i] = k2[q]; k2[q] = a;
+                    int b = id[i]; id[i] = id[q]; id[q] = b;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_spsv_merge_bulk(unsigned char* state, long cap, int hcap,
+                                                          const long long* __restrict__ recs, int nrec,
+                                                          long rec_len, int P, long long* scratch) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    long long* k1 = reinterpret_cast<long long*>(sm);      // [P]
+    long long* k2 = k1 + P;                                 // [P]
+    int* id = reinterpret_cast<int*>(k2 + P);               // [P]
+    __shared__ int s_off[65];
+    __shared__ long long s_m[64];
+    __shared__ long long s_M, s_seen;
+    __shared__ int s_w32[32];
+    __shared__ int s_D;
+    const int tid = threadIdx.x;
+    // scratch: agg_item[P] | agg_count[P] | agg_error[P]
+    long long* a_item = scratch;
+    long long* a_cnt = scratch + P;
+    long long* a_err = scratch + 2 * (size_t)P;
+    if (tid == 0) {
+        int run = 0;
+        long long M = 0, seen = 0;
+        for (int r = 0; r < nrec; ++r) {
+            const long long* rec = recs + (size_t)r * rec_len;
+            long n = rec[0];
+            n = n < 0 ? 0 : (n > cap ? cap : n);
+            s_off[r] = run;
+            run += (int)n;
+            s_m[r] = n == cap ? rec[2 + 3 * (n - 1) + 1] : 0;     // count of the last (smallest) counter
+            M += s_m[r];
+            seen += n;
+        }
+        s_off[nrec] = run;
+        s_M = M; s_seen = seen;
+    }
+    __syncthreads();
+    const int T = s_off[nrec];
+    for (int i = tid; i < P; i += blockDim.x) { k1[i] = 0x7fffffffffffffffll; k2[i] = 0x7fffffffffffffffll; id[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int r = 0; r < nrec; ++r) {
+        const long long* rec = recs + (size_t)r * rec_len;
+        const int n = s_off[r + 1] - s_off[r];
+        for (int i = tid; i < n; i += blockDim.x) {
+            k1[s_off[r] + i] = rec[2 + 3 * i];               // item
+            k2[s_off[r] + i] = r;                            // record (ties keep rank order)
+            id[s_off[r] + i] = s_off[r] + i;                 // entry (its record and slot follow from s_off)
+        }
+    }
+    __syncthreads();
+    spsv_bitonic(k1, k2, id, P);
+    // heads of equal-item runs -> aggregated (count, error); padding sorts last (id = INT_MAX)
+    int run_total = 0;
+    for (int base = 0; base < P; base += blockDim.x) {
+        const int i = base + tid;
+        const bool valid = i < P && id[i] != 0x7fffffff;
+        const bool head = valid && (i == 0 || k1[i - 1] != k1[i] || id[i - 1] == 0x7fffffff);
+        const int incl = hh_block_scan_fwd(head ? 1 : 0, s_w32);
+        if (head) {
+            long long cnt = 0, err = 0, bound = 0;
+            for (int j = i; j < P && id[j] != 0x7fffffff && k1[j] == k1[i]; ++j) {
+                const int r = (int)k2[j];
+                const long long* rec = recs + (size_t)r * rec_len;
+                const int slot = id[j] - s_off[r];
+                cnt += rec[2 + 3 * slot + 1];
+                err += rec[2 + 3 * slot + 2];
+                bound += s_m[r];
+            }
+            const long long rest = s_M - bound;              // the summaries that do not monitor it
+            const int at = run_total + incl - 1;
+            a_item[at] = k1[i]; a_cnt[at] = cnt + rest; a_err[at] = err + rest;
+        }
+        if (tid == (int)blockDim.x - 1) s_D = run_total + incl;
+        __syncthreads();
+        run_total = s_D;
+        __syncthreads();
+    }
+    const int D = run_total;
+    for (int i = tid; i < P; i += blockDim.x) {
+        k1[i] = i < D ? -a_cnt[i] : 0x7fffffffffffffffll;    // count descending
+        k2[i] = i < D ? a_err[i] : 0x7fffffffffffffffll;     // error ascending
+        id[i] = i < D ? i : 0x7fffffff;                      // item ascending (a_item is sorted)
+    }
+    __syncthreads();
+    spsv_bitonic(k1, k2, id, P);
+    const int K = D < (int)cap ? D : (int)cap;
+    SpsvView g = spsv_carve(state, cap, hcap);
+    for (int i = tid; i < hcap; i += blockDim.x) g.hval[i] = -1;
+    __syncthreads();
+    for (int i = tid; i < K; i += blockDim.x) {
+        const int a = id[i];
+        const long long key = a_item[a];
+        g.item[i] = key; g.count[i] = a_cnt[a]; g.error[i] = a_err[a]; g.last[i] = i;
+        g.order[i] = i; g.pos[i] = i;
+        unsigned idx = hash64(key) & (unsigned)(hcap - 1);
+        for (;;) {
+            if (atomicCAS(&g.hval[idx], -1, i) == -1) { g.hkey[idx] = key; break; }
+            idx = (idx + 1) & (unsigned)(hcap - 1);
+        }
+    }
+    if (tid == 0) {
+        SpsvHdr h; h.capacity = cap; h.size = K; h.hcap = hcap; h.tomb = 0;
+        h.seen = s_seen; h.mixed = 1; h.pad = 0;
+        *g.hdr = h;
+    }
+}
 }  // namespace crick
 
 #include "spsv_hh.cuh"
@@ -882,6 +1034,20 @@ crick_spsv_t* crick_spsv_new(int64_t capacity) {
     return s;
 }
 
+// back to the state spsv_new leaves, without releasing anything (asynchronous on `stream`): lets
+// a multi-GPU reduction reuse one output summary per step
+int crick_spsv_reset(crick_spsv_t* s, void* stream) {
+    cudaStream_t st = sp_stream(s, stream);
+    s->pi.clear(); s->pc.clear();
+    count_launch();
+    k_spsv_init<<<1, 256, 0, st>>>(s->d, s->cap, s->hcap, 0);
+    cudaError_t e = cudaGetLastError();
+    s->size_mirror = 0;
+    s->mirror_ok = e == cudaSuccess;
+    s->known_empty = e == cudaSuccess;
+    return e == cudaSuccess ? 0 : fail("spsv_reset", e);
+}
+
 void crick_spsv_free(crick_spsv_t* s) {
     if (!s) return;
     // (only streams this handle owns are touched: `last` may be a caller's stream that no longer
@@ -1041,6 +1207,42 @@ int crick_spsv_merge_records(crick_spsv_t* s, const int64_t* dev_recs, int n_rec
     }
     cudaFreeAsync(tmp, st);
     return e == cudaSuccess ? 0 : fail("spsv_merge_records", e);
+}
+
+int crick_spsv_merge_records_bulk(crick_spsv_t* s, const int64_t* dev_recs, int n_records, void* stream) {
+    if (n_records <= 0) return 0;
+    const int64_t nd = 2 + 3 * (int64_t)s->cap;
+    const bool with_self = !s->known_empty || !s->pi.empty();
+    const int K = n_records + (with_self ? 1 : 0);
+    int P = 1;
+    while (P < K * s->cap) P <<= 1;
+    const size_t smem = (size_t)P * 20;
+    if (K > 64 || smem > 200 * 1024)                       // too many entries for one CTA's sort
+        return crick_spsv_merge_records(s, dev_recs, n_records, stream);
+    cudaStream_t st = sp_stream(s, stream);
+    if (sp_drain(s, st)) return -1;
+    s->mirror_ok = false; s->known_empty = false;
+    long long* ws = nullptr;                               // [own record + copies] | scratch 3 P
+    const size_t recs_bytes = with_self ? (size_t)K * nd * 8 : 0;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), recs_bytes + (size_t)3 * P * 8, st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(spsv bulk merge)", e);
+    const long long* recs = reinterpret_cast<const long long*>(dev_recs);
+    if (with_self) {                                       // the handle's own summary goes first
+        count_launch();
+        k_spsv_export<<<8, 256, 0, st>>>(s->d, s->cap, s->hcap, ws);
+        e = cudaMemcpyAsync(ws + nd, dev_recs, (size_t)n_records * nd * 8, cudaMemcpyDeviceToDevice, st);
+        recs = ws;
+    }
+    if (e == cudaSuccess && smem > 48 * 1024)
+        e = cudaFuncSetAttribute(k_spsv_merge_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        count_launch();
+        k_spsv_merge_bulk<<<1, 1024, smem, st>>>(s->d, s->cap, s->hcap, recs, K, (long)nd, P,
+                                                 ws + recs_bytes / 8);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, st);
+    return e == cudaSuccess ? 0 : fail("spsv_merge_records_bulk", e);
 }
 
 int crick_spsv_set_state(crick_spsv_t* s, const int64_t* counters3, int64_t n) {

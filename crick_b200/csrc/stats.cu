@@ -282,6 +282,34 @@ __global__ void k_stats_merge(StatsState* dst, const StatsState* src) {
 
 using namespace crick;
 
+namespace crick {
+// 9-double wire record on the device: export, and merge of n records in order
+__global__ void k_stats_reset(StatsState* st) {
+    if (threadIdx.x) return;
+    StatsState f;
+    stats_fresh(f);
+    *st = f;
+}
+__global__ void k_stats_export(const StatsState* st, double* r) {
+    if (threadIdx.x) return;
+    const StatsState m = *st;
+    r[0] = (double)m.count; r[1] = m.sum; r[2] = m.vmin; r[3] = m.vmax; r[4] = m.m2; r[5] = m.m3;
+    r[6] = m.m4; r[7] = (double)m.homogeneous; r[8] = m.first_value;
+}
+__global__ void k_stats_merge_records(StatsState* st, const double* __restrict__ recs, int n, long stride) {
+    if (threadIdx.x) return;
+    StatsState T = *st;
+    for (int k = 0; k < n; ++k) {
+        const double* r = recs + (size_t)k * stride;
+        StatsState o;
+        o.count = (long long)r[0]; o.sum = r[1]; o.vmin = r[2]; o.vmax = r[3]; o.m2 = r[4]; o.m3 = r[5];
+        o.m4 = r[6]; o.homogeneous = r[7] != 0.0; o.first_value = r[8]; o.pad = 0;
+        stats_merge_state(T, o);
+    }
+    *st = T;
+}
+}  // namespace crick
+
 struct crick_stats {
     StatsState* d = nullptr;
     StatsPart* parts = nullptr;
@@ -565,6 +593,38 @@ int crick_stats_export_record(crick_stats_t* s, double* r) {
     r[0] = (double)m.count; r[1] = m.sum; r[2] = m.vmin; r[3] = m.vmax; r[4] = m.m2; r[5] = m.m3;
     r[6] = m.m4; r[7] = (double)m.homogeneous; r[8] = m.first_value;
     return 0;
+}
+
+// back to the state stats_new leaves (:25-39), asynchronous on `stream`
+int crick_stats_reset(crick_stats_t* s, void* stream) {
+    cudaStream_t st = ss_stream(s, stream);
+    s->px.clear(); s->pc.clear();
+    count_launch();
+    k_stats_reset<<<1, 32, 0, st>>>(s->d);
+    cudaError_t e = cudaGetLastError();
+    stats_fresh(s->mirror);
+    s->mirror_ok = e == cudaSuccess;
+    return e == cudaSuccess ? 0 : fail("stats_reset", e);
+}
+
+int crick_stats_export_record_dev(crick_stats_t* s, double* dev, void* stream) {
+    cudaStream_t st = ss_stream(s, stream);
+    if (ss_drain(s, st)) return -1;
+    count_launch();
+    k_stats_export<<<1, 32, 0, st>>>(s->d, dev);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail("stats_export_record_dev", e);
+}
+
+int crick_stats_merge_records_dev(crick_stats_t* s, const double* recs, int n, int64_t stride, void* stream) {
+    if (n <= 0) return 0;
+    cudaStream_t st = ss_stream(s, stream);
+    if (ss_drain(s, st)) return -1;
+    s->mirror_ok = false;
+    count_launch();
+    k_stats_merge_records<<<1, 32, 0, st>>>(s->d, recs, n, (long)stride);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail("stats_merge_records_dev", e);
 }
 
 int crick_stats_merge_record(crick_stats_t* s, const double* r) {

@@ -1614,6 +1614,10 @@ k_bin_accumulate2(const double* __restrict__ X, const double* __restrict__ W, do
 //
 // s_bt != nullptr: h.total does not yet include the new items; their weights are summed
 // sequentially in ws.sb order (by another thread, next to the cumulative sum) and added first.
+// SEQ_SUM = false (the one-pass merge of gathered records, which promises no reference bits): the
+// cumulative weights come from a block scan (fixed association: deterministic) instead of the
+// single-thread fl chain -- 1000 dependent DADDs are 9 us of a 30 us kernel.
+template <bool SEQ_SUM = true>
 __device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp, Hdr& h, int m,
                                                    int cap, int* s_nc, double* s_bt) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1657,7 +1661,23 @@ __device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp
     }
     __syncthreads();
     // ---- phase 3: cumulative weights (into kend), then k-scale per item
-    if (tid == 0) serial_cumsum(ws.items, ws.kend, T);
+    if (SEQ_SUM) {
+        if (tid == 0) serial_cumsum(ws.items, ws.kend, T);
+    } else {
+        __shared__ double s_scan_d[32];
+        __shared__ double s_carry;
+        if (tid == 0) s_carry = 0.0;
+        __syncthreads();
+        for (int base = 0; base < T; base += blockDim.x) {
+            const int i = base + tid;
+            const double incl = block_scan_incl<double>(i < T ? ws.items[i].y : 0.0, s_scan_d);
+            const double carry = s_carry;
+            if (i < T) ws.kend[i] = carry + incl;
+            __syncthreads();
+            if (tid == (int)blockDim.x - 1) s_carry = carry + incl;
+            __syncthreads();
+        }
+    }
     if (s_bt != nullptr && tid == 32) {
         double bt = 0.0;
         int i = 0;
@@ -1938,7 +1958,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
 // path of every multi-GPU step.  One CTA; P = power of two >= total centroid count.
 __global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d,
                                                              const double* __restrict__ recs,
-                                                             int nrec, int rec_doubles, int P) {
+                                                             int nrec, int rec_doubles, int P, int fresh) {
     __shared__ int s_off[64 + 1];
     __shared__ double s_tot, s_mn, s_mx;
     const int tid = threadIdx.x;
@@ -1976,8 +1996,11 @@ __global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d
     }
     __syncthreads();
     const int m = s_off[nrec];
-    for (int i = tid; i < P; i += blockDim.x) { key[i] = INFINITY; wgt[i] = 0.0; ord[i] = 0x7fffffff; }
-    __syncthreads();
+    const bool by_rank = nrec <= 16;             // the records are sorted runs: rank them against each other
+    if (!by_rank) {
+        for (int i = tid; i < P; i += blockDim.x) { key[i] = INFINITY; wgt[i] = 0.0; ord[i] = 0x7fffffff; }
+        __syncthreads();
+    }
     for (int r = 0; r < nrec; ++r) {
         const double* rec = recs + (size_t)r * rec_doubles;
         const int n = s_off[r + 1] - s_off[r];
@@ -1988,35 +2011,62 @@ __global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d
         }
     }
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < P / 2; t += blockDim.x) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int q = i | j;
-                bool up = (i & k) == 0;
-                bool q_first = key[q] < key[i] || (key[q] == key[i] && ord[q] < ord[i]);
-                if (q_first == up) {
-                    double t1 = key[i]; key[i] = key[q]; key[q] = t1;
-                    t1 = wgt[i]; wgt[i] = wgt[q]; wgt[q] = t1;
-                    int t2 = ord[i]; ord[i] = ord[q]; ord[q] = t2;
-                }
+    if (by_rank) {
+        // position of element (r, i) in the sorted union = i + #(elements of earlier records <= key)
+        // + #(elements of later records < key): ties keep record order, like the bitonic path's
+        // (key, ord) comparison.  A centroid array is sorted by mean (tdigest_flush), so each count
+        // is one binary search in shared memory.
+        for (int e = tid; e < m; e += blockDim.x) {
+            int r = 0;
+            while (s_off[r + 1] <= e) ++r;
+            const double k = key[e];
+            int rank = e - s_off[r];
+            for (int q = 0; q < nrec; ++q) {
+                if (q == r) continue;
+                int lo = s_off[q], hi = s_off[q + 1];
+                if (q < r) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] <= k) lo = mid + 1; else hi = mid; } }
+                else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < k) lo = mid + 1; else hi = mid; } }
+                rank += lo - s_off[q];
             }
-            __syncthreads();
+            ws.sb[rank] = make_double2(k, wgt[e]);
         }
+    } else {
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < P / 2; t += blockDim.x) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    int q = i | j;
+                    bool up = (i & k) == 0;
+                    bool q_first = key[q] < key[i] || (key[q] == key[i] && ord[q] < ord[i]);
+                    if (q_first == up) {
+                        double t1 = key[i]; key[i] = key[q]; key[q] = t1;
+                        t1 = wgt[i]; wgt[i] = wgt[q]; wgt[q] = t1;
+                        int t2 = ord[i]; ord[i] = ord[q]; ord[q] = t2;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < m; i += blockDim.x) ws.sb[i] = make_double2(key[i], wgt[i]);
     }
-    for (int i = tid; i < m; i += blockDim.x) ws.sb[i] = make_double2(key[i], wgt[i]);
     __syncthreads();
     if (m > 0) {                                  // uniform
         __shared__ int s_nc;
         Hdr h;
-        const DevHdr dh = v.hdr[d];
+        DevHdr dh;
+        if (fresh) {                              // the state tdigest_new leaves (:63-92): no reset launch
+            dh.vmin = DBL_MAX; dh.vmax = -DBL_MAX; dh.total = 0.0; dh.btotal = 0.0;
+            dh.n = 0; dh.bn = 0; dh.pad0 = 0; dh.pad1 = 0;
+        } else {
+            dh = v.hdr[d];
+        }
         h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
         const double2* cg = v.cen + d * (long)cap;
         for (int i = tid; i < h.n; i += blockDim.x) ws.cen[i] = cg[i];
         if (h.vmin > s_mn) h.vmin = s_mn;
         if (h.vmax < s_mx) h.vmax = s_mx;
         h.total = __dadd_rn(h.total, s_tot);
-        block_merge_sorted(ws, v.comp, h, m, cap, &s_nc, nullptr);   // starts with a barrier
+        block_merge_sorted<false>(ws, v.comp, h, m, cap, &s_nc, nullptr);   // starts with a barrier
         double2* cgo = v.cen + d * (long)cap;
         for (int i = tid; i < h.n; i += blockDim.x) cgo[i] = ws.cen[i];
         if (tid == 0) {
@@ -2025,25 +2075,28 @@ __global__ void __launch_bounds__(1024) k_merge_records_bulk(BatchView v, long d
             o.n = h.n; o.bn = 0;
             v.hdr[d] = o;
         }
+    } else if (fresh && tid == 0) {
+        DevHdr o;
+        o.vmin = DBL_MAX; o.vmax = -DBL_MAX; o.total = 0.0; o.btotal = 0.0; o.n = 0; o.bn = 0; o.pad0 = 0; o.pad1 = 0;
+        v.hdr[d] = o;
     }
 }
 
 // returns cudaErrorInvalidValue when the union does not fit one CTA's shared memory (the
 // caller then uses the sequential k_merge_records)
 cudaError_t launch_merge_records_bulk(const BatchView& v, long d, const double* recs, int nrec,
-                                      cudaStream_t st) {
-    if (nrec <= 0) return cudaSuccess;
+                                      cudaStream_t st, bool fresh) {
+    if (nrec <= 0) return fresh ? launch_init_hdr(v.hdr + d, 1, st) : cudaSuccess;
     if (nrec > 64) return cudaErrorInvalidValue;
     int P = 1;
     while (P < nrec * v.cap + 2) P <<= 1;   // (+2: block_merge_sorted keeps 2 (T + 1) ints in ws.sb)
     size_t t = (size_t)v.cap + P;
     size_t smem = (size_t)P * 20 + 16 + (size_t)v.cap * 16 + (size_t)P * 16 + t * 16 + t * 8 + (t + 1) * 4 + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_merge_records_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = need_smem(k_merge_records_bulk, smem);
     if (e != cudaSuccess) return e;
     count_launch();
-    k_merge_records_bulk<<<1, 1024, smem, st>>>(v, d, recs, nrec, 4 + 2 * v.cap, P);
+    k_merge_records_bulk<<<1, 1024, smem, st>>>(v, d, recs, nrec, 4 + 2 * v.cap, P, fresh ? 1 : 0);
     return cudaGetLastError();
 }
 

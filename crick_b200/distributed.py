@@ -163,6 +163,56 @@ def allgather_merge_spsv(sp, group=None):
     return out
 
 
+class SketchAllReduce:
+    """SpaceSaving + SummaryStats of every rank reduced in one exchange (BASELINE config 5): the
+    summary record ``[size, 0, (item, count, error) x capacity]`` and the 9-double moments record
+    travel as ONE int64 buffer per rank, one all-gather, then both merges on the device on the same
+    stream -- no allocation, no host synchronisation.  ``exact=True``: SpaceSaving records are
+    merged one after the other like ``SpaceSaving.merge(rank0, rank1, ...)`` (bit for bit);
+    ``exact=False``: the k-way form of the same merge in one kernel."""
+
+    def __init__(self, capacity, dtype="i8", group=None, exact=False):
+        import torch
+        import torch.distributed as dist
+        from .space_saving import SpaceSaving
+
+        self.group, self.exact = group, exact
+        self.world = dist.get_world_size(group)
+        self.summary = SpaceSaving(capacity, dtype)
+        self.stats = SummaryStats()
+        self.nd = self.summary.record_int64s()
+        self.rec = torch.zeros(self.nd + 9, dtype=torch.int64, device="cuda")
+        self.gathered = torch.empty((self.world, self.nd + 9), dtype=torch.int64, device="cuda")
+
+    def __call__(self, summary, stats=None):
+        """Returns (merged SpaceSaving, merged SummaryStats or None), both reused by the next call.
+        Enqueued on torch's current stream (not the legacy default stream)."""
+        import torch
+        import torch.distributed as dist
+
+        st = torch.cuda.current_stream().cuda_stream
+        if st == 0:
+            raise RuntimeError("run the reduction under `with torch.cuda.stream(s)`")
+        summary.export_record(self.rec.data_ptr(), stream=st)
+        if stats is not None:
+            stats.export_record_device(self.rec.data_ptr() + 8 * self.nd, stream=st)
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.rec, group=self.group)
+        self.summary.clear(stream=st)
+        row = self.nd + 9
+        # the records are `row` int64 apart and the merges take a contiguous block of summary
+        # records: compact them first (one strided device copy)
+        if not hasattr(self, "_dense"):
+            self._dense = torch.empty((self.world, self.nd), dtype=torch.int64, device="cuda")
+        self._dense.copy_(self.gathered[:, :self.nd])
+        self.summary.merge_records(self._dense.data_ptr(), self.world, stream=st, bulk=not self.exact)
+        if stats is not None:
+            self.stats.clear(stream=st)
+            self.stats.merge_records_device(self.gathered.data_ptr() + 8 * self.nd, self.world, stride=row,
+                                            stream=st)
+            return self.summary, self.stats
+        return self.summary, None
+
+
 def allgather_merge_stats(stats, group=None, backend_device="cuda"):
     """All-gather the 9-double SummaryStats records and merge them in rank order."""
     import torch

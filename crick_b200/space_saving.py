@@ -321,11 +321,19 @@ class SpaceSaving:
     def export_record(self, device_ptr, stream=None):
         check(lib.crick_spsv_export_record(self._h, device_ptr, stream), "export_record")
 
-    def merge_records(self, device_ptr, n_records, stream=None):
+    def merge_records(self, device_ptr, n_records, stream=None, bulk=False):
         """Merge `n_records` records (same capacity, device memory) one after the other, each
-        exactly like ``self.merge(other)``."""
-        check(lib.crick_spsv_merge_records(self._h, device_ptr, int(n_records), stream),
-              "merge_records")
+        exactly like ``self.merge(other)``.  ``bulk=True``: the k-way form of the same merge in
+        one kernel -- same guarantees, not the list order nested merges would leave."""
+        fn = lib.crick_spsv_merge_records_bulk if bulk else lib.crick_spsv_merge_records
+        check(fn(self._h, device_ptr, int(n_records), stream), "merge_records")
+
+    def clear(self, stream=None):
+        """Empty the summary in place (the state ``SpaceSaving(capacity, dtype)`` starts with)."""
+        if self._obj is not None:
+            self._obj = ObjectSummary(self._obj.capacity)
+            return
+        check(lib.crick_spsv_reset(self._h, stream), "clear")
 
 
 SpaceSaving.__module__ = "crick.space_saving"

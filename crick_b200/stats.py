@@ -169,6 +169,20 @@ class SummaryStats:
         """The kurtosis (Fisher by default, Pearson with ``fisher=False``)."""
         return lib.crick_stats_kurt(self._h, int(bool(fisher)), int(bool(bias)))
 
+    def clear(self, stream=None):
+        """Empty the summary in place (the state ``SummaryStats()`` starts with)."""
+        check(lib.crick_stats_reset(self._h, stream), "clear")
+
+    def export_record_device(self, device_ptr, stream=None):
+        """The 9-double record written to device memory, asynchronously on `stream`."""
+        check(lib.crick_stats_export_record_dev(self._h, device_ptr, stream), "export_record")
+
+    def merge_records_device(self, device_ptr, n_records, stride=9, stream=None):
+        """``self.merge(*records)`` in order for 9-double records in device memory, `stride`
+        doubles apart; asynchronous on `stream`."""
+        check(lib.crick_stats_merge_records_dev(self._h, device_ptr, int(n_records), int(stride), stream),
+              "merge_records")
+
     # ---- multi-GPU wire format: 9 doubles (SURVEY.md 8e) ----
     def export_record(self):
         r = np.empty(9, dtype=np.float64)

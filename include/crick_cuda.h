@@ -224,6 +224,11 @@ double crick_stats_kurt(crick_stats_t *s, int fisher, int bias); /* :126-136 */
 /* 9-double wire record for all-gather: count, sum, min, max, m2, m3, m4, homogeneous, first */
 int crick_stats_export_record(crick_stats_t *s, double *record9_host);
 int crick_stats_merge_record(crick_stats_t *s, const double *record9_host);
+/* the same on the device, asynchronous on `stream`: export into a device buffer, merge
+ * `n_records` records (`stride` doubles apart, in order) with stats_merge :78-90 each */
+int crick_stats_export_record_dev(crick_stats_t *s, double *record9_dev, void *stream);
+int crick_stats_merge_records_dev(crick_stats_t *s, const double *records_dev, int n_records,
+                                  int64_t stride, void *stream);
 
 /* ---- SpaceSaving, int64 / float64-bit-pattern items (space_saving_stubs.c.in) ---- */
 crick_spsv_t *crick_spsv_new(int64_t capacity);                  /* spsv_int64_new :75-95 */
@@ -263,9 +268,17 @@ int crick_spsv_set_state(crick_spsv_t *s, const int64_t *counters3, int64_t n); 
  * crick_spsv_record_int64s() values); merge_records folds `n_records` such records -- all of this
  * handle's capacity -- into the handle one after the other, each exactly like
  * spsv_merge(self, other) :289-364 would.  Asynchronous on `stream`. */
+/* back to the state spsv_new / stats_new leave, without releasing anything (asynchronous on `stream`) */
+int crick_spsv_reset(crick_spsv_t *s, void *stream);
+int crick_stats_reset(crick_stats_t *s, void *stream);
 int64_t crick_spsv_record_int64s(crick_spsv_t *s);
 int crick_spsv_export_record(crick_spsv_t *s, int64_t *dev_out, void *stream);
 int crick_spsv_merge_records(crick_spsv_t *s, const int64_t *dev_records, int n_records, void *stream);
+/* The same records merged in ONE pass (the k-way form of :289-364: an item a summary does not monitor
+ * contributes that summary's smallest count to count and error; the `capacity` largest are kept):
+ * the guarantees of nested merges without their list order, one kernel instead of n_records
+ * dependent single-warp merges (8 x 1000 counters: ~0.1 ms instead of ~9 ms). */
+int crick_spsv_merge_records_bulk(crick_spsv_t *s, const int64_t *dev_records, int n_records, void *stream);
 int64_t crick_spsv_size(crick_spsv_t *s);
 int64_t crick_spsv_capacity(crick_spsv_t *s);
 /* int64_counters walk, space_saving.pyx:368-386: out = k x (item, count, error); returns rows */

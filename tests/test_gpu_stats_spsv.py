@@ -444,6 +444,85 @@ def test_spsv_records_merge_like_the_reference(cb):
                               np.stack([refs[0].counters()[f] for f in ("item", "count", "error")], 1))
 
 
+def test_spsv_bulk_merge_of_records_and_device_stats_records(cb):
+    """Multi-GPU tail on one GPU: 8 shard summaries -> 8 records -> merged (a) one after the other
+    (the reference's spsv_merge, bit for bit) and (b) by the k-way form in one kernel.  (b) must be
+    a valid summary of the union with the same guarantees, and when every distinct item fits the
+    capacity both hold the exact counts.  SummaryStats records merged on the device == merge()."""
+    rng = np.random.default_rng(77)
+    n, cap = 1600000, 1000
+    for distinct in (600, 50000):
+        items = (rng.zipf(1.2, n) % distinct).astype(np.int64) * 977 + 5
+        parts, sts = [], []
+        nd = cb.SpaceSaving(cap, "i8").record_int64s()
+        recs = cb.DeviceArray((8, nd), "i8")
+        srec = cb.DeviceArray((8, 9))
+        for k in range(8):
+            sl = items[k * n // 8:(k + 1) * n // 8]
+            p, st = cb.SpaceSaving(cap, "i8"), cb.SummaryStats()
+            p.update(sl, stats=st)
+            p.export_record(recs.ptr + 8 * nd * k)
+            st.export_record_device(srec.ptr + 72 * k)
+            parts.append(p); sts.append(st)
+        from crick_b200._lib import lib
+        lib.crick_device_synchronize()
+        exact, bulk = cb.SpaceSaving(cap, "i8"), cb.SpaceSaving(cap, "i8")
+        exact.merge_records(recs.ptr, 8)
+        bulk.merge_records(recs.ptr, 8, bulk=True)
+        via = cb.SpaceSaving(cap, "i8")
+        via.merge(*parts)
+        assert exact.counters().tobytes() == via.counters().tobytes()
+        cb_ = bulk.counters()
+        true = _assert_valid_summary(cb_, items, cap)
+        if distinct <= cap:
+            got = {it: (cn, er) for it, cn, er in cb_.tolist()}
+            assert all(got[it] == (c, 0) for it, c in true.items())
+            assert sorted(exact.counters().tolist()) == sorted(cb_.tolist())
+        # on top of a summary that already holds data: still valid for the union
+        bulk.merge_records(recs.ptr, 4, bulk=True)
+        _assert_valid_summary(bulk.counters(), np.concatenate([items, items[: n // 2]]), cap)
+        bulk.clear()
+        assert bulk.size() == 0
+        bulk.merge_records(recs.ptr, 8, bulk=True)
+        assert bulk.counters().tobytes() == cb_.tobytes()
+        # moments: device records merged in order == merge(*stats)
+        a, b = cb.SummaryStats(), cb.SummaryStats()
+        a.merge_records_device(srec.ptr, 8)
+        b.merge(*sts)
+        assert a.__getstate__() == b.__getstate__()
+        a.clear()
+        assert a.count() == 0 and np.isnan(a.mean())
+
+
+def test_sketch_allreduce_world1_nccl(cb):
+    """SketchAllReduce (one all-gather for summary + moments) on a 1-rank NCCL group."""
+    import torch
+    import torch.distributed as dist
+    from crick_b200.distributed import SketchAllReduce
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29541", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        rng = np.random.default_rng(5)
+        items = rng.zipf(1.3, 300000).astype(np.int64)
+        sp, st = cb.SpaceSaving(100, "i8"), cb.SummaryStats()
+        sp.update(items, stats=st)
+        s = torch.cuda.Stream()
+        for exact in (True, False):
+            red = SketchAllReduce(100, "i8", exact=exact)
+            with torch.cuda.stream(s):
+                msp, mst = red(sp, st)
+                msp, mst = red(sp, st)          # reused buffers and outputs
+            s.synchronize()
+            assert sorted(msp.counters().tolist()) == sorted(sp.counters().tolist())
+            # (stats_merge :78-90 into an empty summary leaves first_value alone, like the reference)
+            assert mst.__getstate__()[:8] == st.__getstate__()[:8]
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_spsv_allgather_world1_nccl(cb):
     import torch
     import torch.distributed as dist

@@ -1,0 +1,42 @@
+"""One multi-GPU step on ONE GPU (a 1-rank NCCL group): update of an n-value shard -> export ->
+all-gather -> merge, as bench.py runs it at N > 1.  Prints ms per step and the hot kernel's share:
+the difference is the fixed cost that limits strong scaling.  python tests/tools/step_probe.py [n] [records]"""
+import ctypes, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+import torch, torch.distributed as dist
+import crick_b200 as cb
+from crick_b200._lib import lib
+from crick_b200.distributed import TDigestAllReduce
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 125000000
+torch.cuda.set_device(0); lib.crick_set_device(0)
+dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
+dx, dw = cb.DeviceArray((n,)), cb.DeviceArray((n,))
+lib.crick_synth_fill(dx.ptr, dw.ptr, n, 1234, 0, 0, None)
+lib.crick_device_synchronize()
+stream = torch.cuda.Stream(); sptr = stream.cuda_stream
+red = TDigestAllReduce(100.0, exact=False)
+t = cb.TDigest(100, mode="parallel")
+def step():
+    t.update(dx, dw, mode="parallel", stream=sptr, check_w="deferred")
+    with torch.cuda.stream(stream):
+        return red(t)
+for _ in range(5): step()
+torch.cuda.synchronize()
+lib.crick_profile_enable(1)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 20
+e0.record(stream)
+for _ in range(K): m = step()
+e1.record(stream)
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / K
+lib.crick_profile_enable(0)
+kms, kn = ctypes.c_double(0), ctypes.c_int64(0)
+lib.crick_profile_collect(ctypes.addressof(kms), ctypes.addressof(kn))
+t.check_weights()
+print(json.dumps({"n": n, "ms_per_step": ms, "kernel_ms": kms.value / kn.value, "fixed_us": 1e3 * (ms - kms.value / kn.value),
+                  "centroids": len(m.centroids())}), flush=True)
+dist.destroy_process_group()
