@@ -343,6 +343,33 @@ def main():
     roofline_unweighted["value_gvalues_s"] = n * K / (ums * 1e-3) / 1e9
     roofline_unweighted["ms_per_step"] = ums / K
 
+    # ---- the same step with the exchange fused into one kernel over NVLink peer memory
+    # (ShardedTDigest / k_exchange_merge: no collective library call); N > 1 only
+    p2p = None
+    if world > 1:
+        try:
+            from crick_b200.distributed import ShardedTDigest
+            sh = ShardedTDigest(COMPRESSION)
+            for _ in range(W):
+                sh.update(dx, dw, stream=B.sptr)
+            B.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(B.stream)
+            for _ in range(K):
+                sh.update(dx, dw, stream=B.sptr)
+            ev1.record(B.stream)
+            B.barrier()
+            pms = B.max_over_ranks(ev0.elapsed_time(ev1))
+            sh.digest.check_weights()
+            p2p = {"value": n * K / (pms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": pms / K,
+                   "centroids": len(sh.digest.centroids()),
+                   "what": "ShardedTDigest.update: bucket points stored into every rank's buffer over NVLink "
+                           "(CUDA IPC peer pointers), flags, one merge -- k_exchange_merge instead of "
+                           "finalize + pack + NCCL all-gather + merge"}
+            sh.close()
+        except Exception as exc:
+            p2p = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     # ---- weak scaling next to it (N > 1): 1e9 values on EVERY GPU, same step
     weak = None
     if world > 1 and not args.no_weak:
@@ -431,7 +458,8 @@ def main():
                        "weights": "validated on the device in the same pass (deferred verdict, no host sync in a step)",
                        "centroids": nc, "digest_size": total_size},
             "roofline": roofline, "roofline_unweighted": roofline_unweighted, "cpu_baseline": cpu,
-            "e2e": e2e, "e2e_pageable": e2e_pageable, "weak": weak, "other_configs": others,
+            "e2e": e2e, "e2e_pageable": e2e_pageable, "weak": weak, "p2p_exchange": p2p,
+            "other_configs": others,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(out)

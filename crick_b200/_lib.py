@@ -27,6 +27,9 @@ _SIG = {
     "crick_device_count": (c_int, []),
     "crick_set_device": (c_int, [c_int]),
     "crick_sm_count": (c_int, []),
+    "crick_get_device": (c_int, []),
+    "crick_cast_to_f64": (c_int, [_P, c_int, c_int, c_int64, _P, _P]),
+    "crick_check_weights": (c_int, [_P, c_int64, _P]),
     "crick_launch_count": (c_int64, []),
     "crick_profile_enable": (c_int, [c_int]),
     "crick_group_kernel": (c_int, [c_int]),
@@ -49,6 +52,15 @@ _SIG = {
     "crick_tdigest_update_checked": (c_int, [_P, _P, _P, c_double, c_int64, c_int, c_int, c_int, _P, _P]),
     "crick_tdigest_update_deferred": (c_int, [_P, _P, _P, c_double, c_int64, c_int, _P]),
     "crick_tdigest_take_bad_weights": (c_int, [_P]),
+    "crick_p2p_buffer_bytes": (c_int64, [c_double, c_int]),
+    "crick_p2p_alloc": (_P, [c_int64]),
+    "crick_p2p_free": (None, [_P]),
+    "crick_ipc_get_handle": (c_int, [_P, _P]),
+    "crick_ipc_open_handle": (_P, [_P]),
+    "crick_ipc_close_handle": (c_int, [_P]),
+    "crick_p2p_new": (_P, [c_int, c_int, _P]),
+    "crick_p2p_destroy": (None, [_P]),
+    "crick_tdigest_update_exchange": (c_int, [_P, _P, _P, _P, c_double, c_int64, _P]),
     "crick_tdigest_update_stats": (c_int, [_P, _P, _P, _P, c_double, c_int64, c_int, c_int, _P, _P]),
     "crick_tdigest_flush": (c_int, [_P]),
     "crick_tdigest_merge": (c_int, [_P, _P, c_int]),
@@ -68,6 +80,7 @@ _SIG = {
     "crick_tdigest_centroids_device": (_P, [_P]),
     "crick_tdigest_set_state": (c_int, [_P, _P, c_int, c_double, c_double, c_double]),
     "crick_tdigest_reset": (c_int, [_P, _P]),
+    "crick_tdigest_debug_header": (c_int, [_P, _P]),
     "crick_tdigest_debug_edges": (c_int, [_P, _P, c_int]),
     "crick_tdigest_debug_buckets": (c_int, [_P, _P, _P, _P, c_int]),
     "crick_tdigest_record_doubles": (c_int, [_P]),

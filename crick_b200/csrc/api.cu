@@ -181,6 +181,11 @@ int crick_set_device(int device) {
     return 0;
 }
 int crick_sm_count(void) { return sm_count(); }
+int crick_get_device(void) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
 int64_t crick_launch_count(void) { return (int64_t)g_launches.load(); }
 void* crick_host_alloc(int64_t bytes) {
     void* p = nullptr;
@@ -322,6 +327,26 @@ int crick_profile_collect(double* total_ms, int64_t* launches) {
     int rc = profile_collect(total_ms, &n);
     *launches = n;
     return rc;
+}
+int crick_cast_to_f64(const void* src, int kind, int itemsize, int64_t n, double* dst, void* stream) {
+    cudaError_t e = launch_cast_f64(src, kind, itemsize, n, dst, reinterpret_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidValue) return fail_msg("crick_cast_to_f64: unsupported dtype");
+    return e == cudaSuccess ? 0 : fail("cast_to_f64", e);
+}
+int crick_check_weights(const double* w_dev, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int* flag = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&flag), sizeof(int), st);
+    if (e != cudaSuccess) return fail("cudaMallocAsync(check_weights)", e);
+    int bad = 0;
+    e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+    if (e == cudaSuccess) e = launch_check_weights(w_dev, n, flag, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(flag, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail("check_weights", e);
+    return bad ? 1 : 0;
 }
 int crick_synth_fill(double* x, double* w, int64_t n, uint64_t seed, int64_t offset, int kind,
                      void* stream) {
@@ -691,7 +716,76 @@ int crick_tdigest_take_bad_weights(crick_tdigest_t* t) {
     int bad = 0;
     cudaError_t e = parallel_take_bad_weights(t->scratch, td_stream(t, nullptr), &bad);
     if (e != cudaSuccess) return fail("take_bad_weights", e);
-    return bad ? 1 : 0;
+    return bad;      // bit 0: bad weights; bit 1: a sharded update timed out waiting for a rank
+}
+
+// ---- sharded update over NVLink peer memory -----------------------------------------------------
+struct crick_p2p {
+    int rank = 0, world = 1;
+    void* buf[16] = {};
+    unsigned long long step = 0;
+};
+
+int64_t crick_p2p_buffer_bytes(double compression, int world) {
+    if (compression < 20) compression = 20; else if (compression > 1000) compression = 1000;
+    return (int64_t)p2p_buffer_bytes(compression, world);
+}
+void* crick_p2p_alloc(int64_t bytes) {
+    void* p = nullptr;                       // plain cudaMalloc: the block is exported through CUDA IPC
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fail("crick_p2p_alloc", e); if (p) cudaFree(p); return nullptr; }
+    return p;
+}
+void crick_p2p_free(void* p) { if (p) cudaFree(p); }
+int crick_ipc_get_handle(void* dev_ptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaError_t e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), dev_ptr);
+    return e == cudaSuccess ? 0 : fail("cudaIpcGetMemHandle", e);
+}
+void* crick_ipc_open_handle(const void* handle64) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { fail("cudaIpcOpenMemHandle", e); return nullptr; }
+    return p;
+}
+int crick_ipc_close_handle(void* p) {
+    cudaError_t e = cudaIpcCloseMemHandle(p);
+    return e == cudaSuccess ? 0 : fail("cudaIpcCloseMemHandle", e);
+}
+crick_p2p_t* crick_p2p_new(int rank, int world, void* const* buffers) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) { fail_msg("crick_p2p_new: bad rank / world"); return nullptr; }
+    crick_p2p* c = new (std::nothrow) crick_p2p();
+    if (!c) return nullptr;
+    c->rank = rank; c->world = world;
+    for (int r = 0; r < world; ++r) {
+        if (!buffers[r]) { fail_msg("crick_p2p_new: null buffer"); delete c; return nullptr; }
+        c->buf[r] = buffers[r];
+    }
+    return c;
+}
+void crick_p2p_destroy(crick_p2p_t* c) { delete c; }
+
+int crick_tdigest_update_exchange(crick_tdigest_t* t, crick_p2p_t* c, const double* x, const double* w,
+                                  double w_scalar, int64_t n, void* stream) {
+    if (!c) return fail_msg("update_exchange: no communicator");
+    if (n > 0 && n < CRICK_PARALLEL_MIN) return fail_msg("update_exchange needs 0 or >= CRICK_PARALLEL_MIN values per rank");
+    cudaStream_t st = td_stream(t, stream);
+    if (td_drain(t, st)) return -1;
+    const bool clean = t->buf_clean;
+    t->mirror_ok = false; t->buf_clean = false;
+    if (td_scratch(t)) return -1;
+    cudaError_t e = clean ? cudaSuccess : launch_flush(t->s.v, 0, 1, 1, st);
+    // a scalar weight tdigest_add drops (:285) drops this rank's shard; the exchange still happens
+    const int64_t n_eff = (!w && w_scalar <= DBL_EPSILON) ? 0 : n;
+    if (e == cudaSuccess)
+        e = launch_parallel_update_exchange(t->s.v, 0, x, w, w_scalar, n_eff, t->scratch, sm_count(), st, true,
+                                            c->rank, c->world, c->buf, ++c->step);
+    if (e == cudaSuccess) t->buf_clean = true;
+    return e == cudaSuccess ? 0 : fail("update_exchange", e);
 }
 
 static int td_update(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
@@ -891,6 +985,11 @@ int crick_tdigest_reset(crick_tdigest_t* t, void* stream) {
 int crick_tdigest_debug_edges(crick_tdigest_t* t, double* out, int max_out) {
     if (!t->scratch) return 0;
     return parallel_debug_edges(t->scratch, out, max_out, td_stream(t, nullptr));
+}
+
+int crick_tdigest_debug_header(crick_tdigest_t* t, void* out256) {
+    if (!t->scratch) return -1;
+    return parallel_debug_header(t->scratch, out256, td_stream(t, nullptr));
 }
 
 int crick_tdigest_debug_buckets(crick_tdigest_t* t, double* out_w, double* out_s, double* out_minmax,

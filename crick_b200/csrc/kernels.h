@@ -66,6 +66,16 @@ cudaError_t parallel_bad_weights(void* scratch, cudaStream_t st, int* bad);
 // untouched) but keep the verdict on the device, sticky, until parallel_take_bad_weights reads
 // and clears it -- the update then needs no host synchronisation at all
 cudaError_t parallel_take_bad_weights(void* scratch, cudaStream_t st, int* bad);
+// Sharded update over peer memory (k_exchange_merge): this rank's shard is binned, its bucket points
+// are stored into every rank's exchange buffer (bufs[r], peer pointers, bufs[rank] = own) and the
+// digest absorbs all ranks' points of step `step` (1, 2, ... : the same on every rank).
+// cudaErrorInvalidValue = does not fit (compression too large): use the all-gather reducer.
+size_t p2p_rec_doubles(double comp);
+size_t p2p_buffer_bytes(double comp, int world);
+cudaError_t launch_parallel_update_exchange(const BatchView& v, long d, const double* X, const double* W,
+                                            double wsc, long n, void* scratch, int sm_count,
+                                            cudaStream_t st, bool check_weights, int rank, int world,
+                                            void* const* bufs, unsigned long long step);
 // The same pipeline in pieces, for host-resident input streamed in chunks: edges
 // from a caller-provided sample (copied to parallel_sample_x/w), any number of
 // accumulate calls (first = 1 on the first), then one finalize.
@@ -79,6 +89,7 @@ cudaError_t parallel_finalize(const BatchView& v, long d, void* scratch, int sm_
                               cudaStream_t st, bool honor_badw = false);
 // debug/test accessor: copy the bucket edges of the last parallel update to the host
 int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st);
+int parallel_debug_header(void* scratch, void* out256, cudaStream_t st);
 int parallel_debug_buckets(void* scratch, double comp, int sm_count, double* out_w, double* out_s,
                            double* out_minmax, int max_out, cudaStream_t st);
 double* parallel_sample_x(void* scratch);
@@ -94,6 +105,12 @@ cudaError_t stats_fused_finish(crick_stats* s, int nused, cudaStream_t st);
 
 void profile_enable(int on);
 int profile_collect(double* total_ms, long long* launches);
+
+// ---- input coercion (synth.cu): safe casts of CUDA arrays to float64 (kind 'f' 2/4/8 bytes,
+// 'i' / 'u' 1/2/4/8 bytes, 'b' bool), cudaErrorInvalidValue for anything else; and the wrapper's
+// weight check (w finite and > 0, tdigest.pyx:304-305) as a tiny reduction: *flag |= 1 if violated
+cudaError_t launch_cast_f64(const void* src, int kind, int itemsize, long n, double* dst, cudaStream_t st);
+cudaError_t launch_check_weights(const double* w, long n, int* flag, cudaStream_t st);
 
 // ---- synthetic data (synth.cu)
 cudaError_t launch_synth(double* x, double* w, long n, unsigned long long seed, long offset,

@@ -4,7 +4,71 @@
 // reproduces the same values.
 #include "kernels.h"
 
+#include <cuda_fp16.h>
+
 namespace crick {
+
+// ---- safe casts to float64 for CUDA-array inputs that are not float64 (the reference accepts
+// anything np.can_cast(dtype, 'f8', 'safe') allows, tdigest.pyx:298-302) -------------------------
+template <typename T>
+__device__ __forceinline__ double to_f64(T v) { return (double)v; }
+template <>
+__device__ __forceinline__ double to_f64<__half>(__half v) { return (double)__half2float(v); }
+
+template <typename T>
+__global__ void k_cast_f64(const T* __restrict__ src, long n, double* __restrict__ dst) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = to_f64<T>(src[i]);
+}
+
+template <typename T>
+static cudaError_t cast_launch(const void* src, long n, double* dst, cudaStream_t st) {
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    count_launch();
+    k_cast_f64<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const T*>(src), n, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cast_f64(const void* src, int kind, int itemsize, long n, double* dst, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (kind == 'f') {
+        if (itemsize == 8) return cast_launch<double>(src, n, dst, st);
+        if (itemsize == 4) return cast_launch<float>(src, n, dst, st);
+        if (itemsize == 2) return cast_launch<__half>(src, n, dst, st);
+    } else if (kind == 'i') {
+        if (itemsize == 8) return cast_launch<long long>(src, n, dst, st);
+        if (itemsize == 4) return cast_launch<int>(src, n, dst, st);
+        if (itemsize == 2) return cast_launch<short>(src, n, dst, st);
+        if (itemsize == 1) return cast_launch<signed char>(src, n, dst, st);
+    } else if (kind == 'u') {
+        if (itemsize == 8) return cast_launch<unsigned long long>(src, n, dst, st);
+        if (itemsize == 4) return cast_launch<unsigned>(src, n, dst, st);
+        if (itemsize == 2) return cast_launch<unsigned short>(src, n, dst, st);
+        if (itemsize == 1) return cast_launch<unsigned char>(src, n, dst, st);
+    } else if (kind == 'b' && itemsize == 1) {
+        return cast_launch<unsigned char>(src, n, dst, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// w finite and > 0 for every element?  (tdigest.pyx:304-305)
+__global__ void k_check_weights(const double* __restrict__ w, long n, int* flag) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = w[i];
+        bad |= !(v > 0.0 && v <= DBL_MAX);
+    }
+    if (__any_sync(CRICK_FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+cudaError_t launch_check_weights(const double* w, long n, int* flag, cudaStream_t st) {
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    count_launch();
+    k_check_weights<<<(unsigned)blocks, 256, 0, st>>>(w, n, flag);
+    return cudaGetLastError();
+}
 
 __device__ __forceinline__ unsigned long long sm64(unsigned long long z) {
     z += 0x9e3779b97f4a7c15ull;

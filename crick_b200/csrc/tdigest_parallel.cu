@@ -109,6 +109,8 @@ struct ParHeader {
     int shift;   // grid 0: cell = ((skey32(x) >> 1) - kbase) >> shift, kbase includes the "+ 1 cell"
     int kbase;
     int badw_sticky;  // set by k_finalize when it refused an update because of badw; cleared by the host
+    int p2p_timeout;  // k_exchange_merge gave up waiting for a rank
+    int pad1;
     long S;      // sample length (power of two)
     int ncta;    // CTAs that wrote partials
     int grid;    // lookup grid: 0 = linear in the ordered bit pattern, 1 = linear in x
@@ -1778,40 +1780,22 @@ __device__ __forceinline__ void block_merge_sorted(const WarpWS& ws, double comp
 }
 
 // 5. finalize: bucket sums -> sorted weighted points -> greedy k-scale merge.
-__global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeader* hdr,
-                                                   const double* __restrict__ edges,
-                                                   const double2* __restrict__ partial,
-                                                   const double2* __restrict__ minmax,
-                                                   unsigned char* gws, int mmax, int use_smem,
-                                                   int honor_badw) {
+//
+// finalize_points: phases a-b -- the per-CTA partials reduced in fixed order and turned into
+// <= mmax weighted points in sorted order (sb[0..m)), plus the exact (min, max) of the batch.
+// Returns m (uniform over the CTA).  1024 threads.
+__device__ __forceinline__ int finalize_points(const ParHeader* hdr, const double* __restrict__ edges,
+                                               const double2* __restrict__ partial,
+                                               const double2* __restrict__ minmax, double2* sb,
+                                               int mmax, double comp, double& mn_out, double& mx_out) {
     __shared__ int s_scan[1024 + 1];
     __shared__ double s_mm[2];
     __shared__ int s_m;
     __shared__ double s_W;
     const int tid = threadIdx.x;
-    grid_dep_wait();          // the partials of k_bin_accumulate
-    // validated update (tdigest.pyx:304-305): the digest is only touched when every weight
-    // passed; the host reads the same flag after this kernel has been enqueued
-    if (honor_badw && hdr->badw) {
-        if (tid == 0) hdr->badw_sticky = 1;   // read (and cleared) by parallel_take_bad_weights
-        return;
-    }
     const int E = hdr->E;
     const int B = E + 1;
     const int ncta = hdr->ncta;
-    const int cap = v.cap;
-    unsigned char* wsbase = use_smem ? smem_raw : gws;
-    // custom carve: cen[cap] | sb[mmax] | items[cap+mmax] | kend | start  (no unsorted buf)
-    WarpWS ws;
-    {
-        size_t t = (size_t)cap + mmax;
-        ws.cen = reinterpret_cast<double2*>(wsbase);
-        ws.sb = ws.cen + cap;
-        ws.buf = ws.sb;
-        ws.items = ws.sb + mmax;
-        ws.kend = reinterpret_cast<double*>(ws.items + t);
-        ws.start = reinterpret_cast<int*>(ws.kend + t);
-    }
     // a. reduce partials over CTAs and the batch total weight.  Bucket b is summed by NS
     // threads, thread (s, b) taking rows s, s + NS, ... (loads independent, 16 in flight), then
     // the NS slice sums are added in slice order: a fixed order, so the result is deterministic.
@@ -1889,7 +1873,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
             const double Wb = s_W;          // weight of this batch
             const double before = s_before[b];
             double q0 = before / Wb, q1 = (before + bw) / Wb;
-            double span = kscale(v.comp, q1) - kscale(v.comp, q0);
+            double span = kscale(comp, q1) - kscale(comp, q0);
             int p = (int)ceil(span * 2.0);
             np = p < 1 ? 1 : p;
         }
@@ -1913,7 +1897,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         double each = w_ / (double)p;
         for (int k = 0; k < p; ++k) {
             double wk = (k == p - 1) ? (w_ - each * (double)(p - 1)) : each;
-            ws.sb[at + k] = make_double2(mean, wk);
+            sb[at + k] = make_double2(mean, wk);
         }
     };
     if (b < B) emit(b, bw, bs, np, pos);
@@ -1922,11 +1906,43 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
         s_m = m > mmax ? mmax : m;
     }
     __syncthreads();
+    mn_out = mn; mx_out = mx;
+    return s_m;
+}
+
+__global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeader* hdr,
+                                                   const double* __restrict__ edges,
+                                                   const double2* __restrict__ partial,
+                                                   const double2* __restrict__ minmax,
+                                                   unsigned char* gws, int mmax, int use_smem,
+                                                   int honor_badw) {
+    const int tid = threadIdx.x;
+    grid_dep_wait();          // the partials of k_bin_accumulate
+    // validated update (tdigest.pyx:304-305): the digest is only touched when every weight
+    // passed; the host reads the same flag after this kernel has been enqueued
+    if (honor_badw && hdr->badw) {
+        if (tid == 0) hdr->badw_sticky = 1;   // read (and cleared) by parallel_take_bad_weights
+        return;
+    }
+    const int cap = v.cap;
+    unsigned char* wsbase = use_smem ? smem_raw : gws;
+    // custom carve: cen[cap] | sb[mmax] | items[cap+mmax] | kend | start  (no unsorted buf)
+    WarpWS ws;
+    {
+        size_t t = (size_t)cap + mmax;
+        ws.cen = reinterpret_cast<double2*>(wsbase);
+        ws.sb = ws.cen + cap;
+        ws.buf = ws.sb;
+        ws.items = ws.sb + mmax;
+        ws.kend = reinterpret_cast<double*>(ws.items + t);
+        ws.start = reinterpret_cast<int*>(ws.kend + t);
+    }
+    double mn, mx;
+    const int m = finalize_points(hdr, edges, partial, minmax, ws.sb, mmax, v.comp, mn, mx);
     // c. merge into the digest (tdigest_flush phases 2-5 with the bucket points as the buffer)
     {
         __shared__ double s_bt;
         __shared__ int s_nc;
-        const int m = s_m;
         Hdr h;
         const DevHdr dh = v.hdr[d];
         h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
@@ -1948,6 +1964,208 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
             }
         }
     }
+}
+
+// 5b. k_exchange_merge -- the tail of a multi-GPU step as ONE kernel over NVLink peer memory.
+//
+// A stream sharded over G GPUs (BASELINE config 2) ends every update with "all ranks' partial
+// results -> one digest on every rank".  Through NCCL that is finalize -> pack -> all-gather ->
+// reset -> merge: five launches and a collective whose latency (not bandwidth: 3 KB per rank) sits
+// on the critical path.  Here the kernel that reduces the rank's bucket partials to <= 2 ov c
+// weighted points
+//   * stores them, with (count, weight, min, max), straight into slot [step & 1][rank] of EVERY
+//     rank's exchange buffer (peer pointers obtained through CUDA IPC: plain st.global over
+//     NVLink / NVSwitch), then publishes the step number in flags[rank] of every rank with a
+//     system-scope release store;
+//   * waits (system-scope acquire loads on its OWN flags) until every rank's points of this step
+//     have arrived;
+//   * ranks the G sorted point runs against each other in shared memory and folds the union into
+//     the digest in one greedy k-scale pass (block_merge_sorted) -- every rank computes the same
+//     digest from the same records in the same order.
+// Two slots per source rank: a rank can only be one step ahead of the slowest reader (its next
+// merge needs that reader's next flag).  The wait gives up after 4 s (flag in ParHeader).
+constexpr int kP2PMaxWorld = 16;
+constexpr int kP2PFlagDoubles = 32;          // flags[16] u64, padded to 256 B
+struct P2PView {
+    int rank, world;
+    int rec_doubles;                          // 4 + 2 * mmax
+    int empty;                                // this rank has no data in this step
+    unsigned long long step;
+    double* buf[kP2PMaxWorld];                // exchange buffer of every rank (buf[rank] = own)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) k_exchange_merge(BatchView v, long d, ParHeader* hdr,
+                                                         const double* __restrict__ edges,
+                                                         const double2* __restrict__ partial,
+                                                         const double2* __restrict__ minmax, int mmax,
+                                                         int pmax, P2PView pv, int honor_badw) {
+    __shared__ int s_off[kP2PMaxWorld + 1];
+    __shared__ double s_tot[kP2PMaxWorld], s_rmn[kP2PMaxWorld], s_rmx[kP2PMaxWorld];
+    __shared__ double s_scan_d[32];
+    __shared__ int s_nc, s_ng, s_timeout;
+    const int tid = threadIdx.x;
+    const int cap = v.cap;
+    // phase timestamps (globaltimer ns) for tests/tools/sharded_check.py: [128 .. 176) of the header block
+    unsigned long long* dbg = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(hdr) + 128);
+    if (tid == 0) dbg[0] = global_ns();
+    grid_dep_wait();          // the partials of k_bin_accumulate
+    if (tid == 0) dbg[1] = global_ns();
+    // carve: cen[cap] | sb[pmax] | items[cap + pmax] | kend | start; the staged keys of the runs
+    // alias items (dead until the merge)
+    WarpWS ws;
+    {
+        size_t t = (size_t)cap + pmax;
+        ws.cen = reinterpret_cast<double2*>(smem_raw);
+        ws.sb = ws.cen + cap;
+        ws.buf = ws.sb;
+        ws.items = ws.sb + pmax;
+        ws.kend = reinterpret_cast<double*>(ws.items + t);
+        ws.start = reinterpret_cast<int*>(ws.kend + t);
+    }
+    double* keys = reinterpret_cast<double*>(ws.items);
+    // ---- 1. this rank's points
+    int m = 0;
+    double mn = INFINITY, mx = -INFINITY;
+    const bool refused = honor_badw && !pv.empty && hdr->badw;     // (uniform)
+    if (refused && tid == 0) hdr->badw_sticky = 1;
+    if (!pv.empty && !refused) m = finalize_points(hdr, edges, partial, minmax, ws.sb, mmax, v.comp, mn, mx);
+    // total weight of the points (block scan: fixed association)
+    double wsum = 0.0;
+    {
+        const double incl = block_scan_incl<double>(tid < m ? ws.sb[tid].y : 0.0, s_scan_d);
+        __shared__ double s_last;
+        if (tid == 1023) s_last = incl;
+        __syncthreads();
+        wsum = s_last;           // m <= mmax <= 1024 for c <= 100 ... larger m: second pass below
+        for (int base = 1024; base < m; base += 1024) {
+            const double inc2 = block_scan_incl<double>(base + tid < m ? ws.sb[base + tid].y : 0.0, s_scan_d);
+            if (tid == 1023) s_last = inc2;
+            __syncthreads();
+            wsum += s_last;
+            __syncthreads();
+        }
+    }
+    // ---- 2. publish: points into slot [step & 1][rank] of every rank, then the step number
+    const size_t slot = (size_t)kP2PFlagDoubles + ((size_t)(pv.step & 1ull) * pv.world + pv.rank) * pv.rec_doubles;
+    for (int r = 0; r < pv.world; ++r) {
+        double* dst = pv.buf[r] + slot;
+        if (tid == 0) { dst[0] = (double)m; dst[1] = wsum; dst[2] = mn; dst[3] = mx; }
+        double2* dp = reinterpret_cast<double2*>(dst + 4);
+        for (int i = tid; i < m; i += blockDim.x) dp[i] = ws.sb[i];
+    }
+    if (tid == 0) dbg[2] = global_ns();
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pv.world)
+        st_release_sys(reinterpret_cast<unsigned long long*>(pv.buf[tid]) + pv.rank, pv.step);
+    if (tid == 0) dbg[3] = global_ns();
+    // ---- 3. wait for every rank's points of this step
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    if (tid < pv.world) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pv.buf[pv.rank]) + tid;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(f) < pv.step) {
+            __nanosleep(64);
+            if (global_ns() - t0 > 4000000000ull) { s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) dbg[4] = global_ns();
+    if (s_timeout) {                            // a rank never arrived: leave the digest alone
+        if (tid == 0) hdr->p2p_timeout = 1;
+        return;
+    }
+    // ---- 4. merge the G sorted runs into the digest
+    const double* own = pv.buf[pv.rank] + (size_t)kP2PFlagDoubles + (size_t)(pv.step & 1ull) * pv.world * pv.rec_doubles;
+    Hdr h;
+    const DevHdr dh = v.hdr[d];
+    h.vmin = dh.vmin; h.vmax = dh.vmax; h.total = dh.total; h.btotal = 0.0; h.n = dh.n; h.bn = 0;
+    {
+        const double2* cg = v.cen + d * (long)cap;
+        for (int i = tid; i < h.n; i += blockDim.x) ws.cen[i] = cg[i];
+    }
+    bool any = false;
+    int r0 = 0;
+    while (r0 < pv.world) {                     // groups of records whose points fit the workspace
+        if (tid == 0) {
+            int run = 0, r = r0;
+            for (; r < pv.world; ++r) {
+                const double* rec = own + (size_t)r * pv.rec_doubles;
+                int n = (int)__ldcg(rec);
+                n = n < 0 ? 0 : (n > mmax ? mmax : n);
+                if (run + n > pmax && r > r0) break;
+                s_off[r - r0] = run;
+                run += n;
+                s_tot[r - r0] = __ldcg(rec + 1); s_rmn[r - r0] = __ldcg(rec + 2); s_rmx[r - r0] = __ldcg(rec + 3);
+            }
+            s_off[r - r0] = run;
+            s_ng = r - r0;                      // records in this group
+        }
+        __syncthreads();
+        const int ng = s_ng;
+        const int T = s_off[ng];
+        for (int q = 0; q < ng; ++q) {          // stage the keys (means) of every run
+            const double2* pts = reinterpret_cast<const double2*>(own + (size_t)(r0 + q) * pv.rec_doubles + 4);
+            const int n = s_off[q + 1] - s_off[q];
+            for (int i = tid; i < n; i += blockDim.x) keys[s_off[q] + i] = __ldcg(&pts[i].x);
+        }
+        __syncthreads();
+        for (int e = tid; e < T; e += blockDim.x) {
+            int q = 0;
+            while (s_off[q + 1] <= e) ++q;
+            const double k = keys[e];
+            int rank = e - s_off[q];
+            for (int o = 0; o < ng; ++o) {
+                if (o == q) continue;
+                int lo = s_off[o], hi = s_off[o + 1];
+                if (o < q) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] <= k) lo = mid + 1; else hi = mid; } }
+                else { while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; } }
+                rank += lo - s_off[o];
+            }
+            const double2* pts = reinterpret_cast<const double2*>(own + (size_t)(r0 + q) * pv.rec_doubles + 4);
+            ws.sb[rank] = make_double2(k, __ldcg(&pts[e - s_off[q]].y));
+        }
+        __syncthreads();
+        if (T > 0) {                            // uniform
+            for (int q = 0; q < ng; ++q) {      // every thread the same fl chain
+                if (s_off[q + 1] > s_off[q]) {
+                    h.total = __dadd_rn(h.total, s_tot[q]);
+                    if (h.vmin > s_rmn[q]) h.vmin = s_rmn[q];
+                    if (h.vmax < s_rmx[q]) h.vmax = s_rmx[q];
+                }
+            }
+            block_merge_sorted<false>(ws, v.comp, h, T, cap, &s_nc, nullptr);
+            any = true;
+        }
+        __syncthreads();
+        r0 += ng;
+    }
+    if (any) {
+        double2* cgo = v.cen + d * (long)cap;
+        for (int i = tid; i < h.n; i += blockDim.x) cgo[i] = ws.cen[i];
+        if (tid == 0) {
+            DevHdr o = dh;
+            o.vmin = h.vmin; o.vmax = h.vmax; o.total = h.total; o.btotal = 0.0;
+            o.n = h.n; o.bn = 0;
+            v.hdr[d] = o;
+        }
+    }
+    if (tid == 0) dbg[5] = global_ns();
 }
 
 // 6. bulk merge of gathered records (multi-GPU tail) -----------------------------------------
@@ -2336,9 +2554,10 @@ cudaError_t parallel_take_bad_weights(void* scratch, cudaStream_t st, int* bad) 
     ParHeader h;
     cudaError_t e = cudaMemcpyAsync(&h, L.hdr, sizeof(h), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    *bad = (e == cudaSuccess) ? h.badw_sticky : 0;
-    if (e == cudaSuccess && h.badw_sticky)
-        e = cudaMemsetAsync(&L.hdr->badw_sticky, 0, sizeof(int), st);
+    // bit 0: a deferred weight check failed; bit 1: k_exchange_merge gave up waiting for a rank
+    *bad = (e == cudaSuccess) ? ((h.badw_sticky ? 1 : 0) | (h.p2p_timeout ? 2 : 0)) : 0;
+    if (e == cudaSuccess && (h.badw_sticky || h.p2p_timeout))
+        e = cudaMemsetAsync(&L.hdr->badw_sticky, 0, 2 * sizeof(int), st);
     return e;
 }
 
@@ -2360,6 +2579,45 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
     e = parallel_finalize(v, d, scratch, sm_count, st, checked);
     if (e == cudaSuccess && checked && !defer_check) e = parallel_bad_weights(scratch, st, bad_weights);
     return e;
+}
+
+// ---- sharded update: sample -> edges -> accumulate on this rank, then k_exchange_merge ----------
+size_t p2p_rec_doubles(double comp) { return 4 + 2 * (size_t)mmax_for(comp); }
+size_t p2p_buffer_bytes(double comp, int world) {
+    return ((size_t)kP2PFlagDoubles + 2 * (size_t)world * p2p_rec_doubles(comp)) * sizeof(double);
+}
+cudaError_t launch_parallel_update_exchange(const BatchView& v, long d, const double* X, const double* W,
+                                            double wsc, long n, void* scratch, int sm_count,
+                                            cudaStream_t st, bool check_weights, int rank, int world,
+                                            void* const* bufs, unsigned long long step) {
+    if (world < 1 || world > kP2PMaxWorld) return cudaErrorInvalidValue;
+    ParLayout L = carve(scratch, v.comp, sm_count);
+    const int mmax = mmax_for(v.comp);
+    // shared memory of the merge: cen[cap] | sb[pmax] | items[cap + pmax] | kend | start, next to
+    // ~39 KB of static arrays; at least one rank's points must fit
+    const size_t budget = 190000;
+    long pmax = ((long)budget - (long)v.cap * 44 - 16) / 44;
+    if (pmax > (long)world * mmax) pmax = (long)world * mmax;
+    if (pmax < mmax) return cudaErrorInvalidValue;      // (huge compressions: use the NCCL reducer)
+    const size_t smem = (size_t)v.cap * 16 + (size_t)pmax * 16 + ((size_t)v.cap + pmax) * 28 + 16;
+    P2PView pv;
+    pv.rank = rank; pv.world = world; pv.rec_doubles = (int)p2p_rec_doubles(v.comp);
+    pv.empty = n <= 0 ? 1 : 0; pv.step = step;
+    for (int r = 0; r < kP2PMaxWorld; ++r) pv.buf[r] = r < world ? reinterpret_cast<double*>(bufs[r]) : nullptr;
+    cudaError_t e = cudaSuccess;
+    if (n > 0) {
+        long S = sample_len(n);
+        SampleSrc src{X, W, wsc, n, L.hdr};
+        e = edges_from_sample(v, L, S, &src, st);
+        if (e != cudaSuccess) return e;
+        e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, nullptr, 0);
+        if (e != cudaSuccess) return e;
+    }
+    e = need_smem(k_exchange_merge, smem);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return launch_dep(k_exchange_merge, dim3(1), dim3(1024), smem, st, v, d, L.hdr, L.edges, L.partial,
+                      L.minmax, mmax, (int)pmax, pv, (check_weights && W) ? 1 : 0);
 }
 
 // test hook: per-bucket (sum w, sum w*x) of the last update, reduced over CTAs in the same
@@ -2392,6 +2650,12 @@ int parallel_debug_buckets(void* scratch, double comp, int sm_count, double* out
     for (int c = 0; c < h.ncta; ++c) { mn = fmin(mn, mm[c].x); mx = fmax(mx, mm[c].y); }
     out_minmax[0] = mn; out_minmax[1] = mx;
     return B;
+}
+
+// test hook: the 256-byte header block (ParHeader + phase timestamps of k_exchange_merge)
+int parallel_debug_header(void* scratch, void* out256, cudaStream_t st) {
+    if (cudaMemcpyAsync(out256, scratch, 256, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
 }
 
 int parallel_debug_edges(void* scratch, double* out, int max_out, cudaStream_t st) {

@@ -92,6 +92,95 @@ class TDigestAllReduce:
         return self.out
 
 
+class ShardedTDigest:
+    """One TDigest over a stream that is sharded across the GPUs of a node (BASELINE config 2).
+
+    Every rank calls ``update(x_shard, w_shard)`` -- collectively, the same number of times --
+    with CUDA arrays; afterwards ``digest`` holds, identically on every rank, the digest of ALL
+    ranks' data seen so far.  The exchange does not go through a collective library: one kernel
+    per rank turns the rank's bucket sums into <= 2 ov c weighted points, stores them into every
+    rank's exchange buffer over NVLink (peer pointers obtained through CUDA IPC), waits for the
+    others' points and folds the union into the digest in one greedy pass (``k_exchange_merge``).
+    Setup (IPC handle exchange) uses ``torch.distributed``'s object all-gather once.
+
+    Weights are validated on the device like ``update(..., check_w="deferred")``: a rank whose
+    weights fail contributes nothing to that step and ``digest.check_weights()`` raises there.
+    """
+
+    def __init__(self, compression=100.0, group=None):
+        import torch.distributed as dist
+        from ._lib import check, check_handle, lib
+
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.digest = TDigest(compression, mode="parallel")
+        nbytes = lib.crick_p2p_buffer_bytes(float(self.digest.compression), self.world)
+        self._own = check_handle(lib.crick_p2p_alloc(nbytes), "crick_p2p_alloc")
+        import ctypes
+        handle = ctypes.create_string_buffer(64)
+        check(lib.crick_ipc_get_handle(self._own, handle), "ipc handle")
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        else:
+            handles[0] = bytes(handle.raw)
+        self._opened = []
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = self._own
+            else:
+                p = check_handle(lib.crick_ipc_open_handle(ctypes.c_char_p(handles[r])), "ipc open")
+                self._opened.append(p)
+                ptrs[r] = p
+        self._comm = check_handle(lib.crick_p2p_new(self.rank, self.world, ptrs), "crick_p2p_new")
+        if self.world > 1:
+            dist.barrier(group=group)       # every rank has mapped every buffer before the first step
+
+    def update(self, x, w=1, stream=None):
+        """Collective: this rank's shard (CUDA arrays; `w` a CUDA array or a scalar).  Returns the
+        digest (valid once the stream has executed the call)."""
+        import math
+        from ._arrays import device_view
+        from ._lib import check, lib
+
+        xd = device_view(x)
+        if xd is None or xd.dtype != np.float64:
+            raise TypeError("x must be a float64 CUDA array")
+        wd = device_view(w)
+        if wd is not None:
+            if wd.dtype != np.float64 or wd.size != xd.size:
+                raise TypeError("w must be a float64 CUDA array shaped like x")
+            wp, wsc = wd.ptr, 0.0
+        else:
+            wp, wsc = None, float(w)
+            if wsc != 1 and (not math.isfinite(wsc) or wsc <= 0):
+                raise ValueError("w must be > 0 and finite")
+        check(lib.crick_tdigest_update_exchange(self.digest._h, self._comm, xd.ptr if xd.size else None, wp,
+                                                wsc, xd.size, stream), "sharded update")
+        self.digest._deferred = True
+        return self.digest
+
+    def close(self):
+        from ._lib import lib
+        if getattr(self, "_comm", None):
+            lib.crick_device_synchronize()
+            lib.crick_p2p_destroy(self._comm)
+            self._comm = None
+            for p in self._opened:
+                lib.crick_ipc_close_handle(p)
+            self._opened = []
+            lib.crick_p2p_free(self._own)
+            self._own = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def allgather_merge_tdigest(digest, group=None):
     """One-shot form: a new TDigest equal to ``TDigest(c).merge(*[digest of rank 0, 1, ...])``."""
     import torch

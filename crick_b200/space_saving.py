@@ -4,7 +4,7 @@ int64 and float64 item types run on the GPU.  The object dtype needs ``PyObject_
 evaluate: that one dtype is a host-side Stream-Summary (``_spsv_object.py``)."""
 import numpy as np
 
-from ._arrays import device_view, korder_pair
+from ._arrays import device_view, korder_pair, release_views
 from ._lib import check, check_handle, handle_array, lib
 from ._spsv_object import ObjectSummary
 
@@ -188,13 +188,13 @@ class SpaceSaving:
             return self._update_object(item, count)
         if stats is not None:
             return self._update_with_stats(item, count, stream, stats)
-        idv = device_view(item)
+        idv = device_view(item, stream)
         if idv is not None:
             if idv.dtype != self.dtype:
                 raise TypeError("CUDA item array must have dtype %s" % self.dtype)
             if idv.size == 0:
                 return
-            cd = device_view(count)
+            cd = device_view(count, stream)
             if cd is not None:
                 if cd.dtype != np.int64 or cd.size != idv.size:
                     raise TypeError("count must be an int64 CUDA array shaped like item")
@@ -206,6 +206,7 @@ class SpaceSaving:
                     raise ValueError("count must be > 0")
                 check(lib.crick_spsv_update(self._h, idv.ptr, None, c, idv.size, 1, 0, mode, stream),
                       "update")
+            release_views((idv, cd), stream)
             return
         item = np.asarray(item)
         check_count = not (np.isscalar(count) and count == 1)
@@ -233,13 +234,14 @@ class SpaceSaving:
         if not (np.isscalar(count) and count == 1):
             raise ValueError("stats= needs count == 1")
         f64 = int(self.dtype.kind == "f")
-        idv = device_view(item)
+        idv = device_view(item, stream)
         if idv is not None:
             if idv.dtype != self.dtype:
                 raise TypeError("CUDA item array must have dtype %s" % self.dtype)
             if idv.size:
                 check(lib.crick_spsv_update_stats(self._h, stats._h, idv.ptr, idv.size, 1, f64, stream),
                       "update")
+                release_views((idv,), stream)
             return
         item = np.asarray(item).astype(self.dtype, casting="safe", copy=False)
         if item.size == 0:

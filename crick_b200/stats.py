@@ -3,7 +3,7 @@ import ctypes
 
 import numpy as np
 
-from ._arrays import device_view, korder_pair
+from ._arrays import device_view, korder_pair, release_views
 from ._lib import check, check_handle, handle_array, lib
 
 
@@ -84,24 +84,27 @@ class SummaryStats:
         Add many elements to the summary.  `x` may be NumPy-compatible or a float64 / int64
         CUDA array; `count` a scalar or an array.
         """  # stats.pyx:108-126
-        xd = device_view(x)
+        xd = device_view(x, stream)
         if xd is not None:
             if xd.dtype not in (np.dtype("f8"), np.dtype("i8")):
-                raise TypeError("x must be float64 or int64 when given as a CUDA array")
+                from ._arrays import as_f64_device
+                xd = as_f64_device(xd, stream)          # other numeric dtypes: safe cast on the device
             if xd.size == 0:
                 return
-            cd = device_view(count)
+            cd = device_view(count, stream)
             if cd is not None:
                 if cd.dtype != np.int64 or cd.size != xd.size:
                     raise TypeError("count must be an int64 CUDA array shaped like x")
                 check(lib.crick_stats_update(self._h, xd.ptr, int(xd.dtype == np.int64), cd.ptr, 0,
                                              xd.size, 1, 1, stream), "update")
+                release_views((xd, cd), stream)
             else:
                 c = _as_int(count, "count")
                 if c <= 0:
                     raise ValueError("count must be > 0")
                 check(lib.crick_stats_update(self._h, xd.ptr, int(xd.dtype == np.int64), None, c,
                                              xd.size, 1, 0, stream), "update")
+                release_views((xd,), stream)
             return
         x = np.asarray(x)
         check_count = not (np.isscalar(count) and count == 1)

@@ -12,7 +12,8 @@ import numbers
 import numpy as np
 
 from . import _lib
-from ._arrays import DeviceArray, device_view, korder_pair
+from ._arrays import (DeviceArray, as_f64_device, device_view, dlpack_capsule, korder_pair,
+                      release_views)
 from ._lib import check, check_handle, lib
 
 CENTROID_DTYPE = np.dtype([("mean", np.float64), ("weight", np.float64)])  # tdigest.pyx:43
@@ -84,7 +85,10 @@ class TDigest:
         last call: raises the ValueError the synchronous check would have raised at the call
         (an update whose weights failed left the digest as it was).  Synchronises."""
         self._deferred = False
-        if check(lib.crick_tdigest_take_bad_weights(self._h), "check_weights"):
+        bits = check(lib.crick_tdigest_take_bad_weights(self._h), "check_weights")
+        if bits & 2:
+            raise RuntimeError("a sharded update timed out waiting for another rank's partial digest")
+        if bits & 1:
             raise ValueError("w must be > 0 and finite")
 
     def min(self):
@@ -115,8 +119,7 @@ class TDigest:
     def _query(self, x, fn, name, out=None):
         dv = device_view(x)
         if dv is not None:
-            if dv.dtype != np.float64:
-                raise TypeError("%s must be float64 when given as a CUDA array" % name)
+            dv = as_f64_device(dv)
             if out is None:
                 out = DeviceArray(dv.shape, "f8")
                 optr = out.ptr
@@ -250,11 +253,20 @@ class TDigest:
         ptr = lib.crick_tdigest_centroids_device(self._h)
         owner = self
 
+        device = lib.crick_get_device()
+
         class _View:
             # (exported writable: PyTorch rejects read-only CUDA arrays; treat it as read-only)
             __cuda_array_interface__ = {"shape": (n, 2), "typestr": "<f8", "data": (ptr, False),
                                         "version": 3, "strides": None}
             _keep = owner
+
+            def __dlpack_device__(self):
+                return (2, device)       # kDLCUDA
+
+            def __dlpack__(self, stream=None, **_):
+                check(lib.crick_device_synchronize(), "synchronize")   # the flush above has run
+                return dlpack_capsule(ptr, (n, 2), np.float64, device, owner)
         return _View()
 
     def __reduce__(self):  # tdigest.pyx:246-247
@@ -319,7 +331,7 @@ class TDigest:
         m = self._mode if mode is None else _lib.mode_code(mode)
         if stats is not None:
             return self._update_with_stats(x, w, stream, check_w, stats)
-        xd = device_view(x)
+        xd = device_view(x, stream)
         if xd is not None:
             return self._update_device(xd, w, m, stream, check_w)
         x = np.asarray(x)
@@ -372,18 +384,18 @@ class TDigest:
         from .stats import SummaryStats
         if not isinstance(stats, SummaryStats):
             raise TypeError("stats must be a SummaryStats")
-        xd = device_view(x)
-        wd = device_view(w)
+        xd = device_view(x, stream)
+        wd = device_view(w, stream)
         bad = ctypes.c_int(0)
         if xd is not None:
-            if xd.dtype != np.float64:
-                raise TypeError("x must be float64 when given as a CUDA array")
+            xd = as_f64_device(xd, stream)
             if xd.size < _lib.PARALLEL_MIN:
                 self._update_device(xd, w, _lib.MODE_REFERENCE, stream, check_w)
                 return stats.update(x)
             if wd is not None:
-                if wd.dtype != np.float64 or wd.size != xd.size:
-                    raise TypeError("w must be a float64 CUDA array shaped like x")
+                wd = as_f64_device(wd, stream)
+                if wd.size != xd.size:
+                    raise ValueError("x and w CUDA arrays must have the same number of elements")
                 wp, wsc = wd.ptr, 0.0
             else:
                 wp, wsc = None, _as_double(w, "w")
@@ -393,6 +405,7 @@ class TDigest:
                                                  1 if wp else 0, stream,
                                                  ctypes.addressof(bad) if check_w else None),
                   "update")
+            release_views((xd, wd), stream)
         else:
             x = np.asarray(x)
             w = np.asarray(w)
@@ -418,18 +431,16 @@ class TDigest:
             raise ValueError("w must be > 0 and finite")
 
     def _update_device(self, xd, w, m, stream, check_w=True):
-        if xd.dtype != np.float64:
-            raise TypeError("x must be float64 when given as a CUDA array")
+        xd = as_f64_device(xd, stream)     # int / float16 / float32 ... CUDA arrays: safe cast on the device
         n = xd.size
         if n == 0:
             return
         eff = m
         if m == _lib.MODE_PARALLEL and n < _lib.PARALLEL_MIN:
             eff = _lib.MODE_REFERENCE
-        wd = device_view(w)
+        wd = device_view(w, stream)
         if wd is not None:
-            if wd.dtype != np.float64:
-                raise TypeError("w must be float64 when given as a CUDA array")
+            wd = as_f64_device(wd, stream)
             if wd.size != n:
                 raise ValueError("x and w CUDA arrays must have the same number of elements")
             parallel = eff == _lib.MODE_PARALLEL or (eff == _lib.MODE_AUTO
@@ -441,6 +452,7 @@ class TDigest:
                     check(lib.crick_tdigest_update_deferred(self._h, xd.ptr, wd.ptr, 0.0, n, eff,
                                                             stream), "update")
                     self._deferred = True
+                    release_views((xd, wd), stream)
                     return
             if check_w and parallel:
                 bad = ctypes.c_int(0)
@@ -449,10 +461,13 @@ class TDigest:
                 if bad.value:
                     raise ValueError("w must be > 0 and finite")
                 return
-            # reference-mode sizes: device weights are not validated (documented divergence:
-            # w <= eps is dropped by the kernel exactly like tdigest_add does)
+            # reference-mode sizes: the wrapper's check (tdigest.pyx:304-305) as a small reduction
+            # over the device weights before anything is added
+            if check_w and check(lib.crick_check_weights(wd.ptr, n, stream), "check weights"):
+                raise ValueError("w must be > 0 and finite")
             check(lib.crick_tdigest_update(self._h, xd.ptr, wd.ptr, 0.0, n, 1, 1, eff, stream),
                   "update")
+            release_views((xd, wd), stream)
             return
         if not np.isscalar(w) and np.ndim(w) != 0:
             raise TypeError("with a CUDA array x, w must be a scalar or a CUDA array")
@@ -460,6 +475,7 @@ class TDigest:
         if wv != 1 and (not math.isfinite(wv) or wv <= 0):
             raise ValueError("w must be > 0 and finite")
         check(lib.crick_tdigest_update(self._h, xd.ptr, None, wv, n, 1, 0, eff, stream), "update")
+        release_views((xd,), stream)
 
     def merge(self, *args):
         """merge(self, *args)
@@ -576,15 +592,17 @@ class TDigestGroup:
         weights : scalar, or an array shaped like ``values``.
         """
         ng = len(self)
-        vd = device_view(values)
+        vd = device_view(values, stream)
         if vd is not None:
-            if vd.dtype != np.float64:
-                raise TypeError("values must be float64 when given as a CUDA array")
+            vd = as_f64_device(vd, stream)
             wptr, wsc = None, 1.0
-            wd = device_view(weights)
+            wd = device_view(weights, stream)
             if wd is not None:
-                if wd.dtype != np.float64 or wd.size != vd.size:
-                    raise TypeError("weights must be a float64 CUDA array shaped like values")
+                wd = as_f64_device(wd, stream)
+                if wd.size != vd.size:
+                    raise TypeError("weights must be a CUDA array shaped like values")
+                if check(lib.crick_check_weights(wd.ptr, wd.size, stream), "check weights"):
+                    raise ValueError("w must be > 0 and finite")
                 wptr = wd.ptr
             else:
                 wsc = _as_double(weights, "weights")
@@ -595,12 +613,14 @@ class TDigestGroup:
                     raise ValueError("values must have shape (n_groups, row_len)")
                 check(lib.crick_tdigest_group_update(self._h, vd.ptr, wptr, wsc, None, vd.shape[1],
                                                      vd.shape[1], 1, stream), "group update")
+                release_views((vd, wd), stream)
             else:
-                od = device_view(offsets)
+                od = device_view(offsets, stream)
                 if od is None or od.dtype != np.int64 or od.size != ng + 1:
                     raise TypeError("offsets must be an int64 CUDA array of n_groups + 1 entries")
                 check(lib.crick_tdigest_group_update(self._h, vd.ptr, wptr, wsc, od.ptr, 0, 0, 1,
                                                      stream), "group update")
+                release_views((vd, wd, od), stream)
             return
         v = np.asarray(values)
         if not np.can_cast(v.dtype, "f8", casting="safe"):

@@ -33,6 +33,7 @@ typedef struct crick_tdigest crick_tdigest_t;
 typedef struct crick_tdigest_group crick_tdigest_group_t;
 typedef struct crick_stats crick_stats_t;
 typedef struct crick_spsv crick_spsv_t;
+typedef struct crick_p2p crick_p2p_t;
 
 /* ---- library ---------------------------------------------------------- */
 const char *crick_last_error(void);
@@ -41,6 +42,7 @@ const char *crick_version(void);
 int crick_device_count(void);
 int crick_set_device(int device);
 int crick_sm_count(void);
+int crick_get_device(void);
 /* kernels launched by this library since load (all threads) -- bench.py's gpu_launches */
 int64_t crick_launch_count(void);
 /* per-launch CUDA-event timing of the hot kernel (k_bin_accumulate), on the stream it is
@@ -62,6 +64,13 @@ int crick_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *s
 int crick_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
 int crick_stream_synchronize(void *stream);
 int crick_device_synchronize(void);
+/* Safe cast of a contiguous CUDA array to float64 (what the reference's NpyIter does on the host,
+ * tdigest_stubs.c:652-666, for every dtype np.can_cast(dtype, 'f8', 'safe') allows): kind 'f'
+ * (2 / 4 / 8 bytes), 'i' or 'u' (1 / 2 / 4 / 8 bytes), 'b' (bool).  Asynchronous on `stream`. */
+int crick_cast_to_f64(const void *src_dev, int kind, int itemsize, int64_t n, double *dst_dev, void *stream);
+/* the wrapper's weight check (tdigest.pyx:304-305) for weights that live on the device: 1 if some
+ * weight is not finite or not > 0, else 0 (synchronises `stream`) */
+int crick_check_weights(const double *w_dev, int64_t n, void *stream);
 /* synthetic counter-based streams for benchmarks/tests: element i depends only on
  * (seed, offset + i).  kind 0 lognormal(0,1) + U(.5,1.5) weights, 1 uniform, 2 normal,
  * 3 zipf(1.1)-like integers.  w_dev may be NULL. */
@@ -101,7 +110,28 @@ int crick_tdigest_update_checked(crick_tdigest_t *t, const double *x, const doub
  * multi-GPU step enqueue update -> export -> all-gather -> merge as one chain. */
 int crick_tdigest_update_deferred(crick_tdigest_t *t, const double *x, const double *w,
                                   double w_scalar, int64_t n, int mode, void *stream);
-int crick_tdigest_take_bad_weights(crick_tdigest_t *t);
+int crick_tdigest_take_bad_weights(crick_tdigest_t *t);   /* bit 0 bad weights, bit 1 exchange timeout */
+/* ---- one stream sharded over the GPUs of a node: update + exchange + merge over peer memory -----
+ * Every rank (one process per GPU) owns an exchange buffer of crick_p2p_buffer_bytes() bytes
+ * (crick_p2p_alloc: plain cudaMalloc, zeroed), exports it with crick_ipc_get_handle (64 bytes, sent
+ * to the other ranks by whatever transport the caller has), opens the others' handles with
+ * crick_ipc_open_handle and builds a communicator from the `world` pointers (buffers[rank] = own).
+ * crick_tdigest_update_exchange is COLLECTIVE: every rank calls it the same number of times with
+ * its shard (device-resident; n = 0 or >= CRICK_PARALLEL_MIN); afterwards `t` on every rank has
+ * absorbed ALL ranks' shards (identical digests).  One kernel per rank stores the rank's bucket
+ * points into every rank's buffer over NVLink, waits for the others' and merges: no collective
+ * library call, no host synchronisation.  Weights are validated like update_deferred
+ * (crick_tdigest_take_bad_weights: bit 0 = bad weights, bit 1 = a rank did not arrive in 4 s). */
+int64_t crick_p2p_buffer_bytes(double compression, int world);
+void *crick_p2p_alloc(int64_t bytes);
+void crick_p2p_free(void *p);
+int crick_ipc_get_handle(void *dev_ptr, void *handle64);
+void *crick_ipc_open_handle(const void *handle64);
+int crick_ipc_close_handle(void *p);
+crick_p2p_t *crick_p2p_new(int rank, int world, void *const *buffers);
+void crick_p2p_destroy(crick_p2p_t *c);
+int crick_tdigest_update_exchange(crick_tdigest_t *t, crick_p2p_t *c, const double *x, const double *w,
+                                  double w_scalar, int64_t n, void *stream);
 /* Parallel-mode update with the SummaryStats moments of x (count 1 per element, NaN skipped:
  * stats_update_ndarray, stats_stubs.c:199-210) accumulated into `stats` IN THE SAME PASS over
  * the data.  n >= CRICK_PARALLEL_MIN.  bad_weights may be NULL (no weight validation). */
@@ -142,6 +172,10 @@ int crick_tdigest_set_state(crick_tdigest_t *t, const double *centroids, int n,
 int crick_tdigest_reset(crick_tdigest_t *t, void *stream);
 /* test hook: bucket edges chosen by the last parallel-mode update (returns their count) */
 int crick_tdigest_debug_edges(crick_tdigest_t *t, double *out, int max_out);
+/* test hook: the 256-byte header block of the parallel scratch (lookup parameters, sticky flags, and
+ * from byte 128 the globaltimer timestamps of the last k_exchange_merge: start, partials ready,
+ * points stored, flags published, all ranks arrived, done) */
+int crick_tdigest_debug_header(crick_tdigest_t *t, void *out256);
 /* test hook: per-bucket (sum w, sum w*x) and (min, max) of the last parallel-mode update,
  * reduced in the kernel's own order (returns the bucket count = edges + 1) */
 int crick_tdigest_debug_buckets(crick_tdigest_t *t, double *out_w, double *out_s,

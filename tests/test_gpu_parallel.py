@@ -272,6 +272,41 @@ def test_deferred_weight_check_needs_no_sync_and_is_sticky(cb):
     assert t4.size() == 0 and len(t4.centroids()) == 0
 
 
+def test_sharded_update_over_peer_memory_world1(cb):
+    """ShardedTDigest (k_exchange_merge) with one rank: the exchange degenerates to the rank's own
+    buffer, and the digest must be the one the plain parallel update of the same data gives in
+    size / min / max, with a rank error no worse than the reference's."""
+    from crick_b200.distributed import ShardedTDigest
+    rng = np.random.default_rng(21)
+    n = 600000
+    x = rng.lognormal(size=n)
+    w = rng.uniform(0.5, 1.5, n)
+    dx, dw = cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w)
+    sh = ShardedTDigest(100)
+    t = sh.update(dx, dw)
+    rank = weighted_rank_fn(x, w)
+    ref = oracle.reference.TDigest(100) if oracle.reference is not None else R.TDigest(100)
+    ref.update(x, w)
+    e_ref = np.abs(rank(ref.quantile(QS9)) - QS9).max()
+    assert t.min() == x.min() and t.max() == x.max()
+    assert abs(t.size() - w.sum()) <= 1e-12 * w.sum()
+    assert np.abs(rank(t.quantile(QS9)) - QS9).max() <= max(e_ref, 3e-4)
+    c1 = t.centroids().copy()
+    # a second step accumulates; unweighted; an empty shard still takes part in the exchange
+    sh.update(dx)
+    sh.update(cb.DeviceArray((0,)))
+    assert abs(sh.digest.size() - (w.sum() + n)) <= 1e-12 * (w.sum() + n)
+    # bad weights: the step contributes nothing and the verdict surfaces later
+    sh2 = ShardedTDigest(100)
+    sh2.update(dx, dw)
+    wb = w.copy(); wb[5] = -1.0
+    sh2.update(dx, cb.DeviceArray.from_numpy(wb))
+    with pytest.raises(ValueError):
+        sh2.digest.centroids()
+    assert sh2.digest.centroids().tobytes() == c1.tobytes()
+    sh.close(); sh2.close()
+
+
 def test_fused_moments_in_the_same_pass(cb):
     """north_star: SummaryStats moments fused into the t-digest pass.  The digest must be the one
     the plain update builds (bit for bit) and the moments must match the stand-alone stats pass

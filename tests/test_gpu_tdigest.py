@@ -439,6 +439,72 @@ def test_merge_all_one_pass_vs_the_exact_tree(cb, ngroups, per, comp):
     assert (np.diff(fast.quantile(np.linspace(0, 1, 101))) >= 0).all()
 
 
+def test_cuda_array_inputs_of_other_libraries_and_dtypes(cb):
+    """tdigest.pyx:298-305 for CUDA arrays: every dtype that casts safely to float64 is accepted
+    (cast on the device), device weights are validated in reference mode too, inputs produced
+    asynchronously on another stream are waited for, and the outputs travel by DLPack."""
+    import torch
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=1500)
+    # (a) dtypes: float32 / float16 / int64 / int32 / uint8 / bool tensors == their host versions
+    for dt in (np.float32, np.float16, np.int64, np.int32, np.uint8, np.bool_):
+        h = (x * 10).astype(dt)
+        t1, t2 = cb.TDigest(100, mode="reference"), cb.TDigest(100, mode="reference")
+        t1.update(torch.from_numpy(h).cuda())
+        t2.update(h)
+        assert t1.centroids().tobytes() == t2.centroids().tobytes(), dt
+    big = rng.lognormal(size=300000).astype(np.float32)
+    t1, t2 = cb.TDigest(100), cb.TDigest(100)
+    t1.update(torch.from_numpy(big).cuda(), torch.ones(big.size, dtype=torch.float32, device="cuda"))
+    t2.update(big.astype(np.float64), np.ones(big.size))
+    assert t1.centroids().tobytes() == t2.centroids().tobytes()
+    with pytest.raises(TypeError):
+        cb.TDigest().update(torch.zeros(10, dtype=torch.complex64, device="cuda"))
+    # (b) device weights in reference mode are checked like host weights
+    t = cb.TDigest(100, mode="reference")
+    xd = torch.from_numpy(x).cuda()
+    for bad in (0.0, -1.0, float("nan"), float("inf")):
+        w = torch.ones(x.size, dtype=torch.float64, device="cuda")
+        w[7] = bad
+        with pytest.raises(ValueError):
+            t.update(xd, w)
+    assert t.size() == 0
+    t.update(xd, torch.full((x.size,), 2.0, dtype=torch.float64, device="cuda"))
+    assert t.size() == 2 * x.size
+    # (c) producer on a side stream, no stream= passed: the update must see the finished data
+    side = torch.cuda.Stream()
+    ref = cb.TDigest(100)
+    for rep in range(20):
+        with torch.cuda.stream(side):
+            a = torch.empty(1 << 20, dtype=torch.float64, device="cuda")
+            a.normal_(generator=None)
+            a.mul_(3.0).add_(float(rep))
+        # without waiting for `side` here: DLPack hands the ordering to the library
+        d = cb.TDigest(100)
+        with torch.cuda.stream(side):
+            d.update(a)
+        host = a.cpu().numpy()
+        assert d.min() == host.min() and d.max() == host.max() and d.size() == host.size
+        with torch.cuda.stream(side):
+            d2 = cb.TDigest(100)
+            d2.update(a, stream=side.cuda_stream)
+        side.synchronize()
+        assert d2.centroids().tobytes() == d.centroids().tobytes()
+    # (d) DLPack export: DeviceArray and the zero-copy centroid view
+    arr = cb.DeviceArray.from_numpy(x)
+    tt = torch.from_dlpack(arr)
+    assert tt.is_cuda and tt.dtype == torch.float64 and np.array_equal(tt.cpu().numpy(), x)
+    del arr
+    assert np.array_equal(tt.cpu().numpy(), x)              # the capsule keeps the buffer alive
+    d = cb.TDigest(100)
+    d.update(x)
+    cv = torch.from_dlpack(d.centroids_device())
+    c = d.centroids()
+    assert cv.shape == (len(c), 2) and np.array_equal(cv.cpu().numpy(), c.view(np.float64).reshape(-1, 2))
+    q = d.quantile(torch.tensor([0.1, 0.5, 0.9], dtype=torch.float32, device="cuda"))   # float32 queries
+    assert np.allclose(torch.from_dlpack(q).cpu().numpy(), d.quantile(np.array([0.1, 0.5, 0.9], dtype=np.float32)))
+
+
 def test_large_query_batch_vs_oracle(cb):
     """Config-4 query shape: millions of device-resident queries, bit-exact vs the oracle, plus
     the size-independent properties (monotone, cdf(quantile(q)) ~ q)."""
