@@ -130,6 +130,8 @@ struct ParLayout {
     double* cw;          // [kSMax]
     double* sx2;         // [kSMax] merged (sorted) sample when it spans several runs
     double* sw2;         // [kSMax]
+    double2* tmin;       // [kSMax] per-thread minimum / maximum of the tail oversampling draws
+    double2* tmax;       // [kSMax]
     double2* partial;    // [ncta_max * kBPad]
     double2* minmax;     // [ncta_max]
     unsigned char* fin;  // finalize workspace (global fallback)
@@ -161,6 +163,7 @@ size_t parallel_scratch_bytes(double comp, int sm_count) {
     size_t b = 256;
     b += sizeof(double) * kEMax + kTabBytes;
     b += 5 * sizeof(double) * kSMax;
+    b += 2 * sizeof(double2) * kSMax;
     b += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     b += sizeof(double2) * (size_t)(2 * sm_count);
     b += fin_ws_bytes(cap, mmax_for(comp)) + 64;
@@ -178,6 +181,8 @@ static ParLayout carve(void* scratch, double comp, int sm_count) {
     L.cw = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.sx2 = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
     L.sw2 = reinterpret_cast<double*>(p); p += sizeof(double) * kSMax;
+    L.tmin = reinterpret_cast<double2*>(p); p += sizeof(double2) * kSMax;
+    L.tmax = reinterpret_cast<double2*>(p); p += sizeof(double2) * kSMax;
     L.partial = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count) * kBPad;
     L.minmax = reinterpret_cast<double2*>(p); p += sizeof(double2) * (size_t)(2 * sm_count);
     L.fin = p;
@@ -237,12 +242,34 @@ __device__ __forceinline__ void sample_one(const double* __restrict__ X, const d
 //                 binary searches (ties: lower run first, so the order is total and fixed), then
 //                 scatters the pair to its final place.
 // (r1_q launch list: the previous 15-launch global bitonic network took 73 us of a 195 us setup.)
+// Tail oversampling.  The edges at the ends of the k-scale grid sit at q_j = sin^2(pi j / (2 ov c)):
+// 6e-5 for c = 100, 2.5e-6 for c = 500 -- below the resolution 1 / S = 6e-5 of the sample, so the
+// first / last buckets would all collapse onto the smallest / largest sampled value and the far
+// tails (what a t-digest is bought for) would be one centroid.  Next to the S / 1024 sorting CTAs
+// the sampling launch therefore runs kTailGroups more CTAs (on other SMs, 128 threads each): a
+// group draws kTailGroupDraws = 2048 more values -- a second sample of 256 Ki values in all -- and
+// keeps its kTailKeep smallest and largest.  Below t* = the smallest of the groups' kTailKeep-th
+// smallest values EVERY draw of the big sample is among the kept ones (a group holding more than
+// kTailKeep of them is a 1e-6 event), so the kept values below t* are the lower end of a sample 16
+// times denser than the main one; k_make_edges reads the grid points out there from it.  Same on
+// the upper side.
+constexpr int kTailDraws = 16;          // the big sample has kTailDraws * S values
+constexpr int kTailGroups = 128;        // CTAs (= groups) of the big sample
+constexpr int kTailThreads = 256;       // active threads per group
+constexpr int kTailPerThread = 8;       // draws per thread (all loads in flight, no spills at 64 registers)
+constexpr int kTailKeep = 4;            // smallest / largest values kept per group
+constexpr int kTailCap = kTailGroups * kTailKeep;   // 512 candidates per side
+constexpr long kTailMinN = 1L << 22;
+static_assert((long)kTailGroups * kTailThreads * kTailPerThread == kTailDraws * kSMax, "the big sample is kTailDraws x the main one");
+
 template <bool SAMPLE>
 __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ keys,
                                                           double* __restrict__ vals,
                                                           const double* __restrict__ X,
                                                           const double* __restrict__ W, double wsc,
-                                                          long n, long S, ParHeader* hdr) {
+                                                          long n, long S, ParHeader* hdr,
+                                                          double2* __restrict__ tmin,
+                                                          double2* __restrict__ tmax) {
     // one (key, source index) pair per thread in registers; compare-exchange partners at
     // distance < 32 come by shuffle, the others through a double-buffered shared array (one
     // barrier per stage).  Order: (key, index), so ties are deterministic.
@@ -253,6 +280,90 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
     const long base = (long)blockIdx.x * kSortChunk;
     if (SAMPLE && blockIdx.x == 0 && t == 0) hdr->S = S;
     double key, val;
+    if (SAMPLE && (long)blockIdx.x >= S / kSortChunk) {
+        // a tail oversampling group: 128 threads x 16 draws, all loads in flight; every thread keeps
+        // the minimum and maximum of its draws, the group its kTailKeep smallest minima and largest
+        // maxima (ranked by counting: ties by thread index), written in order
+        __shared__ double2 s_mn[(kTailThreads / 32) * kTailKeep], s_mx[(kTailThreads / 32) * kTailKeep];
+        if (t >= kTailThreads) return;
+        const long g = (long)blockIdx.x - S / kSortChunk;                         // group 0 .. kTailGroups - 1
+        // draw i of the big sample comes from segment i of n / S2 values at a hashed offset
+        // (multiply-shift instead of sample_one's 64-bit modulo: no host mirror to agree with)
+        const long seg2 = n / (S * kTailDraws);                                   // >= 1 (n >= kTailMinN)
+        const unsigned seg32 = seg2 > 0xffffffffl ? 0xffffffffu : (unsigned)seg2;
+        double xs_[kTailPerThread], ws_[kTailPerThread];
+#pragma unroll
+        for (int e = 0; e < kTailPerThread; ++e) {
+            const long i = (g * kTailThreads + t) * kTailPerThread + e;
+            const long pos = i * seg2 + (long)__umulhi((unsigned)(mix64((unsigned long long)i) >> 32), seg32);
+            const double xv = X[pos], wv = W ? W[pos] : wsc;
+            const bool okv = is_finite_d(xv) && !(wv <= DBL_EPSILON);
+            xs_[e] = okv ? xv + 0.0 : INFINITY;
+            ws_[e] = okv ? wv : 0.0;
+        }
+        double2 mn = make_double2(INFINITY, 0.0), mx = make_double2(-INFINITY, 0.0);
+#pragma unroll
+        for (int e = 0; e < kTailPerThread; ++e) {
+            if (ws_[e] > 0.0) {                    // (rejected draws come back as (+inf, 0))
+                if (xs_[e] < mn.x) mn = make_double2(xs_[e], ws_[e]);
+                if (xs_[e] > mx.x) mx = make_double2(xs_[e], ws_[e]);
+            }
+        }
+        // the kTailKeep smallest minima / largest maxima: per warp by kTailKeep rounds of a shuffle
+        // reduction on (value, lane) -- the winner drops out --, then the same over the warps'
+        // winners.  Ties fall to the lower lane / warp: deterministic.
+        const int lane = t & 31, wid = t >> 5;
+        auto select = [&](double2 mine, bool low, double2* s_out) {
+            double2 cand = mine;
+            for (int r = 0; r < kTailKeep; ++r) {
+                double bx = low ? cand.x : -cand.x;                    // minimise bx
+                int bl = lane;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const double ox = shfl_xor_d(bx, d);
+                    const int ol = __shfl_xor_sync(CRICK_FULL, bl, d);
+                    if (ox < bx || (ox == bx && ol < bl)) { bx = ox; bl = ol; }
+                }
+                const double wx = shfl_d(cand.x, bl), ww_ = shfl_d(cand.y, bl);
+                if (lane == 0) s_out[wid * kTailKeep + r] = make_double2(wx, ww_);
+                if (lane == bl) cand = make_double2(low ? INFINITY : -INFINITY, 0.0);
+            }
+        };
+        select(mn, true, s_mn);
+        select(mx, false, s_mx);
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // (the other 768 threads have left)
+        if (wid == 0) {
+            // 8 warps x kTailKeep winners = 32 candidates: one per lane, same selection once more
+            double2 a = s_mn[lane], b2 = s_mx[lane];
+            double2 cand = a;
+            for (int r = 0; r < kTailKeep; ++r) {
+                double bx = cand.x; int bl = lane;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const double ox = shfl_xor_d(bx, d);
+                    const int ol = __shfl_xor_sync(CRICK_FULL, bl, d);
+                    if (ox < bx || (ox == bx && ol < bl)) { bx = ox; bl = ol; }
+                }
+                const double wx = shfl_d(cand.x, bl), ww_ = shfl_d(cand.y, bl);
+                if (lane == 0) tmin[g * kTailKeep + r] = make_double2(wx, ww_);   // (+inf, 0): fewer valid draws
+                if (lane == bl) cand = make_double2(INFINITY, 0.0);
+            }
+            cand = b2;
+            for (int r = 0; r < kTailKeep; ++r) {
+                double bx = -cand.x; int bl = lane;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const double ox = shfl_xor_d(bx, d);
+                    const int ol = __shfl_xor_sync(CRICK_FULL, bl, d);
+                    if (ox < bx || (ox == bx && ol < bl)) { bx = ox; bl = ol; }
+                }
+                const double wx = shfl_d(cand.x, bl), ww_ = shfl_d(cand.y, bl);
+                if (lane == 0) tmax[g * kTailKeep + r] = make_double2(wx, ww_);
+                if (lane == bl) cand = make_double2(-INFINITY, 0.0);
+            }
+        }
+        return;
+    }
     if (SAMPLE) {
         sample_one(X, W, wsc, n, S, base + t, key, val);
     } else {
@@ -343,7 +454,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const double* __re
 
 // Sorts S pairs (S a power of two >= kSortChunk).  The sorted pairs end up in (*skeys, *svals):
 // the input arrays when S is one run, else (keys2, vals2).
-struct SampleSrc { const double* X; const double* W; double wsc; long n; ParHeader* hdr; };
+struct SampleSrc { const double* X; const double* W; double wsc; long n; ParHeader* hdr; double2* tmin; double2* tmax; };
 static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double* vals2, long S,
                                const SampleSrc* src, cudaStream_t st, const double** skeys,
                                const double** svals) {
@@ -351,10 +462,11 @@ static cudaError_t sort_sample(double* keys, double* vals, double* keys2, double
     cudaError_t e;
     count_launch();
     if (src)
-        k_sort_runs<true><<<nrun, kSortChunk, 0, st>>>(keys, vals, src->X, src->W, src->wsc, src->n, S,
-                                                       src->hdr);
+        k_sort_runs<true><<<src->tmin ? nrun + kTailGroups : nrun, kSortChunk, 0, st>>>(
+            keys, vals, src->X, src->W, src->wsc, src->n, S, src->hdr, src->tmin, src->tmax);
     else
-        k_sort_runs<false><<<nrun, kSortChunk, 0, st>>>(keys, vals, nullptr, nullptr, 0.0, 0, S, nullptr);
+        k_sort_runs<false><<<nrun, kSortChunk, 0, st>>>(keys, vals, nullptr, nullptr, 0.0, 0, S, nullptr,
+                                                        nullptr, nullptr);
     *skeys = keys; *svals = vals;
     if (nrun > 1) {
         const size_t msm = (size_t)S * 8;
@@ -431,7 +543,8 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
                                                      const double* __restrict__ sw,
                                                      double* __restrict__ edges,
                                                      unsigned short* __restrict__ tab, double comp,
-                                                     int ov, long S) {
+                                                     int ov, long S, const double2* __restrict__ tmin,
+                                                     const double2* __restrict__ tmax) {
     // dynamic shared memory: cw[S] cumulative sample weights | the candidate table of each grid
     // static: s_buf = raw edges + dedupe counts (phases b-c), then the per-cell counts (phase d)
     __shared__ __align__(16) unsigned char s_buf[(kTabLen + 6) * 4];
@@ -502,19 +615,139 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     const double Wt = CW(S - 1);
     const int c = (int)ceil(comp);
     const int E0 = ov * c - 1;
-    // b. raw edges at the k-scale grid
-    for (int j = tid; j < E0; j += blockDim.x) {
-        double kq = (double)(j + 1) / (double)ov;                 // k in (0, c)
-        double sn = sin(CRICK_PI_2 * kq / comp);
-        double q = sn * sn;                                        // k^-1(kq)
-        if (q > 1.0) q = 1.0;
-        double target = q * Wt;
-        long lo = 0, hi = S - 1;                                   // first i with cw[i] >= target
-        while (lo < hi) {
-            long mid = (lo + hi) >> 1;
-            if (CW(mid) < target) lo = mid + 1; else hi = mid;
+    // a'. tail oversampling (see k_sort_runs): the groups' kept values beyond t*, sorted, with
+    // their cumulative weights.  Lists live where the lookup tables of phase d will be (s_tab
+    // region, 33 KB): x[512] | cw[512] per side.  Ranking is an O(n^2) count over the 512
+    // candidates of a side (broadcast reads), the cumulative weights one block scan in rank order.
+    __shared__ int s_tn[2];                 // candidates per side (0 = no refinement there)
+    double* t_x = reinterpret_cast<double*>(s_tab);          // [2][kTailCap] sorted values (hi side: descending)
+    double* t_cw = t_x + 2 * kTailCap;                       // [2][kTailCap] inclusive cumulative weights
+    const bool tails = tmin != nullptr && S == kSMax;
+    if (tails) {
+        double* c_x = t_cw + 2 * kTailCap;                   // unsorted candidates, same region (4 x 8 KB <= 2 tables)
+        double* c_w = c_x + 2 * kTailCap;
+        static_assert(8 * kTailCap * sizeof(double) <= 2 * kTabBytes, "tail lists must fit the table region");
+        // thread i < 512: low-side candidate i, else high-side candidate i - 512; t* = the least
+        // extreme of the groups' kTailKeep-th values (a group with fewer valid draws holds +-inf
+        // there: then nothing is refined on that side)
+        __shared__ double s_tstar[2];
+        {
+            const int side = tid >> 9, i = tid & (kTailCap - 1);
+            const double2 a = side ? tmax[i] : tmin[i];
+            c_x[tid] = a.x; c_w[tid] = a.y;
+            double lim = INFINITY;                           // low: min of the kept-th smallest; high: max of the kept-th largest, negated
+            if ((i & (kTailKeep - 1)) == kTailKeep - 1) lim = a.y > 0.0 ? (side ? -a.x : a.x) : -INFINITY;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) lim = fmin(lim, shfl_xor_d(lim, d));
+            if ((tid & 31) == 0) s_wd[tid >> 5] = lim;
         }
-        s_raw[j] = sx[lo];
+        __syncthreads();
+        if (tid < 2) {
+            double lim = INFINITY;
+            for (int k = 0; k < 16; ++k) lim = fmin(lim, s_wd[tid * 16 + k]);
+            s_tstar[tid] = lim;                              // [1] is the NEGATED upper threshold
+        }
+        __syncthreads();
+        {
+            // keep the candidates beyond t*, compacted in index order (ballot + warp offsets), then
+            // rank them by counting: only the kept ones (~100 per side) take part
+            __shared__ int s_wcnt[32];
+            const int side = tid >> 9, lane = tid & 31, wid = tid >> 5;
+            const double xv = c_x[tid], wv = c_w[tid];
+            const bool in = wv > 0.0 && (side ? -xv < s_tstar[1] : xv < s_tstar[0]);
+            const unsigned bal = __ballot_sync(CRICK_FULL, in);
+            if (lane == 0) s_wcnt[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int k = side * 16; k < side * 16 + 16; ++k) { const int cnt_k = s_wcnt[k]; before += k < wid ? cnt_k : 0; total += cnt_k; }
+            if (tid == 0 || tid == kTailCap) s_tn[side] = total;
+            __syncthreads();                                   // every thread has read its candidate
+            if (in) {
+                const int at = side * kTailCap + before + __popc(bal & ((1u << lane) - 1u));
+                t_x[at] = xv; t_cw[at] = wv;                   // (compacted, unsorted: t_x / t_cw as staging)
+            }
+        }
+        __syncthreads();
+        const int nl = s_tn[0], nh = s_tn[1];
+        {
+            const int side = tid >> 9, i = tid & (kTailCap - 1);          // threads 0-511: low side, 512-1023: high
+            const int nn = side ? nh : nl;
+            if (i < nn) {
+                const double xi = t_x[side * kTailCap + i], wi = t_cw[side * kTailCap + i];
+                int rank = 0;
+                for (int o = 0; o < nn; ++o) {
+                    const double xo = t_x[side * kTailCap + o], wo = t_cw[side * kTailCap + o];
+                    // low side ascending, high side descending; ties by weight, then list position
+                    // (entries that tie in both are interchangeable)
+                    const bool first = (side ? xo > xi : xo < xi) ||
+                                       (xo == xi && (wo < wi || (wo == wi && o < i)));
+                    rank += first ? 1 : 0;
+                }
+                c_x[side * kTailCap + rank] = xi;
+                c_w[side * kTailCap + rank] = wi;
+            }
+        }
+        __syncthreads();
+        {
+            const int side = tid >> 9, i = tid & (kTailCap - 1);
+            const bool live = i < (side ? nh : nl);
+            t_x[tid] = live ? c_x[tid] : 0.0;                  // sorted values; weights follow through the scan
+            t_cw[tid] = live ? c_w[tid] : 0.0;
+        }
+        __syncthreads();
+        {
+            // inclusive cumulative weights in rank order (one scan over [low | high], fixed association)
+            const int side = tid >> 9, i = tid & (kTailCap - 1);
+            const double wv = i < (side ? nh : nl) ? t_cw[tid] : 0.0;
+            const double incl = block_scan_incl<double>(wv, s_wd);
+            __shared__ double s_lo_total;
+            if (tid == kTailCap - 1) s_lo_total = incl;
+            __syncthreads();
+            t_cw[tid] = side ? incl - s_lo_total : incl;
+        }
+        __syncthreads();
+    } else if (tid < 2) {
+        s_tn[tid] = 0;
+    }
+    __syncthreads();
+    // b. raw edges at the k-scale grid
+    {
+        const int nl = s_tn[0], nh = s_tn[1];
+        // the dense tail sample stands for kTailDraws * S draws: its expected total weight is
+        // kTailDraws * Wt; it is trusted up to 70 % of what it covers
+        const double lim_lo = nl ? 0.7 * t_cw[nl - 1] : 0.0, lim_hi = nh ? 0.7 * t_cw[kTailCap + nh - 1] : 0.0;
+        int r_lo = 0, r_hi = 0;                  // the innermost list entries a grid point can be given
+        if (nl) { int lo = 0, hi = nl - 1; while (lo < hi) { int mid = (lo + hi) >> 1; if (t_cw[mid] < lim_lo) lo = mid + 1; else hi = mid; } r_lo = lo; }
+        if (nh) { int lo = 0, hi = nh - 1; while (lo < hi) { int mid = (lo + hi) >> 1; if (t_cw[kTailCap + mid] < lim_hi) lo = mid + 1; else hi = mid; } r_hi = lo; }
+        for (int j = tid; j < E0; j += blockDim.x) {
+            double kq = (double)(j + 1) / (double)ov;                 // k in (0, c)
+            double sn = sin(CRICK_PI_2 * kq / comp);
+            double q = sn * sn;                                        // k^-1(kq)
+            if (q > 1.0) q = 1.0;
+            const double tl = q * Wt * (double)kTailDraws, th = (1.0 - q) * Wt * (double)kTailDraws;
+            if (nl && tl <= lim_lo) {
+                int lo = 0, hi = nl - 1;                               // first r with t_cw[r] >= tl
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (t_cw[mid] < tl) lo = mid + 1; else hi = mid; }
+                s_raw[j] = t_x[lo];
+            } else if (nh && th <= lim_hi) {
+                int lo = 0, hi = nh - 1;                               // from the top: first r with cw >= th
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (t_cw[kTailCap + mid] < th) lo = mid + 1; else hi = mid; }
+                s_raw[j] = t_x[kTailCap + lo];
+            } else {
+                double target = q * Wt;
+                long lo = 0, hi = S - 1;                               // first i with cw[i] >= target
+                while (lo < hi) {
+                    long mid = (lo + hi) >> 1;
+                    if (CW(mid) < target) lo = mid + 1; else hi = mid;
+                }
+                // keep the raw edges monotone next to the refined tails: nothing from the main
+                // sample may lie beyond the innermost value the tail lists can hand out
+                double e = sx[lo];
+                if (nl) e = fmax(e, t_x[r_lo]);
+                if (nh) e = fmin(e, t_x[kTailCap + r_hi]);
+                s_raw[j] = e;
+            }
+        }
     }
     __syncthreads();
     // c. dedupe; a value chosen more than once is "heavy" and gets [v, nextafter(v))
@@ -2332,6 +2565,11 @@ long parallel_sample_len(long n) {
     return S;
 }
 
+static bool tail_sampling_enabled() {
+    static const bool on = [] { const char* e = getenv("CRICK_TAIL_SAMPLE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, const SampleSrc* src,
                                      cudaStream_t st) {
     const double *skeys, *svals;
@@ -2341,8 +2579,10 @@ static cudaError_t edges_from_sample(const BatchView& v, ParLayout& L, long S, c
     e = need_smem(k_make_edges, smem);
     if (e != cudaSuccess) return e;
     count_launch();
+    const bool tails = src != nullptr && src->tmin != nullptr;
     return launch_dep(k_make_edges, dim3(1), dim3(1024), smem, st, L.hdr, skeys, svals, L.edges, L.tab,
-                      v.comp, ov_for(v.comp), S);
+                      v.comp, ov_for(v.comp), S, tails ? (const double2*)src->tmin : (const double2*)nullptr,
+                      tails ? (const double2*)src->tmax : (const double2*)nullptr);
 }
 
 // host supplies ns (<= kSMax) sample pairs already copied into parallel_sample_x/w
@@ -2567,7 +2807,8 @@ cudaError_t launch_parallel_update(const BatchView& v, long d, const double* X, 
                                    bool defer_check) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     long S = sample_len(n);
-    SampleSrc src{X, W, wsc, n, L.hdr};
+    const bool tails = S == kSMax && n >= kTailMinN && tail_sampling_enabled();
+    SampleSrc src{X, W, wsc, n, L.hdr, tails ? L.tmin : nullptr, tails ? L.tmax : nullptr};
     cudaError_t e = edges_from_sample(v, L, S, &src, st);
     if (e != cudaSuccess) return e;
     e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, stats_parts, 0);
@@ -2607,7 +2848,8 @@ cudaError_t launch_parallel_update_exchange(const BatchView& v, long d, const do
     cudaError_t e = cudaSuccess;
     if (n > 0) {
         long S = sample_len(n);
-        SampleSrc src{X, W, wsc, n, L.hdr};
+        const bool tails = S == kSMax && n >= kTailMinN && tail_sampling_enabled();
+        SampleSrc src{X, W, wsc, n, L.hdr, tails ? L.tmin : nullptr, tails ? L.tmax : nullptr};
         e = edges_from_sample(v, L, S, &src, st);
         if (e != cudaSuccess) return e;
         e = accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, nullptr, 0);
