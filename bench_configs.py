@@ -58,6 +58,11 @@ def config3(B, cpu, ng_total=10**6, row=1000):
         g.update(d)
         g.flush()
         keep["g"] = g
+    import ctypes
+    nfb = ctypes.c_int64(0)
+    lib.crick_group_exact_fallbacks(ctypes.byref(nfb), 1)
+    run()
+    lib.crick_group_exact_fallbacks(ctypes.byref(nfb), 1)
     t = _timed(B, run, 2)
     g = keep["g"]
     bytes_per_digest = row * 8 + 2080                      # input + ~130 centroids out
@@ -65,7 +70,9 @@ def config3(B, cpu, ng_total=10**6, row=1000):
                        "(sharded by groups over %d GPU(s), no exchange)" % (ng_total, row, B.world),
            "value": ng_total * row / t / 1e9, "unit": "Gvalues/s", "ms": t * 1e3,
            "roofline_frac": ng * bytes_per_digest / t / 1e9 / B.peak,
-           "algorithmic_bytes_per_digest": bytes_per_digest}
+           "algorithmic_bytes_per_digest": bytes_per_digest,
+           "exact_kscale_fallbacks_per_pass": int(nfb.value),
+           "decision_margin": float(lib.crick_group_margin(float("nan")))}
     if B.rank == 0:
         R = _ref()
         rows = [0, 1, 7, ng // 3, ng // 2, ng - 1] + list(range(100, min(ng, 2100), 97))

@@ -33,6 +33,8 @@ _SIG = {
     "crick_launch_count": (c_int64, []),
     "crick_profile_enable": (c_int, [c_int]),
     "crick_group_kernel": (c_int, [c_int]),
+    "crick_group_margin": (c_double, [c_double]),
+    "crick_group_exact_fallbacks": (c_int, [_P, c_int]),
     "crick_stats_kernel": (c_int, [c_int]),
     "crick_profile_collect": (c_int, [_P, _P]),
     "crick_host_alloc": (_P, [c_int64]),

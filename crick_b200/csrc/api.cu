@@ -322,6 +322,15 @@ int crick_device_synchronize(void) {
 }
 int crick_profile_enable(int on) { profile_enable(on); return 0; }
 int crick_group_kernel(int mode) { return ingest_lanes_mode(mode); }
+double crick_group_margin(double margin) { return ingest_lanes_margin(margin); }
+int crick_group_exact_fallbacks(int64_t* out, int reset) {
+    if (!out) return fail("crick_group_exact_fallbacks: null out", cudaErrorInvalidValue);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long n = 0;
+    if (e == cudaSuccess) e = ingest_lanes_fallbacks(&n, reset != 0);
+    *out = (int64_t)n;
+    return e == cudaSuccess ? 0 : fail("crick_group_exact_fallbacks", e);
+}
 int crick_profile_collect(double* total_ms, int64_t* launches) {
     long long n = 0;
     int rc = profile_collect(total_ms, &n);

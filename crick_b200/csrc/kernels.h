@@ -17,6 +17,8 @@ cudaError_t launch_ingest(const BatchView& v, long ngroups, const double* X, con
 // thread-per-digest variant for many groups (tdigest_lanes.cu); same arguments and results
 bool ingest_lanes_wanted(long ngroups);
 int ingest_lanes_mode(int mode);   // -1 auto, 0 warp per digest, 1 thread per digest; returns previous
+double ingest_lanes_margin(double m);   // decision window of the thread-per-digest kernel; returns previous
+cudaError_t ingest_lanes_fallbacks(unsigned long long* out, bool reset);
 cudaError_t launch_ingest_lanes(const BatchView& v, long ngroups, const double* X, const double* W,
                                 double wsc, long sx, long sw, const long* offsets, long fixed_len,
                                 long row_stride, const long* dmap, int flags, cudaStream_t st,

@@ -54,6 +54,15 @@ int crick_profile_collect(double *total_ms, int64_t *launches);
  * one warp per digest; 1 always one thread per digest.  Results are bit-identical either way.
  * Returns the previous setting. */
 int crick_group_kernel(int mode);
+/* The thread-per-digest kernel decides "new centroid or fold" (tdigest_stubs.c:192-216) from a
+ * per-centroid weight window instead of an asin per item, and evaluates the reference's own
+ * k-scale pair only for cumulative weights inside the window (tdigest_lanes.cu, file comment).
+ * margin: half-width of the window in quantile units (default 6e-13; >= 1: every item exact;
+ * < 0: the kernel without the window).  NaN only queries.  Returns the previous value.
+ * crick_group_exact_fallbacks: items decided by the exact pair on the current device since the
+ * last reset (synchronises the device). */
+double crick_group_margin(double margin);
+int crick_group_exact_fallbacks(int64_t *out, int reset);
 /* pinned host memory for callers that want true async H2D (bench e2e leg) */
 void *crick_host_alloc(int64_t bytes);
 void crick_host_free(void *p);

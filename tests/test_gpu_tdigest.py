@@ -332,6 +332,51 @@ def test_grouped_ragged_weighted_and_incremental(cb, group_kernel):
     assert d.centroids().tobytes() == g.centroids(3).tobytes()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("margin", [6e-13, 1e-3, 0.2, 2.0, -1.0])
+def test_group_decision_window_is_exact_for_any_margin(cb, margin):
+    """The thread-per-digest kernel decides from a weight window and falls back to the reference's
+    kscale pair inside it (tdigest_lanes.cu).  Whatever the window -- the certified default, wide
+    ones that send a few percent / most / all items through the fallback, or the kernel without
+    windows (-1) -- every byte equals the warp-per-digest kernel (which evaluates every kscale),
+    and the fallback count moves as the window does."""
+    import ctypes
+    from crick_b200._lib import lib
+    rng = np.random.default_rng(5)
+    ng, row = 1500, 700
+    v = np.concatenate([rng.normal(size=(ng // 2, row)), rng.lognormal(0, 2, size=(ng - ng // 2, row))])
+    w = rng.uniform(0.5, 2.0, v.shape)
+    out = {}
+    nfb = ctypes.c_int64(0)
+    for mode, mg in ((0, 6e-13), (1, margin)):
+        prev = lib.crick_group_kernel(mode)
+        pm = lib.crick_group_margin(mg)
+        try:
+            lib.crick_group_exact_fallbacks(ctypes.byref(nfb), 1)
+            g = cb.TDigestGroup(ng, 100)
+            g.update(v, w)
+            g.update(v[:, ::-1].copy())            # unweighted second pass over existing centroids
+            g.flush()
+            lib.crick_group_exact_fallbacks(ctypes.byref(nfb), 1)
+            out[mode] = (g.meta().copy(), [g.centroids(r) for r in range(0, ng, 7)], nfb.value)
+        finally:
+            lib.crick_group_kernel(prev)
+            lib.crick_group_margin(pm)
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    for a, b in zip(out[0][1], out[1][1]):
+        assert a.tobytes() == b.tobytes()
+    assert out[0][2] == 0                           # the warp-per-digest kernel never counts
+    n_items = 2 * v.size
+    if margin == 6e-13:
+        assert out[1][2] < 1e-4 * n_items
+    elif margin == 1e-3:
+        assert 0 < out[1][2] < 2.0 * n_items
+    elif margin >= 0.2:
+        assert out[1][2] > 0.5 * n_items
+    else:
+        assert out[1][2] == 0
+
+
 @pytest.mark.parametrize("comp", [20, 100, 333.5, 1000])
 def test_group_kernels_agree_on_hostile_input(cb, comp):
     """Thread-per-digest vs warp-per-digest on the same input: NaN / inf (dropped, :285), +-0.0
