@@ -34,6 +34,17 @@ _SIG = {
     "crick_profile_enable": (c_int, [c_int]),
     "crick_group_kernel": (c_int, [c_int]),
     "crick_group_margin": (c_double, [c_double]),
+    "crick_stream_create": (_P, []),
+    "crick_stream_destroy": (None, [_P]),
+    "crick_comm_unique_id": (c_int, [_P]),
+    "crick_comm_init": (_P, [_P, c_int, c_int]),
+    "crick_comm_free": (None, [_P]),
+    "crick_comm_rank": (c_int, [_P]),
+    "crick_comm_world": (c_int, [_P]),
+    "crick_comm_allgather": (c_int, [_P, _P, _P, c_int64, _P]),
+    "crick_tdigest_allgather_merge": (c_int, [_P, _P, _P, c_int, _P]),
+    "crick_spsv_allgather_merge": (c_int, [_P, _P, _P, c_int, _P]),
+    "crick_stats_allgather_merge": (c_int, [_P, _P, _P, _P]),
     "crick_group_exact_fallbacks": (c_int, [_P, c_int]),
     "crick_stats_kernel": (c_int, [c_int]),
     "crick_profile_collect": (c_int, [_P, _P]),

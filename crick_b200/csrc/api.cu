@@ -181,6 +181,15 @@ int crick_set_device(int device) {
     return 0;
 }
 int crick_sm_count(void) { return sm_count(); }
+void* crick_stream_create(void) {
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { fail("cudaStreamCreate", e); return nullptr; }
+    return st;
+}
+void crick_stream_destroy(void* stream) {
+    if (stream) cudaStreamDestroy(static_cast<cudaStream_t>(stream));
+}
 int crick_get_device(void) {
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }

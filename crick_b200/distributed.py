@@ -302,6 +302,74 @@ class SketchAllReduce:
         return self.summary, None
 
 
+class NcclComm:
+    """The reduction without PyTorch: a NCCL communicator owned by libcrick_cuda (``crick_comm_*``,
+    NCCL opened with dlopen), one process per GPU.  Rank 0 calls ``NcclComm.unique_id()`` and ships
+    the 128 bytes to the other ranks by any means; every rank then constructs
+    ``NcclComm(id, rank, world)`` (collective) on its current device (``crick_set_device``).
+
+    ``reduce_tdigest`` / ``reduce_space_saving`` / ``reduce_stats`` leave, identically on every
+    rank, ``out.merge(sketch of rank 0, ..., sketch of rank world - 1)`` in ``out``: export ->
+    ncclAllGather -> merge kernel, three enqueues on ``stream`` and no host synchronisation."""
+
+    def __init__(self, unique_id, rank, world):
+        from ._lib import check_handle, lib
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes NcclComm.unique_id() returned on rank 0")
+        self.rank, self.world = int(rank), int(world)
+        self._h = None
+        self._h = check_handle(lib.crick_comm_init(bytes(unique_id), self.rank, self.world), "crick_comm_init")
+        self.stream = check_handle(lib.crick_stream_create(), "crick_stream_create")
+
+    @staticmethod
+    def unique_id():
+        import ctypes
+        from ._lib import check, lib
+        buf = ctypes.create_string_buffer(128)
+        check(lib.crick_comm_unique_id(buf), "crick_comm_unique_id")
+        return bytes(buf.raw)
+
+    def close(self):
+        from ._lib import lib
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.crick_stream_synchronize(self.stream)
+            lib.crick_comm_free(h)
+            lib.crick_stream_destroy(self.stream)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        from ._lib import check, lib
+        check(lib.crick_stream_synchronize(self.stream), "stream synchronize")
+
+    def reduce_tdigest(self, digest, out=None, exact=False, stream=None):
+        from ._lib import check, lib
+        out = TDigest(digest.compression) if out is None else out
+        check(lib.crick_tdigest_allgather_merge(digest._h, self._h, out._h, int(bool(exact)),
+                                                stream or self.stream), "crick_tdigest_allgather_merge")
+        return out
+
+    def reduce_space_saving(self, summary, out=None, exact=False, stream=None):
+        from ._lib import check, lib
+        from .space_saving import SpaceSaving
+        out = SpaceSaving(summary.capacity, summary.dtype) if out is None else out
+        check(lib.crick_spsv_allgather_merge(summary._h, self._h, out._h, int(bool(exact)),
+                                             stream or self.stream), "crick_spsv_allgather_merge")
+        return out
+
+    def reduce_stats(self, stats, out=None, stream=None):
+        from ._lib import check, lib
+        out = SummaryStats() if out is None else out
+        check(lib.crick_stats_allgather_merge(stats._h, self._h, out._h, stream or self.stream),
+              "crick_stats_allgather_merge")
+        return out
+
+
 def allgather_merge_stats(stats, group=None, backend_device="cuda"):
     """All-gather the 9-double SummaryStats records and merge them in rank order."""
     import torch

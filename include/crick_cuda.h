@@ -34,6 +34,7 @@ typedef struct crick_tdigest_group crick_tdigest_group_t;
 typedef struct crick_stats crick_stats_t;
 typedef struct crick_spsv crick_spsv_t;
 typedef struct crick_p2p crick_p2p_t;
+typedef struct crick_comm crick_comm_t;
 
 /* ---- library ---------------------------------------------------------- */
 const char *crick_last_error(void);
@@ -72,6 +73,9 @@ void crick_device_free(void *p);
 int crick_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
 int crick_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
 int crick_stream_synchronize(void *stream);
+/* a non-blocking stream on the current device, for callers with no other CUDA binding */
+void *crick_stream_create(void);
+void crick_stream_destroy(void *stream);
 int crick_device_synchronize(void);
 /* Safe cast of a contiguous CUDA array to float64 (what the reference's NpyIter does on the host,
  * tdigest_stubs.c:652-666, for every dtype np.can_cast(dtype, 'f8', 'safe') allows): kind 'f'
@@ -326,6 +330,33 @@ int64_t crick_spsv_size(crick_spsv_t *s);
 int64_t crick_spsv_capacity(crick_spsv_t *s);
 /* int64_counters walk, space_saving.pyx:368-386: out = k x (item, count, error); returns rows */
 int64_t crick_spsv_counters(crick_spsv_t *s, int64_t *out3, int64_t k);
+
+/* ---- multi-GPU reduction inside the library: one process per GPU, NCCL loaded with dlopen ----
+ * The reference has no multi-device path; its unit of reduction is merge(*others) of sketches
+ * (tdigest.pyx:310-324, space_saving.pyx:343-366, stats.pyx:128-142).  Here every rank exports its
+ * sketch as a fixed-size device record, one ncclAllGather moves the records over NVLink, and every
+ * rank merges them in rank order with the kernels merge() uses: three enqueues on `stream`, no
+ * host synchronisation, no PyTorch.  libnccl.so.2 (or $CRICK_NCCL_LIB) is opened on first use.
+ *
+ * crick_comm_unique_id: rank 0 obtains CRICK_COMM_ID_BYTES bytes and ships them to the other ranks
+ * by any means (file, socket, MPI); crick_comm_init is collective over all ranks, on each
+ * rank's current device.  *_allgather_merge leave in `out` (!= the input), identically on every
+ * rank, what out.merge(sketch of rank 0, ..., sketch of rank world-1) gives: exact != 0 through the
+ * reference's incremental merge, 0 through the one-pass k-way merge (*_merge_records_bulk).
+ * crick_comm_allgather is the raw collective on device buffers (recv = world x bytes_per_rank). */
+#define CRICK_COMM_ID_BYTES 128
+int crick_comm_unique_id(void *id_out);
+crick_comm_t *crick_comm_init(const void *id_bytes, int rank, int world);
+void crick_comm_free(crick_comm_t *c);
+int crick_comm_rank(crick_comm_t *c);
+int crick_comm_world(crick_comm_t *c);
+int crick_comm_allgather(crick_comm_t *c, const void *send_dev, void *recv_dev, int64_t bytes_per_rank,
+                         void *stream);
+int crick_tdigest_allgather_merge(crick_tdigest_t *t, crick_comm_t *c, crick_tdigest_t *out, int exact,
+                                  void *stream);
+int crick_spsv_allgather_merge(crick_spsv_t *s, crick_comm_t *c, crick_spsv_t *out, int exact,
+                               void *stream);
+int crick_stats_allgather_merge(crick_stats_t *s, crick_comm_t *c, crick_stats_t *out, void *stream);
 
 #ifdef __cplusplus
 }

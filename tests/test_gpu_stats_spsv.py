@@ -595,3 +595,45 @@ def test_spsv_counting_path_with_counts(cb):
         s = cb.SpaceSaving(cap, "i8")
         s.update(items, w, mode=3)
         _assert_valid_summary(s.counters(), items, cap, w)
+
+
+@pytest.mark.gpu
+def test_c_abi_nccl_comm_world1(cb):
+    """crick_comm_* (NCCL opened by the library itself, no torch.distributed): a world of one rank
+    reduces a TDigest, a SpaceSaving and a SummaryStats into fresh sketches that equal
+    ``out.merge(sketch)``; the raw all-gather moves a device buffer.  (tests/tools/comm_check.py is
+    the multi-process form; its 2-GPU output is under profiles/.)"""
+    from crick_b200._lib import lib
+    from crick_b200.distributed import NcclComm
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=50000)
+    items = rng.zipf(1.3, 50000).astype(np.int64)
+    t = cb.TDigest(100.0); t.update(x)
+    s = cb.SpaceSaving(32, "i8"); s.update(items)
+    m = cb.SummaryStats(); m.update(x)
+    comm = NcclComm(NcclComm.unique_id(), 0, 1)
+    try:
+        for exact in (True, False):
+            rt = comm.reduce_tdigest(t, exact=exact)
+            rs = comm.reduce_space_saving(s, exact=exact)
+            rm = comm.reduce_stats(m)
+            comm.synchronize()
+            et = cb.TDigest(100.0); et.merge(t)
+            es = cb.SpaceSaving(32, "i8"); es.merge(s)
+            if exact:
+                assert rt.centroids().tobytes() == et.centroids().tobytes()
+            assert rt.size() == t.size()
+            assert abs(rt.quantile(0.5) - t.quantile(0.5)) < 1e-3
+            got, want = np.asarray(rs.counters()), np.asarray(es.counters())
+            if exact:
+                assert got.tobytes() == want.tobytes()
+            else:                          # the k-way merge keeps the counters, not the order of ties
+                rows = lambda a: sorted(a[i:i + 1].tobytes() for i in range(len(a)))
+                assert rows(got) == rows(want)
+            assert (rm.count(), rm.sum(), rm.var()) == (m.count(), m.sum(), m.var())
+        a = cb.DeviceArray.from_numpy(np.arange(16.0)); b = cb.DeviceArray((16,))
+        assert lib.crick_comm_allgather(comm._h, a.ptr, b.ptr, 128, comm.stream) == 0
+        comm.synchronize()
+        assert np.array_equal(b.to_numpy(), np.arange(16.0))
+    finally:
+        comm.close()
