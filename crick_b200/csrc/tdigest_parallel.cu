@@ -121,6 +121,21 @@ struct ParHeader {
     double inv;
 };
 
+// Timeline stamps (globaltimer, ns) in the 16 u64 slots behind the header (bytes 128..255 of the
+// 256-byte header block; crick_tdigest_debug_header reads them; tests/tools/step_probe.py prints
+// them): 6 / 7 k_sort_runs CTA 0 start / end, 8 / 9 first tail group after its loads / end,
+// 10 / 11 / 12 k_make_edges after the dependency wait / after the tail lists / end, 13 / 14 hot
+// kernel CTA 0 after the wait / end, 0 / 15 / 2 / 5 k_finalize after the wait / after the bucket
+// reduction / after the points / end (k_exchange_merge uses 0..5 for its own phases).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void stamp(ParHeader* hdr, int slot) {
+    reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(hdr) + 128)[slot] = global_ns();
+}
+
 struct ParLayout {
     ParHeader* hdr;
     double* edges;       // [kEMax]
@@ -278,7 +293,7 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
     __shared__ double s_val[kSortChunk];
     const int t = threadIdx.x;
     const long base = (long)blockIdx.x * kSortChunk;
-    if (SAMPLE && blockIdx.x == 0 && t == 0) hdr->S = S;
+    if (SAMPLE && blockIdx.x == 0 && t == 0) { hdr->S = S; stamp(hdr, 6); }
     double key, val;
     if (SAMPLE && (long)blockIdx.x >= S / kSortChunk) {
         // a tail oversampling group: 128 threads x 16 draws, all loads in flight; every thread keeps
@@ -309,6 +324,7 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
                 if (xs_[e] > mx.x) mx = make_double2(xs_[e], ws_[e]);
             }
         }
+        if (g == 0 && t == 0) stamp(hdr, 8);
         // the kTailKeep smallest minima / largest maxima: per warp by kTailKeep rounds of a shuffle
         // reduction on (value, lane) -- the winner drops out --, then the same over the warps'
         // winners.  Ties fall to the lower lane / warp: deterministic.
@@ -361,6 +377,7 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
                 if (lane == 0) tmax[g * kTailKeep + r] = make_double2(wx, ww_);
                 if (lane == bl) cand = make_double2(-INFINITY, 0.0);
             }
+            if (g == 0 && lane == 0) stamp(hdr, 9);
         }
         return;
     }
@@ -398,6 +415,7 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
     __syncthreads();                      // s_val complete (k = 1024 had barriers, but be explicit)
     keys[base + t] = key;
     vals[base + t] = s_val[idx];
+    if (SAMPLE && blockIdx.x == 0 && t == 0) stamp(hdr, 7);
 }
 
 constexpr int kMergeThreads = 256;   // S / 256 CTAs: the searches are a latency chain, so spread them
@@ -558,6 +576,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
     const int tid = threadIdx.x;
     grid_dep_launch();        // k_bin_accumulate may take the other SMs and clear its tables
     grid_dep_wait();          // the sorted sample
+    if (tid == 0) stamp(hdr, 10);
     double* cw = reinterpret_cast<double*>(smem_raw);
     unsigned short* s_tab = reinterpret_cast<unsigned short*>(smem_raw + (S + 1024) * 8);   // [2][kTabLen]
     // a. inclusive scan of the sample weights (fixed order => deterministic).  Warp w owns the
@@ -710,6 +729,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         s_tn[tid] = 0;
     }
     __syncthreads();
+    if (tid == 0) stamp(hdr, 11);
     // b. raw edges at the k-scale grid
     {
         const int nl = s_tn[0], nh = s_tn[1];
@@ -871,6 +891,7 @@ __global__ void __launch_bounds__(1024) k_make_edges(ParHeader* hdr, const doubl
         hdr->kmax = s_kmax[grid];
         hdr->x0 = c0;
         hdr->inv = inv;
+        stamp(hdr, 12);
     }
 }
 
@@ -1736,6 +1757,7 @@ k_bin_accumulate2(const double* __restrict__ X, const double* __restrict__ W, do
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = make_double2(0.0, 0.0);
     }
     grid_dep_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp(hdr, 13);
     const int E = hdr->E;
     const int B = E + 1;
     for (int i = threadIdx.x; i < kTabLen / 2; i += blockDim.x)
@@ -1838,7 +1860,7 @@ k_bin_accumulate2(const double* __restrict__ X, const double* __restrict__ W, do
         for (int wv = 0; wv < nwarps; ++wv) { mn = fmin(mn, s_min[wv]); mx = fmax(mx, s_max[wv]); }
         if (accumulate_into) { double2 o = minmax[blockIdx.x]; mn = fmin(mn, o.x); mx = fmax(mx, o.y); }
         minmax[blockIdx.x] = make_double2(mn, mx);
-        if (blockIdx.x == 0) hdr->ncta = gridDim.x;
+        if (blockIdx.x == 0) { hdr->ncta = gridDim.x; stamp(hdr, 14); }
     }
 }
 
@@ -2068,6 +2090,7 @@ __device__ __forceinline__ int finalize_points(const ParHeader* hdr, const doubl
     }
     s_scan[tid] = 0;
     __syncthreads();
+    if (tid == 0) stamp(const_cast<ParHeader*>(hdr), 15);
     double bw = 0.0, bs = 0.0;
     if (b < B) {
         for (int sl = 0; sl < NS; ++sl) { bw += s_part[sl * B + b].x; bs += s_part[sl * B + b].y; }
@@ -2151,6 +2174,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
                                                    int honor_badw) {
     const int tid = threadIdx.x;
     grid_dep_wait();          // the partials of k_bin_accumulate
+    if (tid == 0) stamp(hdr, 0);
     // validated update (tdigest.pyx:304-305): the digest is only touched when every weight
     // passed; the host reads the same flag after this kernel has been enqueued
     if (honor_badw && hdr->badw) {
@@ -2172,6 +2196,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
     }
     double mn, mx;
     const int m = finalize_points(hdr, edges, partial, minmax, ws.sb, mmax, v.comp, mn, mx);
+    if (tid == 0) stamp(hdr, 2);
     // c. merge into the digest (tdigest_flush phases 2-5 with the bucket points as the buffer)
     {
         __shared__ double s_bt;
@@ -2196,6 +2221,7 @@ __global__ void __launch_bounds__(1024) k_finalize(BatchView v, long d, ParHeade
                 v.hdr[d] = o;
             }
         }
+        if (tid == 0) stamp(hdr, 5);
     }
 }
 
@@ -2234,11 +2260,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 
 __global__ void __launch_bounds__(1024) k_exchange_merge(BatchView v, long d, ParHeader* hdr,

@@ -39,4 +39,12 @@ lib.crick_profile_collect(ctypes.addressof(kms), ctypes.addressof(kn))
 t.check_weights()
 print(json.dumps({"n": n, "ms_per_step": ms, "kernel_ms": kms.value / kn.value, "fixed_us": 1e3 * (ms - kms.value / kn.value),
                   "centroids": len(m.centroids())}), flush=True)
+import numpy as np
+hdr = np.zeros(32, dtype=np.uint64)
+if lib.crick_tdigest_debug_header(t._h, hdr.ctypes.data) == 0:
+    st = hdr[16:].astype(np.int64)
+    names = {6: "sort0_start", 7: "sort0_end", 8: "tail0_loaded", 9: "tail0_end", 10: "edges_start", 11: "edges_tails",
+             12: "edges_end", 13: "hot0_start", 14: "hot0_end", 0: "fin_start", 15: "fin_reduced", 2: "fin_points", 5: "fin_end"}
+    t0 = int(st[6])
+    print(json.dumps({"timeline_us": {names[k]: round((int(st[k]) - t0) / 1e3, 1) for k in (6, 8, 9, 7, 10, 11, 12, 13, 14, 0, 15, 2, 5)}}))
 dist.destroy_process_group()
