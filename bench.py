@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip BASELINE configs 3, 4, 5")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling leg (N > 1)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="plain update calls instead of TDigest.update(..., tail_stream=)")
     return ap.parse_args()
 
 
@@ -199,6 +201,11 @@ class Bench:
             self.dist = dist
         self.stream = torch.cuda.Stream()
         self.sptr = self.stream.cuda_stream
+        # pipelined updates (TDigest.update(..., tail_stream=)): the digest-side tail of a step and the
+        # reduction run here and overlap the next step's sample phase on self.stream
+        self.tail = torch.cuda.Stream()
+        self.tptr = self.tail.cuda_stream
+        self.pipelined = True
         self.peak, self.peak_src = peak_hbm()
 
     def barrier(self):
@@ -237,12 +244,14 @@ class Bench:
         def step():
             # weights validated on the device ("deferred": the verdict is collected after the
             # timed region, nothing waits for it inside a step)
-            if dw is not None:
+            if self.pipelined:
+                digest.update(dx, 1 if dw is None else dw, stream=self.sptr, tail_stream=self.tptr)
+            elif dw is not None:
                 digest.update(dx, dw, mode="parallel", stream=self.sptr, check_w="deferred")
             else:
                 digest.update(dx, mode="parallel", stream=self.sptr)
             if reducer is not None:
-                with torch.cuda.stream(self.stream):
+                with torch.cuda.stream(self.tail if self.pipelined else self.stream):
                     return reducer(digest)
             return digest
 
@@ -257,6 +266,8 @@ class Bench:
         ev0.record(self.stream)
         for _ in range(K):
             merged = step()
+        if self.pipelined:
+            self.stream.wait_stream(self.tail)     # the last step's tail and reduction are inside
         ev1.record(self.stream)
         self.barrier()
         ms = self.max_over_ranks(ev0.elapsed_time(ev1))
@@ -308,6 +319,7 @@ def main():
         return
 
     B = Bench(args)
+    B.pipelined = not args.no_pipeline
     cb, lib, torch = B.cb, B.lib, B.torch
     rank, world = B.rank, B.world
     from crick_b200.distributed import TDigestAllReduce, allgather_merge_tdigest
@@ -455,6 +467,9 @@ def main():
                                       if world > 1 else ""),
                        "values_per_step": n, "values_per_gpu_per_step": m, "compression": COMPRESSION,
                        "l2": "inputs (16 B x %d = %.1f GB per GPU per step) far exceed the 126 MB L2" % (m, 16 * m / 1e9),
+                       "update_call": ("TDigest.update(x, w, stream=, tail_stream=): the step's single-CTA tail and the "
+                                       "reduction run on a second stream and overlap the next step's sample phase"
+                                       if B.pipelined else "TDigest.update(x, w, stream=, check_w='deferred')"),
                        "weights": "validated on the device in the same pass (deferred verdict, no host sync in a step)",
                        "centroids": nc, "digest_size": total_size},
             "roofline": roofline, "roofline_unweighted": roofline_unweighted, "cpu_baseline": cpu,

@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
     const int t = threadIdx.x;
     const long base = (long)blockIdx.x * kSortChunk;
     if (SAMPLE && blockIdx.x == 0 && t == 0) { hdr->S = S; stamp(hdr, 6); }
+    // (no griddepcontrol.launch_dependents here or in k_merge_runs: with both, update -> finalize on
+    // one stream became non-deterministic on driver 580 -- k_finalize, the fifth kernel of the
+    // programmatic chain, intermittently ran ahead of the streaming kernel's results; ~4 us gained
+    // is not worth that.  Measured round 2, tests/tools/step_probe.py.)
     double key, val;
     if (SAMPLE && (long)blockIdx.x >= S / kSortChunk) {
         // a tail oversampling group: 128 threads x 16 draws, all loads in flight; every thread keeps
@@ -306,23 +310,32 @@ __global__ void __launch_bounds__(kSortChunk) k_sort_runs(double* __restrict__ k
         // (multiply-shift instead of sample_one's 64-bit modulo: no host mirror to agree with)
         const long seg2 = n / (S * kTailDraws);                                   // >= 1 (n >= kTailMinN)
         const unsigned seg32 = seg2 > 0xffffffffl ? 0xffffffffu : (unsigned)seg2;
-        double xs_[kTailPerThread], ws_[kTailPerThread];
+        // Only the values are loaded for every draw; the weight is fetched for the thread's minimum
+        // and maximum alone (a weight tdigest_add would drop, :285, then drops that candidate: such
+        // weights are degenerate input, and the oversample only refines edges).  The phase is bound
+        // by the loads a SM can keep in flight, so this halves it.
+        double xs_[kTailPerThread];
+        long ps_[kTailPerThread];
 #pragma unroll
         for (int e = 0; e < kTailPerThread; ++e) {
             const long i = (g * kTailThreads + t) * kTailPerThread + e;
-            const long pos = i * seg2 + (long)__umulhi((unsigned)(mix64((unsigned long long)i) >> 32), seg32);
-            const double xv = X[pos], wv = W ? W[pos] : wsc;
-            const bool okv = is_finite_d(xv) && !(wv <= DBL_EPSILON);
-            xs_[e] = okv ? xv + 0.0 : INFINITY;
-            ws_[e] = okv ? wv : 0.0;
+            ps_[e] = i * seg2 + (long)__umulhi((unsigned)(mix64((unsigned long long)i) >> 32), seg32);
+            xs_[e] = X[ps_[e]];
         }
         double2 mn = make_double2(INFINITY, 0.0), mx = make_double2(-INFINITY, 0.0);
+        long pmn = -1, pmx = -1;
 #pragma unroll
         for (int e = 0; e < kTailPerThread; ++e) {
-            if (ws_[e] > 0.0) {                    // (rejected draws come back as (+inf, 0))
-                if (xs_[e] < mn.x) mn = make_double2(xs_[e], ws_[e]);
-                if (xs_[e] > mx.x) mx = make_double2(xs_[e], ws_[e]);
+            if (is_finite_d(xs_[e])) {
+                const double xv = xs_[e] + 0.0;
+                if (xv < mn.x) { mn.x = xv; pmn = ps_[e]; }
+                if (xv > mx.x) { mx.x = xv; pmx = ps_[e]; }
             }
+        }
+        {
+            const double wlo = pmn < 0 ? 0.0 : (W ? W[pmn] : wsc), whi = pmx < 0 ? 0.0 : (W ? W[pmx] : wsc);
+            mn = (wlo <= DBL_EPSILON || !is_finite_d(wlo)) ? make_double2(INFINITY, 0.0) : make_double2(mn.x, wlo);
+            mx = (whi <= DBL_EPSILON || !is_finite_d(whi)) ? make_double2(-INFINITY, 0.0) : make_double2(mx.x, whi);
         }
         if (g == 0 && t == 0) stamp(hdr, 8);
         // the kTailKeep smallest minima / largest maxima: per warp by kTailKeep rounds of a shuffle
@@ -2848,6 +2861,24 @@ size_t p2p_rec_doubles(double comp) { return 4 + 2 * (size_t)mmax_for(comp); }
 size_t p2p_buffer_bytes(double comp, int world) {
     return ((size_t)kP2PFlagDoubles + 2 * (size_t)world * p2p_rec_doubles(comp)) * sizeof(double);
 }
+// The two halves of launch_parallel_update for pipelined callers: everything up to and including the
+// streaming pass (reads X, W, writes only `scratch`), and the tail that folds the bucket sums into
+// the digest (deferred weight check when `checked`).
+cudaError_t launch_parallel_pass(const BatchView& v, const double* X, const double* W, double wsc, long n,
+                                 void* scratch, int sm_count, cudaStream_t st) {
+    ParLayout L = carve(scratch, v.comp, sm_count);
+    long S = sample_len(n);
+    const bool tails = S == kSMax && n >= kTailMinN && tail_sampling_enabled();
+    SampleSrc src{X, W, wsc, n, L.hdr, tails ? L.tmin : nullptr, tails ? L.tmax : nullptr};
+    cudaError_t e = edges_from_sample(v, L, S, &src, st);
+    if (e != cudaSuccess) return e;
+    return accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, nullptr, 0);
+}
+cudaError_t launch_parallel_tail(const BatchView& v, long d, void* scratch, int sm_count, cudaStream_t st,
+                                 bool checked) {
+    return parallel_finalize(v, d, scratch, sm_count, st, checked);
+}
+
 cudaError_t launch_parallel_update_exchange(const BatchView& v, long d, const double* X, const double* W,
                                             double wsc, long n, void* scratch, int sm_count,
                                             cudaStream_t st, bool check_weights, int rank, int world,

@@ -300,7 +300,7 @@ class TDigest:
             raise ValueError("w must be > 0 and finite")
         check(lib.crick_tdigest_add(self._h, x, w), "add")
 
-    def update(self, x, w=1, mode=None, stream=None, check_w=True, stats=None):
+    def update(self, x, w=1, mode=None, stream=None, check_w=True, stats=None, tail_stream=None):
         """update(self, x, w=1)
 
         Add many samples to this digest.
@@ -327,11 +327,22 @@ class TDigest:
             (``centroids``, ``min``, ``max``, ``quantile`` / ``cdf`` of host arrays, pickling)
             or by ``check_weights()``: update -> export -> all-gather -> merge become one
             enqueue chain.
+        tail_stream : a second ``cudaStream_t`` (CUDA-array inputs of at least PARALLEL_MIN values,
+            with ``stream``): the pipelined form for back-to-back updates.  The kernels that only
+            read ``x`` / ``w`` (sample, edges, the streaming pass) run on ``stream``, the short
+            single-CTA tail that folds the result into the digest runs on ``tail_stream`` -- so
+            does whatever the caller enqueues there afterwards (export, all-gather, merge) --
+            and the next update's sample phase overlaps it.  Weights are checked like
+            ``check_w="deferred"``.  Same results as the plain call.
         """  # tdigest.pyx:282-308
         m = self._mode if mode is None else _lib.mode_code(mode)
         if stats is not None:
             return self._update_with_stats(x, w, stream, check_w, stats)
         xd = device_view(x, stream)
+        if tail_stream is not None:
+            if xd is None or not stream:
+                raise TypeError("tail_stream needs CUDA-array inputs and an explicit stream")
+            return self._update_pipelined(xd, w, stream, tail_stream)
         if xd is not None:
             return self._update_device(xd, w, m, stream, check_w)
         x = np.asarray(x)
@@ -429,6 +440,29 @@ class TDigest:
                                                  0, 0, stream, ctypes.addressof(bad)), "update")
         if bad.value:
             raise ValueError("w must be > 0 and finite")
+
+    def _update_pipelined(self, xd, w, stream, tail_stream):
+        xd = as_f64_device(xd, stream)
+        n = xd.size
+        if n < _lib.PARALLEL_MIN:
+            raise ValueError("tail_stream needs at least %d values per call" % _lib.PARALLEL_MIN)
+        wd = device_view(w, stream)
+        if wd is not None:
+            wd = as_f64_device(wd, stream)
+            if wd.size != n:
+                raise ValueError("x and w CUDA arrays must have the same number of elements")
+            check(lib.crick_tdigest_update_pipelined(self._h, xd.ptr, wd.ptr, 0.0, n, stream, tail_stream),
+                  "update")
+            self._deferred = True
+            release_views((xd, wd), stream)
+            return
+        if not np.isscalar(w) and np.ndim(w) != 0:
+            raise TypeError("with a CUDA array x, w must be a scalar or a CUDA array")
+        wv = _as_double(w, "w")
+        if wv != 1 and (not math.isfinite(wv) or wv <= 0):
+            raise ValueError("w must be > 0 and finite")
+        check(lib.crick_tdigest_update_pipelined(self._h, xd.ptr, None, wv, n, stream, tail_stream), "update")
+        release_views((xd,), stream)
 
     def _update_device(self, xd, w, m, stream, check_w=True):
         xd = as_f64_device(xd, stream)     # int / float16 / float32 ... CUDA arrays: safe cast on the device

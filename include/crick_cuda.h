@@ -124,6 +124,14 @@ int crick_tdigest_update_checked(crick_tdigest_t *t, const double *x, const doub
 int crick_tdigest_update_deferred(crick_tdigest_t *t, const double *x, const double *w,
                                   double w_scalar, int64_t n, int mode, void *stream);
 int crick_tdigest_take_bad_weights(crick_tdigest_t *t);   /* bit 0 bad weights, bit 1 exchange timeout */
+/* Pipelined form of crick_tdigest_update_deferred for back-to-back updates from device arrays
+ * (tdigest.pyx:282-308 per call): the sample / edges kernels and the streaming pass are enqueued on
+ * `stream`, the single-CTA tail that folds the bucket sums into the digest on `tail_stream` behind an
+ * event, on alternating scratch sets -- so the next update's sample work (and the caller's own work
+ * on `tail_stream`: export, all-gather, merge) overlaps.  Two different explicit streams; every
+ * other call on the handle orders itself behind the tail as usual.  n >= CRICK_PARALLEL_MIN. */
+int crick_tdigest_update_pipelined(crick_tdigest_t *t, const double *x, const double *w, double w_scalar,
+                                   int64_t n, void *stream, void *tail_stream);
 /* ---- one stream sharded over the GPUs of a node: update + exchange + merge over peer memory -----
  * Every rank (one process per GPU) owns an exchange buffer of crick_p2p_buffer_bytes() bytes
  * (crick_p2p_alloc: plain cudaMalloc, zeroed), exports it with crick_ipc_get_handle (64 bytes, sent

@@ -652,3 +652,44 @@ def test_parallel_update_is_deterministic(cb):
             t.update(x, mode="parallel")
             seen.add(t.centroids().tobytes())
         assert len(seen) == 1, n
+
+
+@pytest.mark.gpu
+def test_pipelined_updates_equal_plain_updates(cb):
+    """TDigest.update(..., tail_stream=) -- sample phase and pass on one stream, the fold into the digest
+    on a second one, alternating scratch sets -- leaves the same digest, byte for byte, as the plain
+    deferred-check call: over back-to-back updates, with a query and a scalar add in between, with
+    array and scalar weights; a bad weight is reported by check_weights() and skips only its update."""
+    from crick_b200._lib import lib
+    rng = np.random.default_rng(11)
+    n = 1 << 22
+    chunks = [rng.lognormal(0, 1 + 0.2 * i, n) for i in range(5)]
+    ws = [rng.uniform(0.5, 2.0, n) for _ in range(5)]
+    s1, s2 = lib.crick_stream_create(), lib.crick_stream_create()
+    try:
+        a, b = cb.TDigest(100, mode="parallel"), cb.TDigest(100, mode="parallel")
+        dev = [(cb.DeviceArray.from_numpy(x), cb.DeviceArray.from_numpy(w)) for x, w in zip(chunks, ws)]
+        for i, (dx, dw) in enumerate(dev):
+            if i == 3:                       # scalar weight, after a host-side add and a query
+                for t in (a, b):
+                    t.add(0.125, 3.0)
+                assert a.quantile(0.5) == b.quantile(0.5)
+                a.update(dx, 2.0, mode="parallel", stream=s1)
+                b.update(dx, 2.0, stream=s1, tail_stream=s2)
+            else:
+                a.update(dx, dw, mode="parallel", stream=s1, check_w="deferred")
+                b.update(dx, dw, stream=s1, tail_stream=s2)
+        a.check_weights(); b.check_weights()
+        assert a.centroids().tobytes() == b.centroids().tobytes()
+        assert (a.size(), a.min(), a.max()) == (b.size(), b.min(), b.max())
+        before = b.centroids().tobytes()
+        wbad = ws[0].copy(); wbad[12345] = -1.0
+        b.update(dev[0][0], cb.DeviceArray.from_numpy(wbad), stream=s1, tail_stream=s2)
+        b.update(dev[1][0], dev[1][1], stream=s1, tail_stream=s2)
+        with pytest.raises(ValueError):
+            b.check_weights()
+        a.update(dev[1][0], dev[1][1], mode="parallel", stream=s1, check_w="deferred")
+        assert b.centroids().tobytes() == a.centroids().tobytes() != before
+    finally:
+        lib.crick_stream_synchronize(s1); lib.crick_stream_synchronize(s2)
+        lib.crick_stream_destroy(s1); lib.crick_stream_destroy(s2)

@@ -17,11 +17,16 @@ dx, dw = cb.DeviceArray((n,)), cb.DeviceArray((n,))
 lib.crick_synth_fill(dx.ptr, dw.ptr, n, 1234, 0, 0, None)
 lib.crick_device_synchronize()
 stream = torch.cuda.Stream(); sptr = stream.cuda_stream
+tail = torch.cuda.Stream(); tptr = tail.cuda_stream
+PIPE = os.environ.get("PIPE", "1") != "0"
 red = TDigestAllReduce(100.0, exact=False)
 t = cb.TDigest(100, mode="parallel")
 def step():
-    t.update(dx, dw, mode="parallel", stream=sptr, check_w="deferred")
-    with torch.cuda.stream(stream):
+    if PIPE:
+        t.update(dx, dw, stream=sptr, tail_stream=tptr)
+    else:
+        t.update(dx, dw, mode="parallel", stream=sptr, check_w="deferred")
+    with torch.cuda.stream(tail if PIPE else stream):
         return red(t)
 for _ in range(5): step()
 torch.cuda.synchronize()
@@ -30,6 +35,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 K = 20
 e0.record(stream)
 for _ in range(K): m = step()
+stream.wait_stream(tail)
 e1.record(stream)
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
@@ -37,8 +43,9 @@ lib.crick_profile_enable(0)
 kms, kn = ctypes.c_double(0), ctypes.c_int64(0)
 lib.crick_profile_collect(ctypes.addressof(kms), ctypes.addressof(kn))
 t.check_weights()
-print(json.dumps({"n": n, "ms_per_step": ms, "kernel_ms": kms.value / kn.value, "fixed_us": 1e3 * (ms - kms.value / kn.value),
-                  "centroids": len(m.centroids())}), flush=True)
+print(json.dumps({"pipelined": PIPE, "n": n, "ms_per_step": ms, "kernel_ms": kms.value / kn.value, "fixed_us": 1e3 * (ms - kms.value / kn.value),
+                  "centroids": len(m.centroids()),
+                  "centroids_md5": __import__("hashlib").md5(m.centroids().tobytes()).hexdigest()[:12]}), flush=True)
 import numpy as np
 hdr = np.zeros(32, dtype=np.uint64)
 if lib.crick_tdigest_debug_header(t._h, hdr.ctypes.data) == 0:
