@@ -659,8 +659,12 @@ def test_dlpack_only_inputs_and_zero_copy_centroids(cb):
     q = torch.tensor([0.1, 0.5, 0.9], dtype=torch.float64, device="cuda")
     got = a.quantile(DLPackOnly(q)).to_numpy()
     assert got.tobytes() == b.quantile([0.1, 0.5, 0.9]).tobytes()
+    a32, b32 = cb.TDigest(mode="reference"), R.TDigest()
+    a32.update(DLPackOnly(tx.float()))                    # safely castable dtypes are cast on the device
+    b32.update(x.astype(np.float32))
+    same(a32, b32)
     with pytest.raises(TypeError):
-        a.update(DLPackOnly(tx.float()))                  # float32 CUDA arrays are not accepted
+        a.update(DLPackOnly(torch.complex(tx, tx)))       # tdigest.pyx:298-302: not castable to f8
     with pytest.raises(ValueError):
         a.update(DLPackOnly(torch.from_numpy(x.reshape(100, 1000)).cuda()[:, ::2]))   # strided
     view = a.centroids_device()
