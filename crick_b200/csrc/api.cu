@@ -763,8 +763,25 @@ int crick_tdigest_take_bad_weights(crick_tdigest_t* t) {
 // (and whatever the caller enqueues behind it on `tail_stream`: export, all-gather, merge) is still
 // running; with back-to-back updates of 1.25e8 values the step shrinks from pass + ~95 us to
 // pass + ~55 us.  Every other operation on the handle orders itself behind the tail stream as usual
-// (td_stream), so results are the same as crick_tdigest_update_deferred's.  Weights are validated
-// like there (crick_tdigest_take_bad_weights).
+// (td_stream).  The streaming kernel runs on sm_count - crick_pipeline_reserve_sms() CTAs (default 2
+// fewer): the per-CTA partial sums are cut differently, so the digest agrees with
+// crick_tdigest_update_deferred's in the last bits only when the reserve is 0 -- deterministic either
+// way.  Weights are validated like there (crick_tdigest_take_bad_weights).
+// SMs the streaming kernel of a pipelined update leaves free (it runs one CTA per SM and holds that
+// SM's shared memory for the whole pass): the tail stream's kernels -- k_finalize, and the caller's
+// export / NCCL all-gather / merge, which can sit waiting for other ranks -- would otherwise take
+// SMs first and make the pass wait for them (measured at 8 GPUs: pass 0.32 -> 0.40 ms).
+static int g_pipe_reserve = [] {
+    const char* env = getenv("CRICK_PIPE_RESERVE");
+    int v = env ? atoi(env) : 2;
+    return v < 0 ? 0 : (v > 32 ? 32 : v);
+}();
+int crick_pipeline_reserve_sms(int n_sms) {
+    int prev = g_pipe_reserve;
+    if (n_sms >= 0 && n_sms <= 32) g_pipe_reserve = n_sms;
+    return prev;
+}
+
 int crick_tdigest_update_pipelined(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                                    int64_t n, void* stream, void* tail_stream) {
     if (!stream || !tail_stream || stream == tail_stream)
@@ -799,10 +816,11 @@ int crick_tdigest_update_pipelined(crick_tdigest_t* t, const double* x, const do
         e = cudaStreamWaitEvent(st, t->ev_fin[p], 0);
         if (e != cudaSuccess) return fail("update_pipelined: wait", e);
     }
-    e = launch_parallel_pass(t->s.v, x, w, w_scalar, n, t->pipe_scratch[p], sm_count(), st);
+    const int sms = sm_count() > 2 * g_pipe_reserve ? sm_count() - g_pipe_reserve : sm_count();
+    e = launch_parallel_pass(t->s.v, x, w, w_scalar, n, t->pipe_scratch[p], sms, st);
     if (e == cudaSuccess) e = cudaEventRecord(t->ev_pass, st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ts, t->ev_pass, 0);
-    if (e == cudaSuccess) e = launch_parallel_tail(t->s.v, 0, t->pipe_scratch[p], sm_count(), ts, w != nullptr);
+    if (e == cudaSuccess) e = launch_parallel_tail(t->s.v, 0, t->pipe_scratch[p], sms, ts, w != nullptr);
     if (e == cudaSuccess) e = cudaEventRecord(t->ev_fin[p], ts);
     if (e != cudaSuccess) return fail("update_pipelined", e);
     t->fin_recorded[p] = true;

@@ -132,6 +132,10 @@ int crick_tdigest_take_bad_weights(crick_tdigest_t *t);   /* bit 0 bad weights, 
  * other call on the handle orders itself behind the tail as usual.  n >= CRICK_PARALLEL_MIN. */
 int crick_tdigest_update_pipelined(crick_tdigest_t *t, const double *x, const double *w, double w_scalar,
                                    int64_t n, void *stream, void *tail_stream);
+/* SMs a pipelined update's streaming kernel leaves to the tail stream (default 2, env
+ * CRICK_PIPE_RESERVE; 0: same grid, hence bit-identical results, as the plain update).  Returns the
+ * previous value; a negative argument only queries. */
+int crick_pipeline_reserve_sms(int n_sms);
 /* ---- one stream sharded over the GPUs of a node: update + exchange + merge over peer memory -----
  * Every rank (one process per GPU) owns an exchange buffer of crick_p2p_buffer_bytes() bytes
  * (crick_p2p_alloc: plain cudaMalloc, zeroed), exports it with crick_ipc_get_handle (64 bytes, sent

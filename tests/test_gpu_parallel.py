@@ -658,10 +658,14 @@ def test_parallel_update_is_deterministic(cb):
 def test_pipelined_updates_equal_plain_updates(cb):
     """TDigest.update(..., tail_stream=) -- sample phase and pass on one stream, the fold into the digest
     on a second one, alternating scratch sets -- leaves the same digest, byte for byte, as the plain
-    deferred-check call: over back-to-back updates, with a query and a scalar add in between, with
-    array and scalar weights; a bad weight is reported by check_weights() and skips only its update."""
+    deferred-check call when it uses the same grid (reserve 0): over back-to-back updates, with a
+    query and a scalar add in between, with array and scalar weights; a bad weight is reported by
+    check_weights() and skips only its update.  With the default reserve (2 SMs left to the tail
+    stream) the bucket sums are cut differently: same quantiles to 1e-6 relative, and the same bytes
+    from one run to the next."""
     from crick_b200._lib import lib
     rng = np.random.default_rng(11)
+    prev_reserve = lib.crick_pipeline_reserve_sms(0)
     n = 1 << 22
     chunks = [rng.lognormal(0, 1 + 0.2 * i, n) for i in range(5)]
     ws = [rng.uniform(0.5, 2.0, n) for _ in range(5)]
@@ -690,6 +694,22 @@ def test_pipelined_updates_equal_plain_updates(cb):
             b.check_weights()
         a.update(dev[1][0], dev[1][1], mode="parallel", stream=s1, check_w="deferred")
         assert b.centroids().tobytes() == a.centroids().tobytes() != before
+        lib.crick_pipeline_reserve_sms(prev_reserve)
+        assert lib.crick_pipeline_reserve_sms(-1) == prev_reserve
+        runs = []
+        for _ in range(2):
+            c = cb.TDigest(100, mode="parallel")
+            for dx, dw in dev:
+                c.update(dx, dw, stream=s1, tail_stream=s2)
+            runs.append(c.centroids().tobytes())
+            d = cb.TDigest(100, mode="parallel")
+            for dx, dw in dev:
+                d.update(dx, dw, mode="parallel", stream=s1)
+            qs = np.array([0.001, 0.01, 0.25, 0.5, 0.75, 0.99, 0.999])
+            np.testing.assert_allclose(c.quantile(qs), d.quantile(qs), rtol=1e-6)
+            assert abs(c.size() - d.size()) <= 1e-12 * d.size()
+        assert runs[0] == runs[1]
     finally:
+        lib.crick_pipeline_reserve_sms(prev_reserve)
         lib.crick_stream_synchronize(s1); lib.crick_stream_synchronize(s2)
         lib.crick_stream_destroy(s1); lib.crick_stream_destroy(s2)
