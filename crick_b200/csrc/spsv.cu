@@ -853,13 +853,13 @@ static cudaError_t sp_launch_update_hh(crick_spsv* s, const long long* item, con
         count_launch();
         k_hh_fill<<<1024, 256, 0, st>>>(tabkey, kHHTabSlots, kHHEmpty);
         count_launch();
-        k_hh_sample<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(item, n, S, tabkey, tabcnt);
+        k_hh_sample<<<(unsigned)((S + kHHSampleThreads - 1) / kHHSampleThreads), kHHSampleThreads, 0, st>>>(item, n, S, tabkey, tabcnt);
         e = cudaMemsetAsync(hist, 0, 1024 * 4, st);
         if (e != cudaSuccess) break;
         count_launch();
         k_hh_hist<<<128, 1024, 0, st>>>(tabcnt, hist);
         count_launch();
-        k_hh_thresh<<<1, 32, 0, st>>>(hist, C, sel);
+        k_hh_thresh<<<1, 1024, 0, st>>>(hist, C, sel);
         count_launch();
         k_hh_chunks<<<kHHNChunk, 1024, 0, st>>>(tabcnt, sel, chunk_gt, chunk_eq);
         count_launch();
