@@ -441,7 +441,7 @@ int crick_tdigest_add(crick_tdigest_t* t, double x, double w) {
 // double-buffered chunks (copy of chunk k+1 overlaps the accumulate of chunk k)
 // ---- pageable host input ------------------------------------------------------------------
 // cudaMemcpyAsync from ordinary (pageable) memory is staged by the driver on one thread at
-// ~11 GB/s (scripts/pageable_probe.py) -- a fifth of what the link moves from pinned memory.
+// ~11 GB/s (tests/tools/pageable_probe.py) -- a fifth of what the link moves from pinned memory.
 // NumPy arrays are pageable, so the library stages them itself: a few host threads copy each
 // chunk into one of three cached pinned slots while the previous slots are in flight to the GPU.
 constexpr int64_t kStageChunk = 1 << 22;   // values per slot and array (32 MiB)

@@ -1,5 +1,5 @@
 """Per-call latency of TDigest.update on device-resident inputs, by chunk size (the dask
-per-chunk shape).  Usage: [CRICK_CUDA_LIB=...] python scripts/latency_probe.py"""
+per-chunk shape).  Usage: [CRICK_CUDA_LIB=...] python tests/tools/latency_probe.py"""
 import sys, time
 sys.path.insert(0, "/root/repo")
 import torch
