@@ -35,19 +35,22 @@ int fail_msg(const char* what) {
     return -1;
 }
 
-static int g_sm_count = 0;
+// SM count of the CURRENT device, cached per device; the first query of a device also sets its
+// default memory pool's release threshold (the one place that does): freed stream-ordered staging
+// buffers stay cached up to 2 GiB instead of going back to the driver at every synchronisation.
+static std::atomic<int> g_sm_counts[64];
 int sm_count() {
-    if (g_sm_count) return g_sm_count;
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    // keep freed stream-ordered allocations cached: staging buffers are reused every call
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (dev >= 0 && dev < 64 && (n = g_sm_counts[dev].load(std::memory_order_relaxed)) > 0) return n;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
+        unsigned long long thr = 2ull << 30;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    g_sm_count = n;
+    cudaGetLastError();
+    if (dev >= 0 && dev < 64) g_sm_counts[dev].store(n, std::memory_order_relaxed);
     return n;
 }
 
@@ -184,7 +187,6 @@ int crick_device_count(void) {
 int crick_set_device(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail("cudaSetDevice", e);
-    g_sm_count = 0;
     return 0;
 }
 int crick_sm_count(void) { return sm_count(); }
@@ -298,15 +300,23 @@ void crick_device_free(void* p) {
         auto jt = g_mem_dev.find(p);
         if (jt != g_mem_dev.end()) { dev = jt->second; g_mem_dev.erase(jt); }
     }
+    // a block goes back to the cache only when nothing enqueued on ITS device can still touch it
+    auto sync_owner = [&]() {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cudaDeviceSynchronize(); return; }
+        if (cur != dev) cudaSetDevice(dev);
+        cudaDeviceSynchronize();
+        if (cur != dev) cudaSetDevice(cur);
+    };
     if (nb & kCarved) {                       // part of a slab: always back to the cache
         nb &= ~kCarved;
-        cudaDeviceSynchronize();
+        sync_owner();
         std::lock_guard<std::mutex> lk(g_mem_mu);
         g_mem_cache.emplace(std::make_pair(dev, nb), p);
         return;
     }
     if (nb && nb <= ((size_t)128 << 20)) {
-        cudaDeviceSynchronize();
+        sync_owner();
         std::lock_guard<std::mutex> lk(g_mem_mu);
         if (g_mem_cached + nb <= ((size_t)1 << 30)) {
             g_mem_cache.emplace(std::make_pair(dev, nb), p);
@@ -380,24 +390,8 @@ int crick_synth_fill(double* x, double* w, int64_t n, uint64_t seed, int64_t off
 }
 
 // ---- TDigest ---------------------------------------------------------------
-// keep up to 2 GiB of freed staging memory in the device's default pool instead of returning
-// it to the driver at every synchronisation (cudaMallocAsync is then a pointer bump)
-static void tune_mempool_once() {
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = 2ull << 30;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        cudaGetLastError();
-    });
-}
-
 crick_tdigest_t* crick_tdigest_new(double compression) {
     if (!sm_count()) { fail_msg("no CUDA device: libcrick_cuda has no CPU fallback"); return nullptr; }
-    tune_mempool_once();
     crick_tdigest* t = new (std::nothrow) crick_tdigest();
     if (!t) return nullptr;
     if (store_alloc(t->s, compression, 1)) { delete t; return nullptr; }

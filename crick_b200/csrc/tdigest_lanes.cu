@@ -33,6 +33,7 @@
 // with margin = 6e-13 (>= 100x the bound), and per item only  Wc > Whi -> open,  Wc < Wlo -> fold;
 // a Wc inside the window evaluates the reference's own two kscale() and decides from them (counted
 // in g_exact_fallbacks).  Means and weights never depend on k, so the result is the same bits.
+#include "api_common.h"
 #include "kernels.h"
 #include "tdigest_ref.cuh"
 
@@ -247,19 +248,15 @@ __global__ void __launch_bounds__(512, 1) k_ingest_lanes(BatchView v, long ngrou
 // Groups from which the thread-per-digest kernel is used (below it the GPU is not filled:
 // 32 digests per warp).  crick_group_kernel() / CRICK_GROUP_LANES=0|1 force the choice.
 static int lanes_sm_count() {
-    static int sms = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-        return n;
-    }();
-    return sms;
+    const int n = sm_count();        // current device (api.cu caches it per device)
+    return n > 0 ? n : 148;
 }
 
 static int g_lanes_mode = [] {
     const char* env = getenv("CRICK_GROUP_LANES");
     return (env && (env[0] == '0' || env[0] == '1')) ? env[0] - '0' : -1;
 }();
+
 // Decision window half-width in q (see the file comment); 0 < margin; a huge value (>= 1) sends
 // every item through the exact kscale pair, negative selects the kernel without the window.
 static double g_lanes_margin = [] {
