@@ -320,6 +320,9 @@ def main():
 
     B = Bench(args)
     B.pipelined = not args.no_pipeline
+    # SMs the streaming kernel leaves to the tail stream: 2 when a reduction (NCCL kernel waiting for
+    # the other ranks) runs there, none on one GPU where the tail is the 20 us of k_finalize
+    B.lib.crick_pipeline_reserve_sms(2 if B.world > 1 else 0)
     cb, lib, torch = B.cb, B.lib, B.torch
     rank, world = B.rank, B.world
     from crick_b200.distributed import TDigestAllReduce, allgather_merge_tdigest
