@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip BASELINE configs 3, 4, 5")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling leg (N > 1)")
+    ap.add_argument("--overlap", type=int, default=-1, help="overlapped sample phase: 1 / 0 (default: from 4 GPUs)")
+    ap.add_argument("--reserve", type=int, default=-1, help="SMs the pass leaves free (default 0 / 2 / 6)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="plain update calls instead of TDigest.update(..., tail_stream=)")
     return ap.parse_args()
@@ -320,9 +322,16 @@ def main():
 
     B = Bench(args)
     B.pipelined = not args.no_pipeline
-    # SMs the streaming kernel leaves to the tail stream: 2 when a reduction (NCCL kernel waiting for
-    # the other ranks) runs there, none on one GPU where the tail is the 20 us of k_finalize
-    B.lib.crick_pipeline_reserve_sms(2 if B.world > 1 else 0)
+    # How the pipelined call is set up (library switches).  One GPU: the tail is
+    # the 20 us of k_finalize -- no SM reserve.  Two GPUs: 2 SMs for the reduction on the tail stream
+    # (an NCCL kernel waiting for the other rank would otherwise hold SMs the pass wants).  From four
+    # GPUs the pass is short enough (<= 0.64 ms) that the ~50 us of sample -> edges work matter: the
+    # overlapped form runs them for the NEXT step on 6 reserved SMs while the current pass streams.
+    overlap = (B.world >= 4) if args.overlap < 0 else bool(args.overlap)
+    reserve = args.reserve if args.reserve >= 0 else (6 if overlap else (2 if B.world > 1 else 0))
+    B.lib.crick_pipeline_overlap(1 if overlap else 0)
+    B.lib.crick_pipeline_reserve_sms(reserve)
+    B.pipe_cfg = {"overlap_sample_phase": bool(overlap), "reserved_sms": int(reserve)}
     cb, lib, torch = B.cb, B.lib, B.torch
     rank, world = B.rank, B.world
     from crick_b200.distributed import TDigestAllReduce, allgather_merge_tdigest
@@ -473,6 +482,7 @@ def main():
                        "update_call": ("TDigest.update(x, w, stream=, tail_stream=): the step's single-CTA tail and the "
                                        "reduction run on a second stream and overlap the next step's sample phase"
                                        if B.pipelined else "TDigest.update(x, w, stream=, check_w='deferred')"),
+                       "pipeline": B.pipe_cfg if B.pipelined else None,
                        "weights": "validated on the device in the same pass (deferred verdict, no host sync in a step)",
                        "centroids": nc, "digest_size": total_size},
             "roofline": roofline, "roofline_unweighted": roofline_unweighted, "cpu_baseline": cpu,

@@ -38,6 +38,7 @@ _SIG = {
     "crick_stream_destroy": (None, [_P]),
     "crick_tdigest_update_pipelined": (c_int, [_P, _P, _P, c_double, c_int64, _P, _P]),
     "crick_pipeline_reserve_sms": (c_int, [c_int]),
+    "crick_pipeline_overlap": (c_int, [c_int]),
     "crick_comm_unique_id": (c_int, [_P]),
     "crick_comm_init": (_P, [_P, c_int, c_int]),
     "crick_comm_free": (None, [_P]),

@@ -110,6 +110,8 @@ struct crick_tdigest {
     // and the pass of update k + 1 (on the main stream)
     void* pipe_scratch[2] = {nullptr, nullptr};
     cudaEvent_t ev_pass = nullptr, ev_fin[2] = {nullptr, nullptr};
+    cudaStream_t pass_stream = nullptr;      // overlapped sample phase: the passes run here, one after the other
+    cudaEvent_t ev_prep = nullptr;
     bool fin_recorded[2] = {false, false};
     int pipe_next = 0;
 };
@@ -420,6 +422,8 @@ void crick_tdigest_free(crick_tdigest_t* t) {
         if (t->ev_fin[b]) cudaEventDestroy(t->ev_fin[b]);
     }
     if (t->ev_pass) cudaEventDestroy(t->ev_pass);
+    if (t->ev_prep) cudaEventDestroy(t->ev_prep);
+    if (t->pass_stream) { cudaStreamSynchronize(t->pass_stream); cudaStreamDestroy(t->pass_stream); }
     store_free(t->s);
     delete t;
 }
@@ -776,6 +780,22 @@ int crick_pipeline_reserve_sms(int n_sms) {
     return prev;
 }
 
+// Overlapped sample phase.  With it the streaming passes of consecutive pipelined updates run back to
+// back on a stream of the handle's own, and the sample -> edges kernels of update k + 1 -- which need
+// only its x and w -- run on `stream` WHILE the pass of update k streams, on the SMs the reserve
+// leaves free (raise the reserve with it: 144 sort CTAs on 2 SMs would take longer than the pass).
+// A step then costs the pass plus a kernel boundary instead of pass + ~50 us.  x and w of an update
+// must stay valid until `tail_stream` has passed it (the plain pipelined form frees them with `stream`).
+static int g_pipe_overlap = [] {
+    const char* env = getenv("CRICK_PIPE_OVERLAP");
+    return env ? (atoi(env) != 0) : 0;
+}();
+int crick_pipeline_overlap(int on) {
+    int prev = g_pipe_overlap;
+    if (on == 0 || on == 1) g_pipe_overlap = on;
+    return prev;
+}
+
 int crick_tdigest_update_pipelined(crick_tdigest_t* t, const double* x, const double* w, double w_scalar,
                                    int64_t n, void* stream, void* tail_stream) {
     if (!stream || !tail_stream || stream == tail_stream)
@@ -811,8 +831,22 @@ int crick_tdigest_update_pipelined(crick_tdigest_t* t, const double* x, const do
         if (e != cudaSuccess) return fail("update_pipelined: wait", e);
     }
     const int sms = sm_count() > 2 * g_pipe_reserve ? sm_count() - g_pipe_reserve : sm_count();
-    e = launch_parallel_pass(t->s.v, x, w, w_scalar, n, t->pipe_scratch[p], sms, st);
-    if (e == cudaSuccess) e = cudaEventRecord(t->ev_pass, st);
+    if (g_pipe_overlap) {
+        if (!t->pass_stream) {
+            e = cudaStreamCreateWithFlags(&t->pass_stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_prep, cudaEventDisableTiming);
+            if (e != cudaSuccess) return fail("update_pipelined: pass stream", e);
+        }
+        e = launch_parallel_prep(t->s.v, x, w, w_scalar, n, t->pipe_scratch[p], sms, st);
+        if (e == cudaSuccess) e = cudaEventRecord(t->ev_prep, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(t->pass_stream, t->ev_prep, 0);
+        if (e == cudaSuccess)
+            e = launch_parallel_accumulate(t->s.v, x, w, w_scalar, n, t->pipe_scratch[p], sms, t->pass_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(t->ev_pass, t->pass_stream);
+    } else {
+        e = launch_parallel_pass(t->s.v, x, w, w_scalar, n, t->pipe_scratch[p], sms, st);
+        if (e == cudaSuccess) e = cudaEventRecord(t->ev_pass, st);
+    }
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ts, t->ev_pass, 0);
     if (e == cudaSuccess) e = launch_parallel_tail(t->s.v, 0, t->pipe_scratch[p], sms, ts, w != nullptr);
     if (e == cudaSuccess) e = cudaEventRecord(t->ev_fin[p], ts);

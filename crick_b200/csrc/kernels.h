@@ -74,6 +74,10 @@ cudaError_t parallel_take_bad_weights(void* scratch, cudaStream_t st, int* bad);
 // cudaErrorInvalidValue = does not fit (compression too large): use the all-gather reducer.
 size_t p2p_rec_doubles(double comp);
 size_t p2p_buffer_bytes(double comp, int world);
+cudaError_t launch_parallel_prep(const BatchView& v, const double* X, const double* W, double wsc, long n,
+                                 void* scratch, int sm_count, cudaStream_t st);
+cudaError_t launch_parallel_accumulate(const BatchView& v, const double* X, const double* W, double wsc, long n,
+                                       void* scratch, int sm_count, cudaStream_t st);
 cudaError_t launch_parallel_pass(const BatchView& v, const double* X, const double* W, double wsc, long n,
                                  void* scratch, int sm_count, cudaStream_t st);
 cudaError_t launch_parallel_tail(const BatchView& v, long d, void* scratch, int sm_count, cudaStream_t st,

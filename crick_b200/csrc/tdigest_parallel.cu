@@ -2861,18 +2861,26 @@ size_t p2p_rec_doubles(double comp) { return 4 + 2 * (size_t)mmax_for(comp); }
 size_t p2p_buffer_bytes(double comp, int world) {
     return ((size_t)kP2PFlagDoubles + 2 * (size_t)world * p2p_rec_doubles(comp)) * sizeof(double);
 }
-// The two halves of launch_parallel_update for pipelined callers: everything up to and including the
-// streaming pass (reads X, W, writes only `scratch`), and the tail that folds the bucket sums into
-// the digest (deferred weight check when `checked`).
-cudaError_t launch_parallel_pass(const BatchView& v, const double* X, const double* W, double wsc, long n,
+// The pieces of launch_parallel_update for pipelined callers: sample -> edges (reads X, W, writes only
+// `scratch`), the streaming pass (the same), and the tail that folds the bucket sums into the digest
+// (deferred weight check when `checked`).
+cudaError_t launch_parallel_prep(const BatchView& v, const double* X, const double* W, double wsc, long n,
                                  void* scratch, int sm_count, cudaStream_t st) {
     ParLayout L = carve(scratch, v.comp, sm_count);
     long S = sample_len(n);
     const bool tails = S == kSMax && n >= kTailMinN && tail_sampling_enabled();
     SampleSrc src{X, W, wsc, n, L.hdr, tails ? L.tmin : nullptr, tails ? L.tmax : nullptr};
-    cudaError_t e = edges_from_sample(v, L, S, &src, st);
-    if (e != cudaSuccess) return e;
+    return edges_from_sample(v, L, S, &src, st);
+}
+cudaError_t launch_parallel_accumulate(const BatchView& v, const double* X, const double* W, double wsc, long n,
+                                       void* scratch, int sm_count, cudaStream_t st) {
     return accumulate_impl(v, X, W, wsc, n, scratch, sm_count, st, 0, nullptr, 0);
+}
+cudaError_t launch_parallel_pass(const BatchView& v, const double* X, const double* W, double wsc, long n,
+                                 void* scratch, int sm_count, cudaStream_t st) {
+    cudaError_t e = launch_parallel_prep(v, X, W, wsc, n, scratch, sm_count, st);
+    if (e != cudaSuccess) return e;
+    return launch_parallel_accumulate(v, X, W, wsc, n, scratch, sm_count, st);
 }
 cudaError_t launch_parallel_tail(const BatchView& v, long d, void* scratch, int sm_count, cudaStream_t st,
                                  bool checked) {

@@ -136,6 +136,12 @@ int crick_tdigest_update_pipelined(crick_tdigest_t *t, const double *x, const do
  * CRICK_PIPE_RESERVE; 0: same grid, hence bit-identical results, as the plain update).  Returns the
  * previous value; a negative argument only queries. */
 int crick_pipeline_reserve_sms(int n_sms);
+/* Overlapped sample phase for pipelined updates (default off, env CRICK_PIPE_OVERLAP=1): the streaming
+ * passes run back to back on a stream of the handle's own and the sample / edges kernels of the NEXT
+ * update run on `stream` while the current pass streams, on the reserved SMs (use a reserve of ~8
+ * with it).  x and w must then stay valid until `tail_stream` has passed the update.  Returns the
+ * previous setting; any argument other than 0 / 1 only queries. */
+int crick_pipeline_overlap(int on);
 /* ---- one stream sharded over the GPUs of a node: update + exchange + merge over peer memory -----
  * Every rank (one process per GPU) owns an exchange buffer of crick_p2p_buffer_bytes() bytes
  * (crick_p2p_alloc: plain cudaMalloc, zeroed), exports it with crick_ipc_get_handle (64 bytes, sent

@@ -19,6 +19,8 @@ lib.crick_device_synchronize()
 stream = torch.cuda.Stream(); sptr = stream.cuda_stream
 tail = torch.cuda.Stream(); tptr = tail.cuda_stream
 PIPE = os.environ.get("PIPE", "1") != "0"
+if "OVERLAP" in os.environ: lib.crick_pipeline_overlap(int(os.environ["OVERLAP"]))
+if "RESERVE" in os.environ: lib.crick_pipeline_reserve_sms(int(os.environ["RESERVE"]))
 red = TDigestAllReduce(100.0, exact=False)
 t = cb.TDigest(100, mode="parallel")
 def step():
@@ -43,7 +45,7 @@ lib.crick_profile_enable(0)
 kms, kn = ctypes.c_double(0), ctypes.c_int64(0)
 lib.crick_profile_collect(ctypes.addressof(kms), ctypes.addressof(kn))
 t.check_weights()
-print(json.dumps({"pipelined": PIPE, "n": n, "ms_per_step": ms, "kernel_ms": kms.value / kn.value, "fixed_us": 1e3 * (ms - kms.value / kn.value),
+print(json.dumps({"pipelined": PIPE, "overlap": lib.crick_pipeline_overlap(-1), "reserve": lib.crick_pipeline_reserve_sms(-1), "n": n, "ms_per_step": ms, "kernel_ms": kms.value / kn.value, "fixed_us": 1e3 * (ms - kms.value / kn.value),
                   "centroids": len(m.centroids()),
                   "centroids_md5": __import__("hashlib").md5(m.centroids().tobytes()).hexdigest()[:12]}), flush=True)
 import numpy as np
