@@ -127,6 +127,7 @@ def test_spsv_goldens(golden):
     assert [int(v) for v in got["count"]] == g["spsv_f8_bits"][1]
 
 
+@pytest.mark.gpu          # (no GPU needed: runs where oracle/_ref travels with the snapshot, i.e. the GPU tier)
 @needs_ref
 def test_restated_vs_reference_randomised():
     F = oracle.reference
@@ -159,6 +160,7 @@ def test_restated_vs_reference_randomised():
     assert A.scale(0.5).centroids().tobytes() == B.scale(0.5).centroids().tobytes()
 
 
+@pytest.mark.gpu
 @needs_ref
 def test_restated_stats_spsv_vs_reference():
     F = oracle.reference
