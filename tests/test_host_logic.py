@@ -75,3 +75,22 @@ def test_device_view_parses_cuda_array_interface():
 def test_device_view_ignores_cpu_dlpack():
     torch = pytest.importorskip("torch")
     assert device_view(torch.arange(4, dtype=torch.float64)) is None
+
+
+def test_nccl_comm_rejects_a_malformed_unique_id():
+    """NcclComm checks the 128-byte id before anything touches NCCL or a device."""
+    from crick_b200.distributed import NcclComm
+    with pytest.raises(ValueError):
+        NcclComm(b"short", 0, 1)
+
+
+def test_shard_bounds_cover_the_stream_exactly():
+    """Strong scaling shards ONE stream by contiguous ranges (bench.py): the ranges of
+    all ranks tile [0, n) without gaps or overlap, for world sizes that do not divide n as well."""
+    from crick_b200.distributed import shard_bounds
+    for n in (10**9, 10**9 + 7, 5, 0):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shard_bounds(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges) <= 1
