@@ -73,10 +73,17 @@ static cudaError_t need_smem(K kernel, size_t bytes) {
     return e;
 }
 
+// OFF by default since round 2 (CRICK_PDL=1 turns it on).  With programmatic launches a digest
+// updated on one stream while ANOTHER stream's kernels held SMs came out wrong (median 0.53 instead
+// of 1.0; tests/test_gpu_parallel.py::test_pipelined_updates_equal_plain_updates, 5 of 5 runs on one
+// box class, 0 of 3 with plain launches): k_finalize -- the secondary of a 148-CTA primary whose last
+// CTAs were still waiting for an SM -- read bucket rows of the previous update.  Alone on the GPU
+// (every primary CTA resident at once) the chain has never misbehaved, but a library whose handles
+// are meant to be driven from several streams cannot assume that.  Cost: ~10 us per update.
 static bool pdl_enabled() {
     static const bool on = [] {
         const char* env = getenv("CRICK_PDL");
-        return !(env && env[0] == '0');
+        return env && env[0] == '1';
     }();
     return on;
 }
