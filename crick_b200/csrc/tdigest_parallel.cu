@@ -47,11 +47,12 @@ namespace crick {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-// Programmatic dependent launch: the setup kernels of one update are a chain of short
-// dependent grids, so each is launched with cudaLaunchAttributeProgrammaticStreamSerialization --
-// it may be scheduled (and run its own prologue) while its predecessor in the stream is still
-// running, and executes grid_dep_wait() before it touches anything the predecessor wrote.
-// CRICK_PDL=0 falls back to plain launches.
+// Programmatic dependent launch (opt-in, CRICK_PDL=1; see pdl_enabled()): the setup kernels of one
+// update are a chain of short dependent grids, so each can be launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization -- it may be scheduled (and run its own
+// prologue) while its predecessor in the stream is still running, and executes grid_dep_wait()
+// before it touches anything the predecessor wrote.  With plain launches (the default) the two
+// instructions below are no-ops.
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
