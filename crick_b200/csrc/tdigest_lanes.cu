@@ -29,7 +29,10 @@
 // q1 < (1 + cos(pi/c)) / 2 -- beyond that K(q1) + 1 > c and no centroid can open.  The rounded chain
 // the reference evaluates differs from K by: q (1 ulp), 2q-1 (2^-53 absolute), asin (<= 2 ulp of
 // pi/2), three roundings of ~c, the subtraction: together < 2e-15 in units of the asin argument, and
-// qlim itself is computed to ~1e-15.  So ONCE PER CENTROID qlim -> [Wlo, Whi] = total (qlim -+ margin)
+// qlim itself is computed to ~1e-15 -- plus, for a boundary deep in a tail, the quantisation of
+// y1 = fl(2 q1 - 1) next to -+1 as seen through asin: <= 1.4e-17 / sqrt(q1 (1 - q1)), which the window
+// adds (x3.6) once that root is below 3.2e-4 (tests/test_window_decision.py attacks the window on the
+// CPU with the reference's arithmetic).  So ONCE PER CENTROID qlim -> [Wlo, Whi] = total (qlim -+ margin)
 // with margin = 6e-13 (>= 100x the bound), and per item only  Wc > Whi -> open,  Wc < Wlo -> fold;
 // a Wc inside the window evaluates the reference's own two kscale() and decides from them (counted
 // in g_exact_fallbacks).  Means and weights never depend on k, so the result is the same bits.
@@ -168,8 +171,14 @@ __global__ void __launch_bounds__(512, 1) k_ingest_lanes(BatchView v, long ngrou
                     q1 = fmin(q1, 1.0);
                     const double r = sqrt(q1 * (1.0 - q1));
                     const double qlim = q1 * kC + kH + r * kS;
-                    Wlo = total * (qlim - margin);
-                    Whi = q1 > kQtop - margin ? INFINITY : total * (qlim + margin);
+                    // k1 is evaluated by the reference at y1 = fl(2 q1 - 1), quantised to 2^-53 next
+                    // to -1: in the asin argument that is an error of 2^-54 / cos(theta1) with
+                    // cos(theta1) = 2 r, i.e. <= 1.4e-17 / r in qlim -- beyond the margin once
+                    // q1 < ~5e-10 (a boundary behind 1e-9 of the total weight).  Widen the window there.
+                    double m_ = margin;
+                    if (r < 3.2e-4 && r > 0.0) m_ += 5e-17 / r;
+                    Wlo = total * (qlim - m_);
+                    Whi = q1 > kQtop - margin ? INFINITY : total * (qlim + m_);
                     if (q1 > kQtop - margin) Wlo = total * (1.0 - 16.0 * margin - 1e-11);   // no centroid can open beyond
                 };
                 if (CHEAP) set_window(0.0);
